@@ -1,0 +1,923 @@
+// kexp_api.cu -- host side of libkexp.so: C ABI (include/kexp.h), operator upload,
+// batched PCG mass solve driver, Chebyshev term loop captured as one CUDA graph,
+// device-resident batches, statistics.  Kernels: kexp_kernels.cuh.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <cmath>
+#include "kexp_internal.h"
+
+using namespace kexp;
+
+namespace kexp {
+
+int fail(kexp_ctx* ctx, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return 1;
+}
+
+int pick_W(int B) {
+    int W = 2;
+    while (W < B && W < kMaxW) W <<= 1;
+    return W;
+}
+
+void free_csr(DevCsr& d) {
+    cudaFree(d.rowptr); cudaFree(d.col); cudaFree(d.val);
+    d = DevCsr();
+}
+
+int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v) {
+    free_csr(d);
+    d.nrows = nrows; d.ncols = ncols;
+    if (nrows == 0 || rp == nullptr) { d.nrows = 0; return 0; }
+    d.nnz = rp[nrows];
+    for (int64_t k = 0; k < d.nnz; ++k)
+        if (ci[k] < 0 || ci[k] >= ncols) return fail(ctx, "CSR column index out of range");
+    KEXP_CUDA(cudaMalloc(&d.rowptr, sizeof(int) * (size_t)(nrows + 1)));
+    KEXP_CUDA(cudaMalloc(&d.col, sizeof(int) * (size_t)std::max<int64_t>(d.nnz, 1)));
+    KEXP_CUDA(cudaMalloc(&d.val, sizeof(double) * (size_t)std::max<int64_t>(d.nnz, 1)));
+    KEXP_CUDA(cudaMemcpy(d.rowptr, rp, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice));
+    KEXP_CUDA(cudaMemcpy(d.col, ci, sizeof(int) * (size_t)d.nnz, cudaMemcpyHostToDevice));
+    KEXP_CUDA(cudaMemcpy(d.val, v, sizeof(double) * (size_t)d.nnz, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace kexp
+
+// ------------------------------------------------------------------ launch plumbing
+namespace {
+
+struct CaptureStats { int64_t launches = 0; };
+
+template <typename K>
+int max_grid(kexp_ctx* ctx, K kernel) {
+    const void* key = (const void*)kernel;
+    auto it = ctx->occ_cache.find(key);
+    if (it != ctx->occ_cache.end()) return it->second;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0);
+    occ = std::max(1, std::min(occ, 8));
+    int g = occ * ctx->num_sms;
+    ctx->occ_cache[key] = g;
+    return g;
+}
+
+inline int blocks_for(int64_t groups, int lpr) {   // blocks needed so every group has one thread set
+    int64_t per_block = kThreads / lpr;
+    return (int)std::max<int64_t>(1, (groups + per_block - 1) / per_block);
+}
+
+cudaEvent_t next_event(kexp_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+struct TimedLaunch {   // RAII: event pair around one launch when kernel timing is on
+    kexp_ctx* ctx; int cls;
+    TimedLaunch(kexp_ctx* c, int k) : ctx(c), cls(k) {
+        ctx->st_launches++;
+        if (ctx->timing) {
+            int idx = (int)ctx->ev_used;
+            cudaEventRecord(next_event(ctx), ctx->stream);
+            ctx->ev_pending.push_back({cls, idx});
+        }
+    }
+    ~TimedLaunch() {
+        if (ctx->timing) cudaEventRecord(next_event(ctx), ctx->stream);
+    }
+};
+
+void drain_events(kexp_ctx* ctx) {
+    if (!ctx->timing) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& pr : ctx->ev_pending) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev_pool[pr.second], ctx->ev_pool[pr.second + 1]);
+        ctx->cls[pr.first].ms += ms;
+        ctx->cls[pr.first].launches++;
+    }
+    ctx->ev_pending.clear();
+    ctx->ev_used = 0;
+}
+
+int ensure_panels(kexp_ctx* ctx, int W) {
+    if (W <= ctx->curW) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
+    ctx->graphs.clear();
+    double** bufs[] = {&ctx->S0, &ctx->S1, &ctx->Y, &ctx->T, &ctx->X, &ctx->P, &ctx->Q};
+    for (auto b : bufs) { cudaFree(*b); *b = nullptr; }
+    const size_t full = sizeof(double) * (size_t)ctx->n * W, part = sizeof(double) * (size_t)std::max<int64_t>(ctx->n_s, 1) * W;
+    KEXP_CUDA(cudaMalloc(&ctx->S0, full));
+    KEXP_CUDA(cudaMalloc(&ctx->S1, full));
+    KEXP_CUDA(cudaMalloc(&ctx->Y, full));
+    KEXP_CUDA(cudaMalloc(&ctx->T, full));
+    KEXP_CUDA(cudaMalloc(&ctx->X, part));
+    KEXP_CUDA(cudaMalloc(&ctx->P, part));
+    KEXP_CUDA(cudaMalloc(&ctx->Q, part));
+    ctx->curW = W;
+    return 0;
+}
+
+int ensure_stage(kexp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->stage_bytes) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr; ctx->stage_bytes = 0;
+    KEXP_CUDA(cudaMalloc(&ctx->d_stage, bytes));
+    ctx->stage_bytes = bytes;
+    return 0;
+}
+
+// ---- one batched application of M^-1 K on the work panels: input `in` (n x W),
+// leaves T (rows needing no solve), X (solved rows). W is a template parameter.
+template <int W>
+void enqueue_operator(kexp_ctx* ctx, const double* in) {
+    constexpr int LPR = W / 2, RPW = 32 / LPR;
+    cudaStream_t s = ctx->stream;
+    const int n = (int)ctx->n, ns = (int)ctx->n_s;
+    {   // T = Kt * in
+        auto k = spmm_kernel<W, 0>;
+        int grid = std::min(max_grid(ctx, k), std::max(1, (n + RPW * 8 - 1) / (RPW * 8)));
+        TimedLaunch tl(ctx, KC_SPMM_K);
+        k<<<grid, kThreads, 0, s>>>(ctx->Kt.rowptr, ctx->Kt.col, ctx->Kt.val, in, ctx->T, n, nullptr, nullptr, nullptr);
+    }
+    const int ntri = ns / 3;
+    {
+        auto k = cg_init_kernel<W>;
+        int grid = std::min(max_grid(ctx, k), blocks_for(ntri, LPR));
+        TimedLaunch tl(ctx, KC_CG_INIT);
+        k<<<grid, kThreads, 0, s>>>(ctx->T, ctx->X, ctx->P, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+    }
+    for (int it = 0; it < ctx->max_it; ++it) {
+        {
+            auto k = spmm_kernel<W, 1>;
+            int grid = std::min(max_grid(ctx, k), std::max(1, (ns + RPW * 8 - 1) / (RPW * 8)));
+            TimedLaunch tl(ctx, KC_SPMM_CG);
+            k<<<grid, kThreads, 0, s>>>(ctx->As.rowptr, ctx->As.col, ctx->As.val, ctx->P, ctx->Q, ns, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+        }
+        {
+            auto k = cg_update_xr_kernel<W>;
+            int grid = std::min(max_grid(ctx, k), blocks_for(ntri, LPR));
+            TimedLaunch tl(ctx, KC_CG_XR);
+            k<<<grid, kThreads, 0, s>>>(ctx->X, ctx->T, ctx->P, ctx->Q, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+        }
+        {
+            auto k = cg_update_p_kernel<W>;
+            int grid = std::min(max_grid(ctx, k), blocks_for(ntri, LPR));
+            TimedLaunch tl(ctx, KC_CG_P);
+            k<<<grid, kThreads, 0, s>>>(ctx->T, ctx->P, ctx->d_Pinv, ntri, ctx->d_sc);
+        }
+    }
+    ctx->st_op_apps++;
+}
+
+template <int W>
+void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep st) {
+    constexpr int LPR = W / 2;
+    cudaStream_t s = ctx->stream;
+    const int ns = (int)ctx->n_s, nb = (int)ctx->n_b, nd = (int)ctx->n_d;
+    {
+        auto k = cheb_update_kernel<W, 0>;
+        int grid = std::min(max_grid(ctx, k), blocks_for(ns, LPR));
+        TimedLaunch tl(ctx, KC_CHEB);
+        k<<<grid, kThreads, 0, s>>>(ctx->X, nullptr, nullptr, nullptr, nullptr, nullptr, S, ctx->Y, ns, coef, ctx->d_tscale, st);
+    }
+    if (nb > 0) {
+        auto k = cheb_update_kernel<W, 1>;
+        int grid = std::min(max_grid(ctx, k), blocks_for(nb, LPR));
+        const size_t o = (size_t)ns * W;
+        TimedLaunch tl(ctx, KC_CHEB);
+        k<<<grid, kThreads, 0, s>>>(ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, S + o, ctx->Y + o, nb, coef, ctx->d_tscale, st);
+    }
+    if (nd > 0) {
+        const size_t o = (size_t)(ns + nb) * W;
+        TimedLaunch tl(ctx, KC_CHEB);
+        if (ctx->d_Dblk) {
+            auto k = cheb_update_kernel<W, 2>;
+            int grid = std::min(max_grid(ctx, k), blocks_for(nd / 3, LPR));
+            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st);
+        } else {
+            auto k = cheb_update_kernel<W, 0>;
+            int grid = std::min(max_grid(ctx, k), blocks_for(nd, LPR));
+            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st);
+        }
+    }
+}
+
+template <int W>
+void enqueue_op_finish(kexp_ctx* ctx, double* out) {
+    constexpr int LPR = W / 2;
+    cudaStream_t s = ctx->stream;
+    const int ns = (int)ctx->n_s, nb = (int)ctx->n_b, nd = (int)ctx->n_d;
+    {
+        TimedLaunch tl(ctx, KC_MISC);
+        op_finish_kernel<W, 0><<<std::min(4 * ctx->num_sms, blocks_for(ns, LPR)), kThreads, 0, s>>>(ctx->X, nullptr, nullptr, nullptr, nullptr, nullptr, out, ns);
+    }
+    if (nb > 0) {
+        const size_t o = (size_t)ns * W;
+        TimedLaunch tl(ctx, KC_MISC);
+        op_finish_kernel<W, 1><<<std::min(4 * ctx->num_sms, blocks_for(nb, LPR)), kThreads, 0, s>>>(ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, out + o, nb);
+    }
+    if (nd > 0) {
+        const size_t o = (size_t)(ns + nb) * W;
+        TimedLaunch tl(ctx, KC_MISC);
+        if (ctx->d_Dblk)
+            op_finish_kernel<W, 2><<<std::min(4 * ctx->num_sms, blocks_for(nd / 3, LPR)), kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, out + o, nd);
+        else
+            op_finish_kernel<W, 0><<<std::min(4 * ctx->num_sms, blocks_for(nd, LPR)), kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, out + o, nd);
+    }
+}
+
+// The whole cheby_exp.apply for one panel: S0 holds the input, Y receives the result.
+template <int W>
+void enqueue_cheby(kexp_ctx* ctx, int id) {
+    const ChebTable& tb = ctx->cheb[id];
+    const size_t nelem2 = (size_t)ctx->n * W / 2;
+    {
+        TimedLaunch tl(ctx, KC_CHEB);
+        int grid = (int)std::min<size_t>((size_t)8 * ctx->num_sms, (nelem2 + kThreads - 1) / kThreads);
+        cheb_init_kernel<W><<<std::max(grid, 1), kThreads, 0, ctx->stream>>>(ctx->S0, ctx->Y, nelem2, tb.d_coef);
+    }
+    for (int n = 1; n <= tb.ncheb; ++n) {
+        const double* in = (n & 1) ? ctx->S0 : ctx->S1;     // S_{n-1}
+        double* Sn = (n & 1) ? ctx->S1 : ctx->S0;           // holds S_{n-2}, becomes S_n
+        enqueue_operator<W>(ctx, in);
+        ChebStep st;
+        st.n = n; st.has_old = (n >= 2) ? 1 : 0; st.cs = (n == 1) ? 1.0 : 2.0;
+        enqueue_cheb_update<W>(ctx, Sn, tb.d_coef, st);
+    }
+}
+
+#define DISPATCH_W(W, CALL)                  \
+    switch (W) {                             \
+        case 2: { constexpr int kW = 2; CALL; } break;   \
+        case 4: { constexpr int kW = 4; CALL; } break;   \
+        case 8: { constexpr int kW = 8; CALL; } break;   \
+        case 16: { constexpr int kW = 16; CALL; } break; \
+        case 32: { constexpr int kW = 32; CALL; } break; \
+        case 64: { constexpr int kW = 64; CALL; } break; \
+        default: return kexp::fail(ctx, "unsupported panel width"); \
+    }
+
+int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
+    if (ctx->timing || !ctx->use_graph) {
+        DISPATCH_W(W, enqueue_cheby<kW>(ctx, id));
+        KEXP_CUDA(cudaGetLastError());
+        return 0;
+    }
+    auto key = std::make_pair(id, W);
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+        // warm the occupancy cache outside capture
+        cudaGraph_t graph;
+        int64_t l0 = ctx->st_launches, a0 = ctx->st_op_apps;
+        KEXP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        DISPATCH_W(W, enqueue_cheby<kW>(ctx, id));
+        KEXP_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+        ctx->st_launches = l0; ctx->st_op_apps = a0;     // counted per replay below
+        cudaGraphExec_t exec;
+        KEXP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = ctx->graphs.emplace(key, exec).first;
+    }
+    KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
+    const ChebTable& tb = ctx->cheb[id];
+    ctx->st_op_apps += tb.ncheb;
+    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + 3 * ctx->max_it + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
+    return 0;
+}
+
+void invalidate_graphs(kexp_ctx* ctx) {
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
+    ctx->graphs.clear();
+}
+
+// occupancy queries must not happen during capture: touch every kernel once
+template <int W>
+void warm_occupancy(kexp_ctx* ctx) {
+    max_grid(ctx, spmm_kernel<W, 0>); max_grid(ctx, spmm_kernel<W, 1>);
+    max_grid(ctx, cg_init_kernel<W>); max_grid(ctx, cg_update_xr_kernel<W>); max_grid(ctx, cg_update_p_kernel<W>);
+    max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
+}
+
+int set_tscale(kexp_ctx* ctx, int id, const double* t, int col0, int B, int W) {
+    const double L = ctx->cheb[id].L;
+    cudaStreamSynchronize(ctx->stream);        // h_pin reuse
+    for (int k = 0; k < kMaxW; ++k) ctx->h_pin[k] = (k < W && col0 + k < B) ? t[col0 + k] / L : 0.0;
+    KEXP_CUDA(cudaMemcpyAsync(ctx->d_tscale, ctx->h_pin, sizeof(double) * kMaxW, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int check_ready(kexp_ctx* ctx, int id) {
+    if (!ctx) return 1;
+    if (!ctx->have_op) return kexp::fail(ctx, "operator not set (kexp_set_operator)");
+    if (id < 0 || id >= KEXP_MAX_CHEBY || ctx->cheb[id].ncheb < 0) return kexp::fail(ctx, "Chebyshev table not set (kexp_set_cheby)");
+    return 0;
+}
+
+template <int W>
+void launch_pack(kexp_ctx* ctx, const double* d_src, int64_t ld, int shared_x, int B, int col0, double* dst) {
+    dim3 blk(32, 8);
+    int grid = (int)((ctx->n + 31) / 32);
+    pack_kernel<W><<<grid, blk, 0, ctx->stream>>>(d_src, ld, shared_x, B, col0, ctx->d_perm, dst, (int)ctx->n);
+}
+
+template <int W>
+void launch_unpack(kexp_ctx* ctx, const double* src, double* d_dst, int64_t ld, int B, int col0) {
+    dim3 blk(32, 8);
+    int grid = (int)((ctx->n + 31) / 32);
+    unpack_kernel<W><<<grid, blk, 0, ctx->stream>>>(src, ctx->d_perm, (int)ctx->n, d_dst, ld, B, col0);
+}
+
+template <int W>
+void launch_colsum(kexp_ctx* ctx, const double* Ypanel, double* v_dev, int accumulate) {
+    int grid = std::min(8 * ctx->num_sms, blocks_for(ctx->n, W / 2));
+    weighted_colsum_kernel<W><<<grid, kThreads, 0, ctx->stream>>>(Ypanel, ctx->d_w, ctx->d_perm, (int)ctx->n, v_dev, accumulate);
+}
+
+template <int W>
+void launch_spmm_K(kexp_ctx* ctx, const double* in, double* out) {
+    constexpr int RPW = 32 / (W / 2);
+    const int n = (int)ctx->n;
+    auto k = spmm_kernel<W, 0>;
+    int grid = std::min(max_grid(ctx, k), std::max(1, (n + RPW * 8 - 1) / (RPW * 8)));
+    k<<<grid, kThreads, 0, ctx->stream>>>(ctx->Kt.rowptr, ctx->Kt.col, ctx->Kt.val, in, out, n, nullptr, nullptr, nullptr);
+}
+
+template <int W>
+void launch_operator_full(kexp_ctx* ctx, const double* in, double* out) {
+    enqueue_operator<W>(ctx, in);
+    enqueue_op_finish<W>(ctx, out);
+}
+
+int pack_panel(kexp_ctx* ctx, const double* d_src, int64_t ld, int shared_x, int B, int col0, int W, double* dst) {
+    TimedLaunch tl(ctx, KC_MISC);
+    DISPATCH_W(W, launch_pack<kW>(ctx, d_src, ld, shared_x, B, col0, dst));
+    return 0;
+}
+
+int unpack_panel(kexp_ctx* ctx, const double* src, double* d_dst, int64_t ld, int B, int col0, int W) {
+    TimedLaunch tl(ctx, KC_MISC);
+    DISPATCH_W(W, launch_unpack<kW>(ctx, src, d_dst, ld, B, col0));
+    return 0;
+}
+
+int colsum_panel(kexp_ctx* ctx, const double* Ypanel, const double* w, int col0, int B, int W, double* v_dev, int accumulate) {
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < kMaxW; ++k) ctx->h_pin[kMaxW + k] = (k < W && col0 + k < B) ? w[col0 + k] : 0.0;
+    KEXP_CUDA(cudaMemcpyAsync(ctx->d_w, ctx->h_pin + kMaxW, sizeof(double) * kMaxW, cudaMemcpyHostToDevice, ctx->stream));
+    TimedLaunch tl(ctx, KC_MISC);
+    DISPATCH_W(W, launch_colsum<kW>(ctx, Ypanel, v_dev, accumulate));
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* kexp_version(void) { return "kexp-b200 0.1 (sm_100a)"; }
+
+const char* kexp_last_error(kexp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int kexp_create(kexp_ctx** out, int device) {
+    if (!out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "kexp_create: no CUDA device (this library has no CPU path)\n");
+        return 2;
+    }
+    if (device < 0 || device >= ndev) return 3;
+    if (cudaSetDevice(device) != cudaSuccess) return 4;
+    kexp_ctx* ctx = new kexp_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        fprintf(stderr, "kexp_create: device %d is sm_%d%d; this build targets sm_100a (B200)\n", device, prop.major, prop.minor);
+        delete ctx;
+        return 5;
+    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_sc, sizeof(CgScalars)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_sc, 0, sizeof(CgScalars)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_partials, sizeof(double) * 2 * 8 * (size_t)ctx->num_sms * kMaxW) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counter, sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_counter, 0, sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_tscale, sizeof(double) * kMaxW) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_w, sizeof(double) * kMaxW) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_pin, sizeof(double) * 2 * kMaxW) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
+    if (!ok) { kexp_destroy(ctx); return 6; }
+    const char* g = getenv("KEXP_NO_GRAPH");
+    if (g && g[0] == '1') ctx->use_graph = false;
+    if (kexp_set_mass_solver(ctx, 1e-12, 60, 3)) { kexp_destroy(ctx); return 7; }
+    *out = ctx;
+    return 0;
+}
+
+int kexp_destroy(kexp_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
+    kexp::krylov_free(ctx);
+    free_csr(ctx->Kt); free_csr(ctx->As); free_csr(ctx->Rt);
+    double* bufs[] = {ctx->S0, ctx->S1, ctx->Y, ctx->T, ctx->X, ctx->P, ctx->Q, ctx->d_Dblk, ctx->d_Pinv,
+                      ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_v};
+    for (double* b : bufs) cudaFree(b);
+    cudaFree(ctx->d_perm); cudaFree(ctx->d_sc); cudaFree(ctx->d_counter);
+    for (int i = 0; i < KEXP_MAX_CHEBY; ++i) cudaFree(ctx->cheb[i].d_coef);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->nccl_comm && ctx->nccl_lib) {
+        typedef int (*destroy_t)(void*);
+        destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+        if (f) f(ctx->nccl_comm);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+static int build_block_jacobi(kexp_ctx* ctx, int64_t n_s, const int32_t* rp, const int32_t* ci, const double* v,
+                              int precond, std::vector<double>& Pinv) {
+    if (n_s % 3 != 0) return kexp::fail(ctx, "mass system size must be a multiple of 3 (BDM2 entity blocks)");
+    const int64_t nb = n_s / 3;
+    Pinv.assign((size_t)nb * 9, 0.0);
+    for (int64_t b = 0; b < nb; ++b) {
+        double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int i = 0; i < 3; ++i) {
+            const int64_t r = 3 * b + i;
+            for (int k = rp[r]; k < rp[r + 1]; ++k) {
+                const int64_t c = ci[k];
+                if (c >= 3 * b && c < 3 * b + 3 && (precond == 3 || c == r)) A[i][c - 3 * b] += v[k];
+            }
+        }
+        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        if (!(std::fabs(det) > 0.0)) return kexp::fail(ctx, "singular diagonal block in the mass matrix");
+        double* P = &Pinv[(size_t)b * 9];
+        P[0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det;
+        P[1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / det;
+        P[2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
+        P[3] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / det;
+        P[4] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det;
+        P[5] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / det;
+        P[6] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det;
+        P[7] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det;
+        P[8] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+    }
+    return 0;
+}
+
+int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
+                           const int32_t* Kt_rowptr, const int32_t* Kt_col, const double* Kt_val,
+                           const int32_t* As_rowptr, const int32_t* As_col, const double* As_val,
+                           const int32_t* Rt_rowptr, const int32_t* Rt_col, const double* Rt_val,
+                           const double* Dblk, const double* Pinv_blocks, const int32_t* perm) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (n <= 0 || n_s <= 0 || n_b < 0 || n_s + n_b > n) return kexp::fail(ctx, "bad operator plan sizes");
+    if (n_s % 3) return kexp::fail(ctx, "n_s must be a multiple of 3");
+    if (n >= (int64_t)1 << 31) return kexp::fail(ctx, "n too large for 32-bit row indices");
+    if (!Kt_rowptr || !As_rowptr) return kexp::fail(ctx, "null matrix");
+    const int64_t n_d = n - n_s - n_b;
+    if (Dblk && n_d % 3) return kexp::fail(ctx, "block rows must be a multiple of 3");
+    if (n_b > 0 && !Rt_rowptr) return kexp::fail(ctx, "back-substitution matrix missing");
+    invalidate_graphs(ctx);
+    ctx->have_op = false;
+    ctx->n = n; ctx->n_s = n_s; ctx->n_b = n_b; ctx->n_d = n_d;
+    ctx->curW = 0;   // panels are re-allocated for the new size
+    if (upload_csr(ctx, ctx->Kt, (int)n, (int)n, Kt_rowptr, Kt_col, Kt_val)) return 1;
+    if (upload_csr(ctx, ctx->As, (int)n_s, (int)n_s, As_rowptr, As_col, As_val)) return 1;
+    if (upload_csr(ctx, ctx->Rt, (int)n_b, (int)n_s, n_b ? Rt_rowptr : nullptr, Rt_col, Rt_val)) return 1;
+    ctx->h_As_rowptr.assign(As_rowptr, As_rowptr + n_s + 1);
+    ctx->h_As_col.assign(As_col, As_col + As_rowptr[n_s]);
+    ctx->h_As_val.assign(As_val, As_val + As_rowptr[n_s]);
+    cudaFree(ctx->d_Dblk); ctx->d_Dblk = nullptr;
+    if (Dblk && n_d > 0) {
+        KEXP_CUDA(cudaMalloc(&ctx->d_Dblk, sizeof(double) * 3 * (size_t)n_d));
+        KEXP_CUDA(cudaMemcpy(ctx->d_Dblk, Dblk, sizeof(double) * 3 * (size_t)n_d, cudaMemcpyHostToDevice));
+    }
+    std::vector<double> Pinv;
+    const double* P = Pinv_blocks;
+    if (!P) {
+        if (build_block_jacobi(ctx, n_s, As_rowptr, As_col, As_val, ctx->precond, Pinv)) return 1;
+        P = Pinv.data();
+    }
+    cudaFree(ctx->d_Pinv); ctx->d_Pinv = nullptr;
+    KEXP_CUDA(cudaMalloc(&ctx->d_Pinv, sizeof(double) * 3 * (size_t)n_s));
+    KEXP_CUDA(cudaMemcpy(ctx->d_Pinv, P, sizeof(double) * 3 * (size_t)n_s, cudaMemcpyHostToDevice));
+    cudaFree(ctx->d_perm); ctx->d_perm = nullptr;
+    if (perm) {
+        std::vector<char> seen((size_t)n, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            if (perm[i] < 0 || perm[i] >= n || seen[perm[i]]) return kexp::fail(ctx, "perm is not a permutation");
+            seen[perm[i]] = 1;
+        }
+        KEXP_CUDA(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t)n));
+        KEXP_CUDA(cudaMemcpy(ctx->d_perm, perm, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    cudaFree(ctx->d_v); ctx->d_v = nullptr;
+    KEXP_CUDA(cudaMalloc(&ctx->d_v, sizeof(double) * (size_t)n));
+    ctx->have_op = true;
+    return 0;
+}
+
+int kexp_set_operator(kexp_ctx* ctx, int64_t n_u, int64_t n_eta,
+                      const int32_t* K_rowptr, const int32_t* K_col, const double* K_val,
+                      const int32_t* Mu_rowptr, const int32_t* Mu_col, const double* Mu_val,
+                      const double* Meta_inv_blocks, int64_t n_cells) {
+    if (!ctx) return 1;
+    if (n_eta != 3 * n_cells) return kexp::fail(ctx, "n_eta must equal 3*n_cells (DG1)");
+    if (!Meta_inv_blocks) return kexp::fail(ctx, "Meta_inv_blocks is null");
+    return kexp_set_operator_plan(ctx, n_u + n_eta, n_u, 0, K_rowptr, K_col, K_val, Mu_rowptr, Mu_col, Mu_val,
+                                  nullptr, nullptr, nullptr, Meta_inv_blocks, nullptr, nullptr);
+}
+
+int kexp_set_mass_solver(kexp_ctx* ctx, double rtol, int max_it, int precond) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (!(rtol > 0.0) || max_it < 1 || (precond != 1 && precond != 3)) return kexp::fail(ctx, "bad mass solver parameters");
+    invalidate_graphs(ctx);
+    const bool rebuild = ctx->have_op && precond != ctx->precond;
+    ctx->rtol = rtol; ctx->max_it = max_it; ctx->precond = precond;
+    if (rebuild) {
+        std::vector<double> Pinv;
+        if (build_block_jacobi(ctx, ctx->n_s, ctx->h_As_rowptr.data(), ctx->h_As_col.data(), ctx->h_As_val.data(), precond, Pinv)) return 1;
+        KEXP_CUDA(cudaMemcpy(ctx->d_Pinv, Pinv.data(), sizeof(double) * Pinv.size(), cudaMemcpyHostToDevice));
+    }
+    const double r2 = rtol * rtol;
+    KEXP_CUDA(cudaMemcpy(&ctx->d_sc->rtol2, &r2, sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int kexp_set_cheby(kexp_ctx* ctx, int id, const double* a, int ncheb, double L) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (id < 0 || id >= KEXP_MAX_CHEBY) return kexp::fail(ctx, "cheby id out of range");
+    if (!a || ncheb < 0 || !(L > 0.0)) return kexp::fail(ctx, "bad Chebyshev table");
+    invalidate_graphs(ctx);
+    ChebTable& tb = ctx->cheb[id];
+    cudaFree(tb.d_coef); tb.d_coef = nullptr;
+    KEXP_CUDA(cudaMalloc(&tb.d_coef, sizeof(double) * (size_t)(ncheb + 1)));
+    KEXP_CUDA(cudaMemcpy(tb.d_coef, a, sizeof(double) * (size_t)(ncheb + 1), cudaMemcpyHostToDevice));
+    tb.ncheb = ncheb; tb.L = L;
+    return 0;
+}
+
+// ------------------------------------------------------------------ batches
+int kexp_batch_create(kexp_ctx* ctx, int B, kexp_batch** out) {
+    if (!ctx || !out) return 1;
+    cudaSetDevice(ctx->device);
+    if (!ctx->have_op) return kexp::fail(ctx, "operator not set");
+    if (B < 1) return kexp::fail(ctx, "B must be >= 1");
+    kexp_batch* b = new kexp_batch();
+    b->ctx = ctx; b->B = B;
+    for (int c0 = 0; c0 < B; c0 += kMaxW) {
+        const int W = pick_W(std::min(B - c0, kMaxW));
+        double* p = nullptr;
+        if (cudaMalloc(&p, sizeof(double) * (size_t)ctx->n * W) != cudaSuccess) {
+            kexp_batch_destroy(b);
+            return kexp::fail(ctx, "out of device memory for batch");
+        }
+        b->panelW.push_back(W); b->panel.push_back(p);
+    }
+    *out = b;
+    return 0;
+}
+
+int kexp_batch_destroy(kexp_batch* b) {
+    if (!b) return 0;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    for (double* p : b->panel) cudaFree(p);
+    delete b;
+    return 0;
+}
+
+int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared) {
+    if (!b || !X) return 1;
+    kexp_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    const int nvec = x_is_shared ? 1 : b->B;
+    if (!x_is_shared && ldx < ctx->n) return kexp::fail(ctx, "ldx < n");
+    if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * nvec)) return 1;
+    KEXP_CUDA(cudaMemcpy2DAsync(ctx->d_stage, sizeof(double) * ctx->n, X, sizeof(double) * (x_is_shared ? ctx->n : ldx),
+                                sizeof(double) * ctx->n, nvec, cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t p = 0; p < b->panel.size(); ++p)
+        if (pack_panel(ctx, ctx->d_stage, ctx->n, x_is_shared, b->B, (int)p * kMaxW, b->panelW[p], b->panel[p])) return 1;
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
+    if (!b || !Y) return 1;
+    kexp_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    if (ldy < ctx->n) return kexp::fail(ctx, "ldy < n");
+    if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
+    for (size_t p = 0; p < b->panel.size(); ++p)
+        if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * kMaxW, b->panelW[p])) return 1;
+    KEXP_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, ctx->d_stage, sizeof(double) * ctx->n, sizeof(double) * ctx->n, b->B,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
+    if (check_ready(ctx, id)) return 1;
+    if (!in || !out || !t) return kexp::fail(ctx, "null argument");
+    if (in == out) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
+    if (in->B != out->B) return kexp::fail(ctx, "batch sizes differ");
+    cudaSetDevice(ctx->device);
+    int maxW = 0;
+    for (int W : in->panelW) maxW = std::max(maxW, W);
+    if (ensure_panels(ctx, maxW)) return 1;
+    for (int W : in->panelW) DISPATCH_W(W, warm_occupancy<kW>(ctx));
+    if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    for (size_t p = 0; p < in->panel.size(); ++p) {
+        const int W = in->panelW[p];
+        const size_t bytes = sizeof(double) * (size_t)ctx->n * W;
+        if (set_tscale(ctx, id, t, (int)p * kMaxW, in->B, W)) return 1;
+        KEXP_CUDA(cudaMemcpyAsync(ctx->S0, in->panel[p], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (run_cheby_panel(ctx, id, W)) return 1;
+        KEXP_CUDA(cudaMemcpyAsync(out->panel[p], ctx->Y, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    return 0;
+}
+
+int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t) {
+    if (!ctx) return 1;
+    if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
+    if (ctx->timing) drain_events(ctx);
+    return 0;
+}
+
+int kexp_synchronize(kexp_ctx* ctx) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    KEXP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kexp_last_device_ms(kexp_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return 1;
+    cudaSetDevice(ctx->device);
+    KEXP_CUDA(cudaEventSynchronize(ctx->ev_b));
+    float f = 0.f;
+    KEXP_CUDA(cudaEventElapsedTime(&f, ctx->ev_a, ctx->ev_b));
+    *ms = f;
+    return 0;
+}
+
+int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev) {
+    if (!b || !w || !v_dev) return 1;
+    kexp_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    for (size_t p = 0; p < b->panel.size(); ++p)
+        if (colsum_panel(ctx, b->panel[p], w, (int)p * kMaxW, b->B, b->panelW[p], v_dev, p > 0)) return 1;
+    return 0;
+}
+
+int kexp_cheby_apply_batch(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
+                           double* Y, int64_t ldy, const double* t, int B) {
+    if (check_ready(ctx, id)) return 1;
+    if (!X || !Y || !t || B < 1) return kexp::fail(ctx, "bad arguments");
+    if (X == Y) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
+    kexp_batch *bi = nullptr, *bo = nullptr;
+    int rc = kexp_batch_create(ctx, B, &bi);
+    if (!rc) rc = kexp_batch_create(ctx, B, &bo);
+    if (!rc) rc = kexp_batch_upload(bi, X, ldx, x_is_shared);
+    if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
+    if (!rc) rc = kexp_batch_download(bo, Y, ldy);
+    kexp_batch_destroy(bi);
+    kexp_batch_destroy(bo);
+    return rc;
+}
+
+int kexp_cheby_apply(kexp_ctx* ctx, int id, const double* x, double* y, double t) {
+    if (!ctx) return 1;
+    return kexp_cheby_apply_batch(ctx, id, x, ctx->n, 0, y, ctx->n, &t, 1);
+}
+
+int kexp_allreduce_sum_dev(kexp_ctx* ctx, double* v_dev, int64_t count);
+
+int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
+                             const double* t, const double* w, int B, double* v_out, int do_allreduce) {
+    if (check_ready(ctx, id)) return 1;
+    if (!X || !t || !w || !v_out || B < 1) return kexp::fail(ctx, "bad arguments");
+    kexp_batch *bi = nullptr, *bo = nullptr;
+    int rc = kexp_batch_create(ctx, B, &bi);
+    if (!rc) rc = kexp_batch_create(ctx, B, &bo);
+    if (!rc) rc = kexp_batch_upload(bi, X, ldx, x_is_shared);
+    if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
+    if (!rc) rc = kexp_batch_average_dev(bo, w, ctx->d_v);
+    if (!rc && do_allreduce) rc = kexp_allreduce_sum_dev(ctx, ctx->d_v, ctx->n);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(v_out, ctx->d_v, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = kexp::fail(ctx, cudaGetErrorString(e));
+    }
+    kexp_batch_destroy(bi);
+    kexp_batch_destroy(bo);
+    return rc;
+}
+
+int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
+    if (!ctx) return 1;
+    if (!ctx->have_op) return kexp::fail(ctx, "operator not set");
+    if (!in || !out || in->B != out->B) return kexp::fail(ctx, "bad batches");
+    cudaSetDevice(ctx->device);
+    int maxW = 0;
+    for (int W : in->panelW) maxW = std::max(maxW, W);
+    if (ensure_panels(ctx, maxW)) return 1;
+    KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    for (size_t p = 0; p < in->panel.size(); ++p) {
+        const int W = in->panelW[p];
+        DISPATCH_W(W, launch_operator_full<kW>(ctx, in->panel[p], out->panel[p]));
+    }
+    KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    KEXP_CUDA(cudaGetLastError());
+    if (ctx->timing) drain_events(ctx);
+    return 0;
+}
+
+int kexp_spmm_K_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
+    if (!ctx) return 1;
+    if (!ctx->have_op) return kexp::fail(ctx, "operator not set");
+    if (!in || !out || in->B != out->B || in == out) return kexp::fail(ctx, "bad batches");
+    cudaSetDevice(ctx->device);
+    KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    for (size_t p = 0; p < in->panel.size(); ++p) {
+        const int W = in->panelW[p];
+        TimedLaunch tl(ctx, KC_SPMM_K);
+        DISPATCH_W(W, launch_spmm_K<kW>(ctx, in->panel[p], out->panel[p]));
+    }
+    KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    KEXP_CUDA(cudaGetLastError());
+    if (ctx->timing) drain_events(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------ stats / timing
+int kexp_set_kernel_timing(kexp_ctx* ctx, int on) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->timing = on != 0;
+    return 0;
+}
+
+int kexp_get_spmm_cg_ms(kexp_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return 1;
+    *ms = ctx->cls[KC_SPMM_CG].ms;
+    return 0;
+}
+
+// ms / launches / model bytes of one kernel class since the last reset (class ids: KClass)
+int kexp_get_class_stats(kexp_ctx* ctx, int cls, double* ms, int64_t* launches, double* bytes_per_launch_per_col) {
+    if (!ctx || cls < 0 || cls >= KC_COUNT) return 1;
+    if (ms) *ms = ctx->cls[cls].ms;
+    if (launches) *launches = ctx->cls[cls].launches;
+    if (bytes_per_launch_per_col) {
+        const double ns = (double)ctx->n_s, n = (double)ctx->n;
+        double b = 0.0;
+        switch (cls) {
+            case KC_SPMM_K: b = 16.0 * n; break;
+            case KC_CG_INIT: b = 24.0 * ns; break;
+            case KC_SPMM_CG: b = 16.0 * ns; break;
+            case KC_CG_XR: b = 48.0 * ns; break;
+            case KC_CG_P: b = 24.0 * ns; break;
+            case KC_CHEB: b = 40.0 * n; break;
+            default: b = 0.0;
+        }
+        *bytes_per_launch_per_col = b;
+    }
+    return 0;
+}
+
+// matrix bytes read once per launch by a kernel class (independent of the batch width)
+int kexp_get_class_matrix_bytes(kexp_ctx* ctx, int cls, double* bytes) {
+    if (!ctx || !bytes) return 1;
+    double b = 0.0;
+    const double pinv = 24.0 * (double)ctx->n_s;
+    switch (cls) {
+        case KC_SPMM_K: b = ctx->Kt.bytes(); break;
+        case KC_CG_INIT: b = pinv; break;
+        case KC_SPMM_CG: b = ctx->As.bytes(); break;
+        case KC_CG_XR: b = pinv; break;
+        case KC_CG_P: b = pinv; break;
+        case KC_CHEB: b = ctx->Rt.bytes() + (ctx->d_Dblk ? 24.0 * (double)ctx->n_d : 0.0); break;
+        default: b = 0.0;
+    }
+    *bytes = b;
+    return 0;
+}
+
+int kexp_stats(kexp_ctx* ctx, kexp_stats_t* out) {
+    if (!ctx || !out) return 1;
+    cudaSetDevice(ctx->device);
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    CgScalars sc;
+    KEXP_CUDA(cudaMemcpy(&sc, ctx->d_sc, sizeof(CgScalars), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->n = ctx->n;
+    out->n_solve = ctx->n_s;
+    out->cg_solves = (int64_t)(sc.total_solves - ctx->base_solves);
+    out->cg_iterations = (int64_t)(sc.total_iters - ctx->base_iters);
+    out->op_applications = ctx->st_op_apps;
+    out->kernel_launches = ctx->st_launches;
+    out->bicg_iterations = ctx->st_bicg;
+    out->last_max_rel_residual = sc.max_rel_res;
+    out->spmm_cg_launches = out->cg_iterations;
+    out->spmm_cg_bytes = 0.0;     // per-column figures: see kexp_get_class_stats
+    out->model_bytes = 0.0;
+    return 0;
+}
+
+int kexp_stats_reset(kexp_ctx* ctx) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    CgScalars sc;
+    KEXP_CUDA(cudaMemcpy(&sc, ctx->d_sc, sizeof(CgScalars), cudaMemcpyDeviceToHost));
+    ctx->base_iters = sc.total_iters; ctx->base_solves = sc.total_solves;
+    ctx->st_op_apps = 0; ctx->st_launches = 0; ctx->st_bicg = 0;
+    for (int i = 0; i < KC_COUNT; ++i) ctx->cls[i] = ClassStat();
+    return 0;
+}
+
+// ------------------------------------------------------------------ NCCL (dlopen: uses the
+// libnccl already loaded in the process, e.g. torch's, else the system one)
+typedef struct { char internal[128]; } kexp_nccl_id_t;
+
+static void* nccl_handle(kexp_ctx* ctx) {
+    void* h = ctx ? ctx->nccl_lib : nullptr;
+    if (h) return h;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    if (ctx) ctx->nccl_lib = h;
+    return h;
+}
+
+int kexp_comm_unique_id(void* id128) {
+    if (!id128) return 1;
+    void* h = nccl_handle(nullptr);
+    if (!h) return 2;
+    typedef int (*fn_t)(kexp_nccl_id_t*);
+    fn_t f = (fn_t)dlsym(h, "ncclGetUniqueId");
+    if (!f) return 3;
+    return f((kexp_nccl_id_t*)id128);
+}
+
+int kexp_comm_init(kexp_ctx* ctx, const void* id128, int rank, int nranks) {
+    if (!ctx || !id128) return 1;
+    cudaSetDevice(ctx->device);
+    void* h = nccl_handle(ctx);
+    if (!h) return kexp::fail(ctx, "libnccl.so.2 not found");
+    typedef int (*fn_t)(void**, int, kexp_nccl_id_t, int);
+    fn_t f = (fn_t)dlsym(h, "ncclCommInitRank");
+    if (!f) return kexp::fail(ctx, "ncclCommInitRank not found");
+    kexp_nccl_id_t id;
+    memcpy(&id, id128, sizeof(id));
+    int rc = f(&ctx->nccl_comm, nranks, id, rank);
+    if (rc) return kexp::fail(ctx, "ncclCommInitRank failed: " + std::to_string(rc));
+    ctx->rank = rank; ctx->nranks = nranks;
+    return 0;
+}
+
+int kexp_allreduce_sum_dev(kexp_ctx* ctx, double* v_dev, int64_t count) {
+    if (!ctx || !v_dev) return 1;
+    if (!ctx->nccl_comm) {
+        if (ctx->nranks == 1) return 0;
+        return kexp::fail(ctx, "kexp_comm_init not called");
+    }
+    cudaSetDevice(ctx->device);
+    typedef int (*fn_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    fn_t f = (fn_t)dlsym(ctx->nccl_lib, "ncclAllReduce");
+    if (!f) return kexp::fail(ctx, "ncclAllReduce not found");
+    const int ncclFloat64 = 8, ncclSum = 0;
+    int rc = f(v_dev, v_dev, (size_t)count, ncclFloat64, ncclSum, ctx->nccl_comm, ctx->stream);
+    if (rc) return kexp::fail(ctx, "ncclAllReduce failed: " + std::to_string(rc));
+    return 0;
+}
+
+}  // extern "C"

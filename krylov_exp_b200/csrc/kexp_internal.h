@@ -1,0 +1,126 @@
+// kexp_internal.h -- host-side state shared by the translation units of libkexp.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/kexp.h"
+#include "kexp_kernels.cuh"
+
+namespace kexp {
+
+struct DevCsr {
+    int* rowptr = nullptr;
+    int* col = nullptr;
+    double* val = nullptr;
+    int nrows = 0;
+    int ncols = 0;
+    int64_t nnz = 0;
+    double bytes() const { return 12.0 * (double)nnz + 4.0 * (double)(nrows + 1); }
+};
+
+// kernel classes for statistics / timing (profiles/ and bench.py's roofline use these)
+enum KClass { KC_SPMM_K = 0, KC_CG_INIT, KC_SPMM_CG, KC_CG_XR, KC_CG_P, KC_CHEB, KC_MISC, KC_COUNT };
+
+struct ClassStat {
+    double ms = 0.0;
+    int64_t launches = 0;
+    double bytes = 0.0;
+};
+
+struct ChebTable {
+    int ncheb = -1;
+    double L = 0.0;
+    double* d_coef = nullptr;      // ncheb+1 doubles
+};
+
+struct KrylovState;               // kexp_krylov.cu
+
+}  // namespace kexp
+
+struct kexp_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // operator plan
+    int64_t n = 0, n_s = 0, n_b = 0, n_d = 0;
+    kexp::DevCsr Kt, As, Rt;
+    double* d_Dblk = nullptr;      // n_d/3 blocks or null
+    double* d_Pinv = nullptr;      // n_s/3 blocks
+    int* d_perm = nullptr;         // user -> internal or null
+    bool have_op = false;
+    // raw user matrices kept for the plain plan (jacobi rebuild) -- host copies
+    std::vector<int32_t> h_As_rowptr, h_As_col;
+    std::vector<double> h_As_val;
+
+    // mass solver
+    double rtol = 1e-12;
+    int max_it = 60;
+    int precond = 3;
+
+    kexp::ChebTable cheb[KEXP_MAX_CHEBY];
+
+    // work panels (width curW), internal order
+    int curW = 0;
+    double *S0 = nullptr, *S1 = nullptr, *Y = nullptr, *T = nullptr, *X = nullptr, *P = nullptr, *Q = nullptr;
+    kexp::CgScalars* d_sc = nullptr;
+    double* d_partials = nullptr;
+    unsigned* d_counter = nullptr;
+    double* d_tscale = nullptr;    // kMaxW doubles: t_k / L
+    double* d_w = nullptr;         // kMaxW doubles: averaging weights
+    double* h_pin = nullptr;       // pinned staging (kMaxW*2 doubles)
+    double* d_stage = nullptr;     // device staging for host-layout vectors
+    size_t stage_bytes = 0;
+    double* h_stage = nullptr;     // pinned host staging
+    size_t h_stage_bytes = 0;
+    double* d_v = nullptr;         // n doubles (average result)
+
+    // graphs keyed by (cheby id, W)
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    bool use_graph = true;
+
+    // timing / stats
+    bool timing = false;
+    kexp::ClassStat cls[kexp::KC_COUNT];
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<std::pair<int, int>> ev_pending;   // (class, index of start event)
+    size_t ev_used = 0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    double last_ms = 0.0;
+    int64_t st_op_apps = 0, st_launches = 0, st_bicg = 0;
+    unsigned long long base_iters = 0, base_solves = 0;
+    std::map<const void*, int> occ_cache;
+
+    // krylov
+    kexp::KrylovState* kry = nullptr;
+
+    // nccl (dlopen'ed)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+struct kexp_batch {
+    kexp_ctx* ctx = nullptr;
+    int B = 0;
+    std::vector<int> panelW;       // width of each panel
+    std::vector<double*> panel;    // [n][W] device buffers, internal order
+};
+
+namespace kexp {
+int fail(kexp_ctx* ctx, const std::string& msg);
+int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v);
+void free_csr(DevCsr& d);
+int pick_W(int B);
+void krylov_free(kexp_ctx* ctx);
+}  // namespace kexp
+
+#define KEXP_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return kexp::fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+    } while (0)

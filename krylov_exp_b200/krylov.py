@@ -1,0 +1,83 @@
+"""Drop-in mirror of the reference's `krylov_exp` class (shift-and-invert Arnoldi).
+
+Same constructor and `apply(x, y, t, its=-999)` as /root/reference/krylov_exp.py:6-7,50.
+`solver` implements w = (M + gamma K)^-1 M v (test_krylov.py:34-62); on the GPU the depth
+unknowns are eliminated on the host once (M_eta is block diagonal):
+
+    (M_u + gamma K_uu - gamma^2 K_ue M_eta^-1 K_eu) w_u = M_u v_u - gamma K_ue v_eta
+    w_eta = v_eta - gamma M_eta^-1 K_eu w_u
+
+and the sparse, mildly non-symmetric system is solved by block-Jacobi BiCGStab on the
+device.  The modified Gram-Schmidt sweep in the M inner product (krylov_exp.py:73-80),
+the small Hessenberg inverse / exponential (:87-99) and the final combination (:102-109)
+all run in libkexp.so; see csrc/kexp_krylov.cu.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from .operator import Operator, _csr, _csr_args, _blockdiag
+from .function import as_array, write_back
+
+
+class ShiftedOperator:
+    """Host-side description of `solver` for the GPU: built from K, M_u, M_eta and gamma."""
+
+    def __init__(self, op: Operator, K, Mu, Meta_blocks, gamma, rtol=1e-13, max_it=2000):
+        K, Mu = _csr(K), _csr(Mu)
+        n_u = Mu.shape[0]
+        n = K.shape[0]
+        Meta_blocks = np.ascontiguousarray(Meta_blocks, dtype=np.float64)
+        Meta = _blockdiag(Meta_blocks)
+        Meta_inv = _blockdiag(np.linalg.inv(Meta_blocks))
+        Kuu, Kue, Keu = K[:n_u][:, :n_u], K[:n_u][:, n_u:], K[n_u:][:, :n_u]
+        g = float(gamma)
+        self.gamma = g
+        self.Ash = _csr(Mu + g * Kuu - (g * g) * (Kue @ Meta_inv @ Keu))
+        self.Brhs = _csr(sp.hstack([Mu, -g * Kue]))
+        self.Eback = _csr(-g * (Meta_inv @ Keu))
+        self.M = _csr(sp.block_diag([Mu, Meta]))
+        self.op = op
+        a, b, e, m = _csr_args(self.Ash), _csr_args(self.Brhs), _csr_args(self.Eback), _csr_args(self.M)
+        op._check(op.lib.kexp_set_krylov_operator(
+            op.ctx, g, _lib.ptr(a[0]), _lib.ptr(a[1]), _lib.ptr(a[2]), _lib.ptr(b[0]), _lib.ptr(b[1]), _lib.ptr(b[2]),
+            _lib.ptr(e[0]), _lib.ptr(e[1]), _lib.ptr(e[2]), _lib.ptr(m[0]), _lib.ptr(m[1]), _lib.ptr(m[2]),
+            float(rtol), int(max_it)), "kexp_set_krylov_operator")
+
+
+class krylov_exp(object):
+    def __init__(self, solver, solver_in, solver_out, gamma,
+                 kdim, operator_solver, operator_in, operator_out):
+        if not isinstance(solver, ShiftedOperator):
+            raise TypeError("solver must be a krylov_exp_b200.ShiftedOperator (build it from K, M and gamma; "
+                            "with Firedrake use firedrake_adapter to export K and M first)")
+        self.solver = solver
+        self.solver_in, self.solver_out = solver_in, solver_out
+        g = gamma.evaluate(0, 0, 0, 0) if hasattr(gamma, "evaluate") else float(gamma)   # krylov_exp.py:59
+        if abs(g - solver.gamma) > 1e-14 * abs(g):
+            raise ValueError("gamma differs from the one the shifted operator was built with")
+        self.gamma = gamma
+        self.kdim = int(kdim)
+        self.operator_solver, self.operator_in, self.operator_out = operator_solver, operator_in, operator_out
+        self.op = solver.op
+        self.H = np.zeros((self.kdim + 1, self.kdim))             # krylov_exp.py:45
+        self.residuals = None
+        self.u = None
+
+    def apply(self, x, y, t, its=-999, residuals=True):
+        """y <- exp(-t M^-1 K) x by SAI-Arnoldi (krylov_exp.py:50-109; note the sign, :89,96)."""
+        if its < 0:
+            its = self.kdim                                          # krylov_exp.py:66-67
+        assert its <= self.kdim                                      # krylov_exp.py:68
+        xin = np.ascontiguousarray(as_array(x), dtype=np.float64)
+        yout = np.empty_like(xin)
+        u = np.zeros(its)
+        res = np.zeros(its) if residuals else None
+        self.H[:] = 0.0
+        lib = self.op.lib
+        self.op._check(lib.kexp_krylov_apply(self.op.ctx, _lib.ptr(xin), _lib.ptr(yout), float(t), self.kdim, int(its),
+                                             _lib.ptr(self.H), _lib.ptr(u), _lib.ptr(res)), "kexp_krylov_apply")
+        self.u, self.residuals = u, res
+        write_back(y, yout)

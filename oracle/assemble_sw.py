@@ -214,7 +214,9 @@ class SWOperator:
         return self.n_u + self.n_eta
 
     def Meta(self):
-        return sp.block_diag(list(self.Meta_blocks), format="csr")
+        nb = self.Meta_blocks.shape[0]
+        return sp.bsr_matrix((self.Meta_blocks, np.arange(nb), np.arange(nb + 1)),
+                             shape=(3 * nb, 3 * nb)).tocsr()
 
     def M(self):
         return sp.block_diag([self.Mu, self.Meta()], format="csr")
