@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- exp(sL)v applications per second on the averaged-model hot path.
+
+Workload M1 (BASELINE.json configs[1]): icosahedral sphere ref_level 5,
+degree-3 geometry, BDM2 x DG1 (N = 215 040), dt = 0.25 h, rho = 1, tol = 1e-8
+(L = 13.4595, 29 Chebyshev terms), 64 averaging samples per GPU.
+
+One "step" = one averaged nonlinear evaluation's worth of exponentials
+(timestepping_methods.py:7-11):
+    forward   exp(+t_k L) U         one shared input, 64 sample times
+    backward  exp(-t_k L) X_k       64 distinct inputs
+    average   V = sum_k w_k (.)     weighted column reduction (+ NCCL all-reduce when N > 1)
+= 128 applications of exp(sL) per GPU per step.
+
+  value  applications/s with inputs resident in HBM (device batches)
+  e2e    same through the host-pointer C-ABI calls (pinned host buffers, H2D/D2H inside)
+  roofline  dominant kernel: algorithmic bytes / CUDA-event launch time vs measured HBM peak
+  cpu_baseline  the oracle's C/OpenMP port of the reference algorithm on the host cores
+
+`--impl reference` times the CPU port alone (the reference itself needs Firedrake/PETSc,
+which cannot be installed here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 900.0            # 0.25 h (averaged_sw_explicit.py:18,80)
+RHO = 1.0
+TOL = 1e-8            # averaged_sw_explicit.py:166-172
+NCHEB0 = 10000
+METRIC = "exp(sL)v applications/sec at icosa ref5 x 64 samples"
+
+
+def workload(ref_level, samples, seed=1234):
+    """Operator + M1 inputs.  Assembly is host-side input generation (krylov_exp_b200.assembly)."""
+    from krylov_exp_b200.assembly import assemble_sw, test_pulse
+    from krylov_exp_b200.samples import EIGS, sample_times_weights
+    sw = assemble_sw(ref_level)
+    eig = EIGS[ref_level - 3] if 3 <= ref_level <= 5 else EIGS[2] * 2.0 ** (ref_level - 5) * 1.03
+    L = eig * DT * RHO
+    t, w = sample_times_weights(samples, DT, RHO)
+    x = test_pulse(sw)
+    return sw, L, t, w, x
+
+
+def noisy_inputs(sw, x, B, out, seed=1234):
+    amp = 1e-3 * np.abs(x).max()
+    for k in range(B):
+        rng = np.random.default_rng(seed + k)
+        out[k] = x
+        out[k, sw.n_u:] += amp * rng.standard_normal(sw.n_eta)
+        out[k, :sw.n_u] += amp * np.sqrt(sw.g / sw.H) * sw.radius / 2 ** sw.ref_level * rng.standard_normal(sw.n_u)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cpu_reference_run(sw, L, t, x, ncols, steps, warmup, rtol=1e-5, literal=True):
+    """The reference's CPU algorithm (literal recurrence cheby_exp.py:110-165, CG at PETSc's default
+    rtol 1e-5, one sample time per core) through the oracle's C/OpenMP port.  Returns per-step seconds."""
+    from oracle import coeffs
+    from oracle.cpu_port import CpuCheby
+    cpu = CpuCheby(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=rtol, max_it=500)
+    c, n = coeffs.cheby_coeffs(NCHEB0, TOL, L)
+    coef = c if literal else coeffs.real_recurrence_coeffs(c, n)
+    X = noisy_inputs(sw, x, ncols, np.empty((ncols, sw.n)))
+    tk = np.resize(-t, ncols)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        cpu.apply_batch(coef, n, L, X, tk, literal=literal)
+        times.append(time.perf_counter() - t0)
+    return times[warmup:], cpu.num_threads(), n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kexp", choices=["kexp", "reference"])
+    ap.add_argument("--ref-level", type=int, default=5)
+    ap.add_argument("--samples", type=int, default=64, help="averaging samples per GPU")
+    ap.add_argument("--cg-rtol", type=float, default=1e-12)
+    ap.add_argument("--max-it", type=int, default=40)
+    ap.add_argument("--no-condense", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = len(os.sched_getaffinity(0))
+    workload_name = f"M1: icosahedral ref{args.ref_level} BDM2xDG1, dt=0.25h rho=1 tol=1e-8, {args.samples} samples/GPU"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sw, L, t, w, x = workload(args.ref_level, args.samples)
+        ncols = cores
+        times, nthreads, ncheb = cpu_reference_run(sw, L, t, x, ncols, args.steps, max(args.warmup, 1))
+        per = float(np.mean(times))
+        val = ncols / per
+        sample = (f"{ncols} of the {args.samples} backward applications per step (one per host thread), literal "
+                  f"2*ncheb-1={2 * ncheb - 1} operator solves each, block-Jacobi CG rtol 1e-5 (PETSc default)")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "applications/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name, "ncheb": ncheb, "L": L},
+            "cpu_baseline": {"value": val, "unit": "applications/s", "cores": nthreads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "applications/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = Python on Firedrake/PETSc (not installable here); timed: oracle/cpu_cheby.c, the C/OpenMP "
+                    "port of its algorithm, without Firedrake's per-solve RHS re-assembly"}))
+        return
+
+    # ------------------------------------------------------------------ GPU arm
+    import torch
+    import torch.distributed as dist
+    import krylov_exp_b200 as kx
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sw, L, t, w, x = workload(args.ref_level, args.samples)
+    B = args.samples
+    # weak scaling: every rank owns `samples` columns of a window with world*samples samples
+    t_all, w_all = kx.sample_times_weights(B * world, DT, RHO)
+    t = np.ascontiguousarray(t_all[rank * B:(rank + 1) * B])
+    w = np.ascontiguousarray(w_all[rank * B:(rank + 1) * B])
+
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, device=local_rank, condense=not args.no_condense,
+                     rtol=args.cg_rtol, max_it=args.max_it)
+    ce = kx.cheby_exp(op, None, None, NCHEB0, TOL, L)
+    n = op.n
+
+    # pinned host buffers (e2e) and device-resident batches (value)
+    hX = torch.empty((B, n), dtype=torch.float64).pin_memory().numpy()
+    hY = torch.empty((B, n), dtype=torch.float64).pin_memory().numpy()
+    hx = torch.empty((n,), dtype=torch.float64).pin_memory().numpy()
+    hx[:] = x
+    noisy_inputs(sw, x, B, hX, seed=1234 + rank * B)
+    b_fwd_in, b_fwd_out, b_bwd_in, b_bwd_out = op.batch(B), op.batch(B), op.batch(B), op.batch(B)
+    b_fwd_in.upload(hx, shared=True)
+    b_bwd_in.upload(hX)
+    v = torch.zeros(n, dtype=torch.float64, device=f"cuda:{local_rank}")
+
+    def step_dev():
+        ce.apply_dev(b_fwd_in, b_fwd_out, t)
+        ce.apply_dev(b_bwd_in, b_bwd_out, -t)
+        b_bwd_out.average_into(w, v.data_ptr())
+        if world > 1:
+            op.synchronize()
+            dist.all_reduce(v)
+
+    def barrier():
+        op.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    op.stats_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_host0 = time.perf_counter()
+    op.timer_start()
+    for _ in range(args.steps):
+        step_dev()
+    ms_dev = op.timer_stop()
+    barrier()
+    ms_host = (time.perf_counter() - t_host0) * 1e3
+    clocks = sampler.stop()
+    st = op.stats()
+    # device time on the library stream; with N > 1 the torch all-reduce runs on torch's stream, so the
+    # host-bracketed time (barrier + synchronize on both sides) is the one that contains everything
+    ms_total = ms_dev if world == 1 else ms_host
+    if world > 1:
+        tt = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    apps_per_step = 2 * B * world
+    ms_per_step = ms_total / args.steps
+    value = apps_per_step / (ms_per_step * 1e-3)
+    cg_its_per_solve = st["cg_iterations"] / max(st["cg_solves"], 1)
+
+    # ------------------------------------------------------------ e2e through host pointers
+    e2e = None
+    if not args.no_e2e:
+        def step_host():
+            ce.apply_batch(hx, t, shared=True, out=hY)              # H2D 1 vector, D2H B vectors
+            return ce.apply_average(hX, -t, w, allreduce=False)     # H2D B vectors, D2H 1 vector
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        ksteps = max(2, min(args.steps, 5))
+        for _ in range(ksteps):
+            vh = step_host()
+            if world > 1:
+                tv = torch.from_numpy(vh).to(f"cuda:{local_rank}")
+                dist.all_reduce(tv)
+                vh = tv.cpu().numpy()
+        barrier()
+        e_ms = (time.perf_counter() - t0) * 1e3 / ksteps
+        if world > 1:
+            tt = torch.tensor([e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_ms = float(tt.item())
+        e2e = {"value": apps_per_step / (e_ms * 1e-3), "unit": "applications/s",
+               "h2d_bytes_per_step": int(8 * n * (B + 1)), "d2h_bytes_per_step": int(8 * n * (B + 1)),
+               "ms_per_step": e_ms, "timing": "host clock around synchronous C-ABI calls (copies included)"}
+
+    # ------------------------------------------------------------ roofline of the dominant kernel
+    roofline, kernels = None, None
+    if not args.no_roofline and rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        op.set_kernel_timing(True)
+        op.stats_reset()
+        ce.apply_dev(b_bwd_in, b_bwd_out, -t)
+        op.synchronize()
+        st_t = op.stats()
+        kernels = {}
+        total_ms = 0.0
+        for name in ("spmm_K", "cg_init", "spmm_cg", "cg_update_xr", "cg_update_p", "cheb_update"):
+            cs = op.class_stats(name)
+            executed = cs["launches"]
+            if name in ("spmm_cg", "cg_update_xr", "cg_update_p"):
+                executed = st_t["cg_iterations"]      # launches after convergence return at once
+            bytes_launch = cs["bytes_per_col"] * B + cs["matrix_bytes"]
+            if name == "cheb_update":                 # three row-range launches form one pass
+                executed = st_t["op_applications"]
+            avg_ms = cs["ms"] / max(executed, 1)
+            kernels[name] = {"ms_total": cs["ms"], "launches": int(executed), "avg_us": avg_ms * 1e3,
+                             "algorithmic_bytes": bytes_launch, "gbs": bytes_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None}
+            total_ms += cs["ms"]
+        for k in kernels.values():
+            k["share"] = k["ms_total"] / total_ms if total_ms > 0 else None
+        dom = max(kernels, key=lambda k: kernels[k]["ms_total"])
+        kd = kernels[dom]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kd["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kd["gbs"] / peak if kd["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_us": kd["avg_us"], "algorithmic_bytes_per_launch": kd["algorithmic_bytes"],
+                    "share_of_step": kd["share"]}
+        # whole-apply effective bandwidth from the byte model (all kernels)
+        model_bytes = sum(k["algorithmic_bytes"] * k["launches"] for k in kernels.values())
+        roofline["whole_apply_gbs"] = model_bytes / (total_ms * 1e-3) / 1e9 if total_ms > 0 else None
+        roofline["whole_apply_frac"] = roofline["whole_apply_gbs"] / peak if total_ms > 0 else None
+        op.set_kernel_timing(False)
+        traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                roofline["traffic"] = json.load(open(traffic_file)).get(dom)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------ CPU baseline (rank 0, N = 1)
+    cpu = None
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        times, nthreads, ncheb = cpu_reference_run(sw, L, t, x, cores, 1, 1)
+        cpu = {"value": cores / float(np.mean(times)), "unit": "applications/s", "cores": nthreads, "kind": "port",
+               "sample": f"{cores} backward applications (one per host thread), literal 2*ncheb-1={2 * ncheb - 1} solves, "
+                         f"block-Jacobi CG rtol 1e-5; oracle/cpu_cheby.c"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "applications/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name, "ncheb": int(ce.ncheb), "L": L, "N": int(n), "applications_per_step": apps_per_step,
+                       "l2": "working set ~0.6 GB per GPU (> 126 MB L2), no explicit flush",
+                       "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi PCG rtol {args.cg_rtol:g}, "
+                                     f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}",
+                       "parallelism": f"samples sharded, {B}/GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "timing": {"device_ms": ms_dev, "host_ms": ms_host},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -107,10 +107,19 @@ int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev);
 int kexp_synchronize(kexp_ctx* ctx);
 /* ms of device time between the start and end of the last *_dev / apply call (CUDA events) */
 int kexp_last_device_ms(kexp_ctx* ctx, double* ms);
+/* CUDA events on the library's stream around an arbitrary sequence of calls */
+int kexp_timer_start(kexp_ctx* ctx);
+int kexp_timer_stop(kexp_ctx* ctx, double* ms);
 /* CUDA-event time accumulated over the CG-loop SpMM launches since reset; only collected
  * when timing mode is on (it disables graph replay and adds two event records per launch) */
 int kexp_set_kernel_timing(kexp_ctx* ctx, int on);
 int kexp_get_spmm_cg_ms(kexp_ctx* ctx, double* ms);
+
+/* per kernel class (0 spmm_K, 1 cg_init, 2 spmm_cg, 3 cg_update_xr, 4 cg_update_p, 5 cheb_update,
+ * 6 misc): event time and launches since reset (timing mode), algorithmic vector bytes per
+ * launch and sample column, and matrix bytes per launch (DESIGN.md byte model) */
+int kexp_get_class_stats(kexp_ctx* ctx, int cls, double* ms, int64_t* launches, double* bytes_per_launch_per_col);
+int kexp_get_class_matrix_bytes(kexp_ctx* ctx, int cls, double* bytes);
 
 /* one batched application of M^-1 K (operator_solver.solve(), cheby_exp.py:128) */
 int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out);

@@ -45,6 +45,8 @@ PROTOTYPES = {
     "kexp_cheby_apply_dev": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "kexp_batch_average_dev": (C.c_int, [_p, _p, _p]),
     "kexp_synchronize": (C.c_int, [_p]),
+    "kexp_timer_start": (C.c_int, [_p]),
+    "kexp_timer_stop": (C.c_int, [_p, C.POINTER(C.c_double)]),
     "kexp_last_device_ms": (C.c_int, [_p, C.POINTER(C.c_double)]),
     "kexp_set_kernel_timing": (C.c_int, [_p, C.c_int]),
     "kexp_get_spmm_cg_ms": (C.c_int, [_p, C.POINTER(C.c_double)]),
@@ -58,7 +60,6 @@ PROTOTYPES = {
     "kexp_allreduce_sum_dev": (C.c_int, [_p, _p, C.c_int64]),
     "kexp_stats": (C.c_int, [_p, C.POINTER(Stats)]),
     "kexp_stats_reset": (C.c_int, [_p]),
-    # not in the public header's core set: per-kernel-class timing used by bench.py
     "kexp_get_class_stats": (C.c_int, [_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "kexp_get_class_matrix_bytes": (C.c_int, [_p, C.c_int, C.POINTER(C.c_double)]),
 }

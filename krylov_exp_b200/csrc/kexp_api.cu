@@ -25,7 +25,47 @@ int pick_W(int B) {
 
 void free_csr(DevCsr& d) {
     cudaFree(d.rowptr); cudaFree(d.col); cudaFree(d.val);
+    cudaFree(d.browptr); cudaFree(d.blocks);
     d = DevCsr();
+}
+
+// CSR -> BSR(3x3) with 80-byte blocks {9 values row-major, block column in the low word of
+// the 10th double}.  Only kept when padding zeros cost < 40 % (BDM2/DG1 matrices: 0 %).
+static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v) {
+    if (nrows % 3 || ncols % 3 || nrows == 0) return 0;
+    const char* env = getenv("KEXP_NO_BSR");
+    if (env && env[0] == '1') return 0;
+    const int nbr = nrows / 3;
+    std::vector<int> browptr((size_t)nbr + 1, 0);
+    std::vector<double> blocks;
+    blocks.reserve((size_t)(rp[nrows] / 9 + nbr) * 10);
+    std::vector<int> cols;
+    for (int b = 0; b < nbr; ++b) {
+        cols.clear();
+        for (int k = rp[3 * b]; k < rp[3 * b + 3]; ++k) cols.push_back(ci[k] / 3);
+        std::sort(cols.begin(), cols.end());
+        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+        const size_t base = blocks.size();
+        blocks.resize(base + cols.size() * 10, 0.0);
+        for (size_t j = 0; j < cols.size(); ++j) {
+            int64_t bits = (int64_t)cols[j];
+            memcpy(&blocks[base + j * 10 + 9], &bits, sizeof(double));
+        }
+        for (int i = 0; i < 3; ++i)
+            for (int k = rp[3 * b + i]; k < rp[3 * b + i + 1]; ++k) {
+                const size_t j = std::lower_bound(cols.begin(), cols.end(), ci[k] / 3) - cols.begin();
+                blocks[base + j * 10 + 3 * i + (ci[k] % 3)] += v[k];
+            }
+        browptr[b + 1] = browptr[b] + (int)cols.size();
+    }
+    const int64_t nblocks = browptr[nbr];
+    if ((double)nblocks * 9.0 > 1.4 * (double)rp[nrows]) return 0;
+    KEXP_CUDA(cudaMalloc(&d.browptr, sizeof(int) * (size_t)(nbr + 1)));
+    KEXP_CUDA(cudaMalloc(&d.blocks, sizeof(double) * 10 * (size_t)std::max<int64_t>(nblocks, 1)));
+    KEXP_CUDA(cudaMemcpy(d.browptr, browptr.data(), sizeof(int) * (size_t)(nbr + 1), cudaMemcpyHostToDevice));
+    KEXP_CUDA(cudaMemcpy(d.blocks, blocks.data(), sizeof(double) * 10 * (size_t)nblocks, cudaMemcpyHostToDevice));
+    d.nbr = nbr; d.nblocks = nblocks;
+    return 0;
 }
 
 int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v) {
@@ -41,7 +81,7 @@ int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp
     KEXP_CUDA(cudaMemcpy(d.rowptr, rp, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.col, ci, sizeof(int) * (size_t)d.nnz, cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.val, v, sizeof(double) * (size_t)d.nnz, cudaMemcpyHostToDevice));
-    return 0;
+    return build_bsr3(ctx, d, nrows, ncols, rp, ci, v);
 }
 
 }  // namespace kexp
@@ -135,36 +175,51 @@ int ensure_stage(kexp_ctx* ctx, size_t bytes) {
     return 0;
 }
 
+// Y = A X (MODE 0) or the CG product q = A p with the fused p.q reduction (MODE 1); BSR(3x3)
+// kernel when the matrix has that structure, generic CSR kernel otherwise.
+template <int W, int MODE>
+void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
+    constexpr int LPR = W / 2, RPW = 32 / LPR;
+    if (A.bsr()) {
+        auto k = bsr3_spmm_kernel<W, MODE>;
+        constexpr int per_cta = (kThreads / 32) * BsrCfg<W>::BRW;
+        int grid = std::min(max_grid(ctx, k), std::max(1, (A.nbr + per_cta - 1) / per_cta));
+        k<<<grid, kThreads, 0, ctx->stream>>>(A.browptr, A.blocks, X, Y, A.nbr, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+    } else {
+        auto k = spmm_kernel<W, MODE>;
+        int grid = std::min(max_grid(ctx, k), std::max(1, (A.nrows + RPW * 8 - 1) / (RPW * 8)));
+        if (MODE == 1) grid = std::min(grid, 2 * ctx->num_sms);
+        k<<<grid, kThreads, 0, ctx->stream>>>(A.rowptr, A.col, A.val, X, Y, A.nrows, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+    }
+}
+
 // ---- one batched application of M^-1 K on the work panels: input `in` (n x W),
 // leaves T (rows needing no solve), X (solved rows). W is a template parameter.
 template <int W>
 void enqueue_operator(kexp_ctx* ctx, const double* in) {
-    constexpr int LPR = W / 2, RPW = 32 / LPR;
+    constexpr int LPR = W / 2;
     cudaStream_t s = ctx->stream;
-    const int n = (int)ctx->n, ns = (int)ctx->n_s;
+    const int ns = (int)ctx->n_s;
+    const int red_grid = 2 * ctx->num_sms;      // reduction kernels: few, fat blocks keep the last-block sum short
     {   // T = Kt * in
-        auto k = spmm_kernel<W, 0>;
-        int grid = std::min(max_grid(ctx, k), std::max(1, (n + RPW * 8 - 1) / (RPW * 8)));
         TimedLaunch tl(ctx, KC_SPMM_K);
-        k<<<grid, kThreads, 0, s>>>(ctx->Kt.rowptr, ctx->Kt.col, ctx->Kt.val, in, ctx->T, n, nullptr, nullptr, nullptr);
+        launch_spmm<W, 0>(ctx, ctx->Kt, in, ctx->T);
     }
     const int ntri = ns / 3;
     {
         auto k = cg_init_kernel<W>;
-        int grid = std::min(max_grid(ctx, k), blocks_for(ntri, LPR));
+        int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPR));
         TimedLaunch tl(ctx, KC_CG_INIT);
         k<<<grid, kThreads, 0, s>>>(ctx->T, ctx->X, ctx->P, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
     }
     for (int it = 0; it < ctx->max_it; ++it) {
         {
-            auto k = spmm_kernel<W, 1>;
-            int grid = std::min(max_grid(ctx, k), std::max(1, (ns + RPW * 8 - 1) / (RPW * 8)));
             TimedLaunch tl(ctx, KC_SPMM_CG);
-            k<<<grid, kThreads, 0, s>>>(ctx->As.rowptr, ctx->As.col, ctx->As.val, ctx->P, ctx->Q, ns, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+            launch_spmm<W, 1>(ctx, ctx->As, ctx->P, ctx->Q);
         }
         {
             auto k = cg_update_xr_kernel<W>;
-            int grid = std::min(max_grid(ctx, k), blocks_for(ntri, LPR));
+            int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPR));
             TimedLaunch tl(ctx, KC_CG_XR);
             k<<<grid, kThreads, 0, s>>>(ctx->X, ctx->T, ctx->P, ctx->Q, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
         }
@@ -304,6 +359,7 @@ void invalidate_graphs(kexp_ctx* ctx) {
 template <int W>
 void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, spmm_kernel<W, 0>); max_grid(ctx, spmm_kernel<W, 1>);
+    max_grid(ctx, bsr3_spmm_kernel<W, 0>); max_grid(ctx, bsr3_spmm_kernel<W, 1>);
     max_grid(ctx, cg_init_kernel<W>); max_grid(ctx, cg_update_xr_kernel<W>); max_grid(ctx, cg_update_p_kernel<W>);
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
 }
@@ -345,11 +401,7 @@ void launch_colsum(kexp_ctx* ctx, const double* Ypanel, double* v_dev, int accum
 
 template <int W>
 void launch_spmm_K(kexp_ctx* ctx, const double* in, double* out) {
-    constexpr int RPW = 32 / (W / 2);
-    const int n = (int)ctx->n;
-    auto k = spmm_kernel<W, 0>;
-    int grid = std::min(max_grid(ctx, k), std::max(1, (n + RPW * 8 - 1) / (RPW * 8)));
-    k<<<grid, kThreads, 0, ctx->stream>>>(ctx->Kt.rowptr, ctx->Kt.col, ctx->Kt.val, in, out, n, nullptr, nullptr, nullptr);
+    launch_spmm<W, 0>(ctx, ctx->Kt, in, out);
 }
 
 template <int W>
@@ -431,6 +483,7 @@ int kexp_destroy(kexp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
+    if (ctx->tmp_in) { kexp_batch_destroy(ctx->tmp_in); kexp_batch_destroy(ctx->tmp_out); ctx->tmp_in = ctx->tmp_out = nullptr; }
     kexp::krylov_free(ctx);
     free_csr(ctx->Kt); free_csr(ctx->As); free_csr(ctx->Rt);
     double* bufs[] = {ctx->S0, ctx->S1, ctx->Y, ctx->T, ctx->X, ctx->P, ctx->Q, ctx->d_Dblk, ctx->d_Pinv,
@@ -443,6 +496,8 @@ int kexp_destroy(kexp_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->nccl_comm && ctx->nccl_lib) {
         typedef int (*destroy_t)(void*);
         destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
@@ -499,6 +554,7 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
     if (Dblk && n_d % 3) return kexp::fail(ctx, "block rows must be a multiple of 3");
     if (n_b > 0 && !Rt_rowptr) return kexp::fail(ctx, "back-substitution matrix missing");
     invalidate_graphs(ctx);
+    if (ctx->tmp_in) { kexp_batch_destroy(ctx->tmp_in); kexp_batch_destroy(ctx->tmp_out); ctx->tmp_in = ctx->tmp_out = nullptr; }
     ctx->have_op = false;
     ctx->n = n; ctx->n_s = n_s; ctx->n_b = n_b; ctx->n_d = n_d;
     ctx->curW = 0;   // panels are re-allocated for the new size
@@ -677,6 +733,25 @@ int kexp_synchronize(kexp_ctx* ctx) {
     return 0;
 }
 
+int kexp_timer_start(kexp_ctx* ctx) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (!ctx->ev_t0) { KEXP_CUDA(cudaEventCreate(&ctx->ev_t0)); KEXP_CUDA(cudaEventCreate(&ctx->ev_t1)); }
+    KEXP_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return 0;
+}
+
+int kexp_timer_stop(kexp_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->ev_t0) return 1;
+    cudaSetDevice(ctx->device);
+    KEXP_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    KEXP_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    float f = 0.f;
+    KEXP_CUDA(cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+    *ms = f;
+    return 0;
+}
+
 int kexp_last_device_ms(kexp_ctx* ctx, double* ms) {
     if (!ctx || !ms) return 1;
     cudaSetDevice(ctx->device);
@@ -696,19 +771,31 @@ int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev) {
     return 0;
 }
 
+// scratch batches of the host-pointer entry points, kept between calls (cudaMalloc/cudaFree
+// of ~100 MB panels would otherwise dominate small applies)
+static int scratch_batches(kexp_ctx* ctx, int B, kexp_batch** bi, kexp_batch** bo) {
+    if (ctx->tmp_in && ctx->tmp_in->B != B) {
+        kexp_batch_destroy(ctx->tmp_in); kexp_batch_destroy(ctx->tmp_out);
+        ctx->tmp_in = ctx->tmp_out = nullptr;
+    }
+    if (!ctx->tmp_in) {
+        if (kexp_batch_create(ctx, B, &ctx->tmp_in)) return 1;
+        if (kexp_batch_create(ctx, B, &ctx->tmp_out)) { kexp_batch_destroy(ctx->tmp_in); ctx->tmp_in = nullptr; return 1; }
+    }
+    *bi = ctx->tmp_in; *bo = ctx->tmp_out;
+    return 0;
+}
+
 int kexp_cheby_apply_batch(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
                            double* Y, int64_t ldy, const double* t, int B) {
     if (check_ready(ctx, id)) return 1;
     if (!X || !Y || !t || B < 1) return kexp::fail(ctx, "bad arguments");
     if (X == Y) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
     kexp_batch *bi = nullptr, *bo = nullptr;
-    int rc = kexp_batch_create(ctx, B, &bi);
-    if (!rc) rc = kexp_batch_create(ctx, B, &bo);
+    int rc = scratch_batches(ctx, B, &bi, &bo);
     if (!rc) rc = kexp_batch_upload(bi, X, ldx, x_is_shared);
     if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
     if (!rc) rc = kexp_batch_download(bo, Y, ldy);
-    kexp_batch_destroy(bi);
-    kexp_batch_destroy(bo);
     return rc;
 }
 
@@ -724,8 +811,7 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
     if (check_ready(ctx, id)) return 1;
     if (!X || !t || !w || !v_out || B < 1) return kexp::fail(ctx, "bad arguments");
     kexp_batch *bi = nullptr, *bo = nullptr;
-    int rc = kexp_batch_create(ctx, B, &bi);
-    if (!rc) rc = kexp_batch_create(ctx, B, &bo);
+    int rc = scratch_batches(ctx, B, &bi, &bo);
     if (!rc) rc = kexp_batch_upload(bi, X, ldx, x_is_shared);
     if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
     if (!rc) rc = kexp_batch_average_dev(bo, w, ctx->d_v);
@@ -735,8 +821,6 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = kexp::fail(ctx, cudaGetErrorString(e));
     }
-    kexp_batch_destroy(bi);
-    kexp_batch_destroy(bo);
     return rc;
 }
 

@@ -17,7 +17,16 @@ struct DevCsr {
     int nrows = 0;
     int ncols = 0;
     int64_t nnz = 0;
-    double bytes() const { return 12.0 * (double)nnz + 4.0 * (double)(nrows + 1); }
+    // BSR(3x3) copy (80-byte blocks: 9 values + block column), built when the matrix has
+    // the 3-dofs-per-entity structure with little fill
+    int* browptr = nullptr;
+    double* blocks = nullptr;
+    int nbr = 0;
+    int64_t nblocks = 0;
+    bool bsr() const { return blocks != nullptr; }
+    double bytes() const {
+        return bsr() ? 80.0 * (double)nblocks + 4.0 * (double)(nbr + 1) : 12.0 * (double)nnz + 4.0 * (double)(nrows + 1);
+    }
 };
 
 // kernel classes for statistics / timing (profiles/ and bench.py's roofline use these)
@@ -88,7 +97,9 @@ struct kexp_ctx {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, int>> ev_pending;   // (class, index of start event)
     size_t ev_used = 0;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    struct kexp_batch* tmp_in = nullptr;
+    struct kexp_batch* tmp_out = nullptr;
     double last_ms = 0.0;
     int64_t st_op_apps = 0, st_launches = 0, st_bicg = 0;
     unsigned long long base_iters = 0, base_solves = 0;

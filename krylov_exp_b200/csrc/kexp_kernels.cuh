@@ -103,8 +103,16 @@ __device__ __forceinline__ void final_sums(const double* __restrict__ partials, 
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
         double s = 0.0;
-        for (int b = part; b < (int)gridDim.x; b += NSPLIT)
-            s += __ldcg(partials + ((size_t)a * gridDim.x + b) * W + c);
+        const double* base = partials + (size_t)a * gridDim.x * W + c;
+        int b = part;
+        for (; b + 7 * NSPLIT < (int)gridDim.x; b += 8 * NSPLIT) {   // 8 loads in flight, summed in order
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + (size_t)(b + u * NSPLIT) * W);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; b < (int)gridDim.x; b += NSPLIT) s += __ldcg(base + (size_t)b * W);
         red[a][part][c] = s;
     }
     __syncthreads();
@@ -179,6 +187,130 @@ spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const d
     }
     if (MODE == 1) {
         if (block_partials<W, 1>(dot, partials, counter)) {
+            double s[1];
+            final_sums<W, 1>(partials, s);
+            if (threadIdx.x < W) {
+                const int c = threadIdx.x;
+                sc->pq[c] = s[0];
+                sc->alpha[c] = (sc->active[c] && s[0] > 0.0) ? sc->rz[c] / s[0] : 0.0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// BSR(3x3) SpMM -- the layout BDM2/DG1 matrices have naturally (3 dofs per mesh entity).
+// A block is 80 bytes: 9 values row-major + the block-column index in the low word of the
+// 10th double, so one block is five aligned 16-byte broadcast loads.  A group of LPB lanes
+// owns one block row (3 output rows) and each lane CPT = min(W,8) sample columns: every
+// gathered X value feeds 3 FMAs and every matrix value 8, which takes the L1/shared-memory
+// data path off the critical path.  Each CTA walks a CONTIGUOUS range of block rows so the
+// gathered rows of neighbouring mesh entities are re-used out of L1 instead of L2.
+// MODE as in spmm_kernel.
+// ------------------------------------------------------------------------------------
+template <int W>
+struct BsrCfg {
+    static constexpr int CPT = (W >= 8) ? 8 : W;   // sample columns per thread
+    static constexpr int LPB = W / CPT;            // lanes per block row
+    static constexpr int BRW = 32 / LPB;           // block rows per warp
+    static constexpr int NV = CPT / 2;             // double2 per row per thread
+};
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
+                 const double* __restrict__ X, double* __restrict__ Y, int nbr,
+                 CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
+    using C = BsrCfg<W>;
+    constexpr int LPB = C::LPB, BRW = C::BRW, NV = C::NV;
+    if (MODE == 1 && sc->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % LPB, g = lane / LPB;
+    const int per = nbr / gridDim.x, rem = nbr % gridDim.x;
+    const int start = blockIdx.x * per + min((int)blockIdx.x, rem);
+    const int end = start + per + ((int)blockIdx.x < rem ? 1 : 0);
+    double2 dot[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) dot[j] = make_double2(0.0, 0.0);
+
+    for (int base = start; base < end; base += (kThreads / 32) * BRW) {
+        const int br = base + warp * BRW + g;
+        if (br < end) {
+            double2 acc[3][NV];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) acc[i][j] = make_double2(0.0, 0.0);
+            const int k0 = __ldg(browptr + br), k1 = __ldg(browptr + br + 1);
+            for (int k = k0; k < k1; ++k) {
+                const double2* bp = reinterpret_cast<const double2*>(blocks + (size_t)10 * k);
+                const double2 v01 = __ldg(bp), v23 = __ldg(bp + 1), v45 = __ldg(bp + 2), v67 = __ldg(bp + 3), v8c = __ldg(bp + 4);
+                const int c = __double2loint(v8c.y);
+                const double a[3][3] = {{v01.x, v01.y, v23.x}, {v23.y, v45.x, v45.y}, {v67.x, v67.y, v8c.x}};
+                const double* xr = X + (size_t)(3 * c) * W + 2 * l;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    double2 x[NV];
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) x[j] = ld2(xr + (size_t)r * W + 2 * LPB * j);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < NV; ++j) {
+                            acc[i][j].x = fma(a[i][r], x[j].x, acc[i][j].x);
+                            acc[i][j].y = fma(a[i][r], x[j].y, acc[i][j].y);
+                        }
+                }
+            }
+            double* yr = Y + (size_t)(3 * br) * W + 2 * l;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) st2(yr + (size_t)i * W + 2 * LPB * j, acc[i][j]);
+            if (MODE == 1) {
+                const double* pr = X + (size_t)(3 * br) * W + 2 * l;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        const double2 p = ld2(pr + (size_t)i * W + 2 * LPB * j);
+                        dot[j].x = fma(p.x, acc[i][j].x, dot[j].x);
+                        dot[j].y = fma(p.y, acc[i][j].y, dot[j].y);
+                    }
+            }
+        }
+    }
+    if (MODE == 1) {
+        // block partial: lanes with equal l across the warp's block rows, then across warps
+        __shared__ double2 sh[kThreads / 32][W / 2];
+        __shared__ bool s_last;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            double2 v = dot[j];
+#pragma unroll
+            for (int off = 16; off >= LPB; off >>= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+            }
+            if (lane < LPB) sh[warp][l + LPB * j] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < W / 2) {
+            double2 s = sh[0][threadIdx.x];
+#pragma unroll
+            for (int w = 1; w < kThreads / 32; ++w) { s.x += sh[w][threadIdx.x].x; s.y += sh[w][threadIdx.x].y; }
+            st2(partials + (size_t)blockIdx.x * W + 2 * threadIdx.x, s);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(counter, 1u);
+            s_last = (ticket == gridDim.x - 1);
+            if (s_last) *counter = 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
             double s[1];
             final_sums<W, 1>(partials, s);
             if (threadIdx.x < W) {

@@ -204,6 +204,14 @@ class Operator:
         self._check(self.lib.kexp_get_class_matrix_bytes(self.ctx, KCLASS[name], C.byref(mb)), "class_matrix_bytes")
         return {"ms": ms.value, "launches": ln.value, "bytes_per_col": b.value, "matrix_bytes": mb.value}
 
+    def timer_start(self):
+        self._check(self.lib.kexp_timer_start(self.ctx), "kexp_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.kexp_timer_stop(self.ctx, C.byref(ms)), "kexp_timer_stop")
+        return ms.value
+
     def last_device_ms(self):
         ms = C.c_double()
         self._check(self.lib.kexp_last_device_ms(self.ctx, C.byref(ms)), "kexp_last_device_ms")

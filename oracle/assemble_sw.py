@@ -1,381 +1,10 @@
-"""TEST INFRASTRUCTURE (oracle) -- not a product path.
+"""TEST INFRASTRUCTURE (oracle).  The discrete operator the oracle works on.
 
-Standalone assembler for the linear rotating shallow-water operator used by the
-reference, on the BDM2 x DG1 compatible finite-element pair on the refined
-icosahedral sphere.  Firedrake/PETSc (where the reference's arithmetic lives) is
-not installable here, so this file restates the *discrete operator definition*:
-
-  forms      /root/reference/averaged_sw_explicit.py:142-148
-                 K(v,phi;u,eta) = -<f k x u, v> + g <eta, div v> - H <div u, phi>
-                 M              = <u, v> + <eta, phi>
-  c-scaled   /root/reference/test_cheby.py:38-44, L_eigs.py:36-42 (g,H -> c=sqrt(gH))
-  constants  /root/reference/averaged_sw_explicit.py:40-45,57
-  mesh       IcosahedralSphereMesh(radius, refinement_level, degree) [ext: Firedrake],
-             base icosahedron + flat midpoint refinement + radial projection, P3 geometry
-  spaces     /root/reference/averaged_sw_explicit.py:54-56  (BDM 2, DG 1)
-  H(div)     /root/reference/calculate_norm.py:95 (norm_type="Hdiv")
-
-Pinned by: the largest-imaginary generalised eigenvalue of (K, M) against
-/root/reference/eigs.dat:2-4 (tests/test_oracle_assembler.py).  Any unisolvent
-BDM2 basis gives the same operator up to a change of basis; eigenvalues and the
-M / H(div) norms are basis independent.
-
-Only tests/, bench.py's cpu_baseline leg and __graft_entry__.smoke() may import this.
+The standalone BDM2 x DG1 icosahedral assembler lives in krylov_exp_b200/assembly.py
+(host-side input generation, standing in for Firedrake's assembly which the north star
+keeps on the host).  The oracle re-exports it so that the CUDA path and the CPU oracle
+are compared on identical K, M_u, M_eta; everything downstream of the matrices (operator
+application, mass solves, recurrences, norms) is restated independently in this package.
 """
-from __future__ import annotations
-
-import dataclasses
-import numpy as np
-import scipy.sparse as sp
-from scipy.special import roots_jacobi, roots_legendre
-
-R_EARTH = 6371220.0       # averaged_sw_explicit.py:40
-H_MEAN = 5960.0           # averaged_sw_explicit.py:42
-OMEGA = 7.292e-5          # averaged_sw_explicit.py:43
-GRAV = 9.8                # averaged_sw_explicit.py:44
-
-_PHI = (1.0 + np.sqrt(5.0)) / 2.0
-ICOS_VERTS = np.array([
-    [-1, _PHI, 0], [1, _PHI, 0], [-1, -_PHI, 0], [1, -_PHI, 0],
-    [0, -1, _PHI], [0, 1, _PHI], [0, -1, -_PHI], [0, 1, -_PHI],
-    [_PHI, 0, -1], [_PHI, 0, 1], [-_PHI, 0, -1], [-_PHI, 0, 1]], dtype=np.float64)
-ICOS_FACES = np.array([
-    [0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11],
-    [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
-    [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9],
-    [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
-
-
-# --------------------------------------------------------------------------- mesh
-def icosahedral_mesh(ref_level: int, radius: float = R_EARTH):
-    """Vertices (on the sphere) and cells of the refined icosahedron.
-
-    Refinement is done on the FLAT faces (edge midpoints), all vertices are pushed
-    radially to `radius` afterwards -- the IcosahedralSphereMesh recipe.  Cells are
-    numbered hierarchically (the four children of a cell are consecutive), which is
-    also the locality order the GPU kernels like.
-    """
-    verts = [v.copy() for v in ICOS_VERTS]
-    cells = [tuple(f) for f in ICOS_FACES]
-    for _ in range(ref_level):
-        mid = {}
-
-        def midpoint(a, b):
-            key = (a, b) if a < b else (b, a)
-            m = mid.get(key)
-            if m is None:
-                m = len(verts)
-                verts.append(0.5 * (verts[a] + verts[b]))
-                mid[key] = m
-            return m
-
-        new = []
-        for (a, b, c) in cells:
-            ab, bc, ca = midpoint(a, b), midpoint(b, c), midpoint(c, a)
-            new += [(a, ab, ca), (ab, b, bc), (ca, bc, c), (ab, bc, ca)]
-        cells = new
-    V = np.array(verts)
-    V *= (radius / np.linalg.norm(V, axis=1))[:, None]
-    C = np.array(cells, dtype=np.int64)
-    # outward (counter-clockwise seen from outside) orientation
-    n = np.cross(V[C[:, 1]] - V[C[:, 0]], V[C[:, 2]] - V[C[:, 0]])
-    flip = np.einsum('ij,ij->i', n, V[C].mean(axis=1)) < 0
-    C[flip] = C[flip][:, [0, 2, 1]]
-    return V, C
-
-
-# ---------------------------------------------------------------- reference element
-def duffy_quadrature(n: int):
-    """n*n-point collapsed Gauss-Jacobi rule on the unit triangle, exact to degree 2n-1."""
-    xa, wa = roots_jacobi(n, 0, 0)
-    xb, wb = roots_jacobi(n, 1, 0)
-    a = 0.5 * (xa + 1.0)
-    b = 0.5 * (xb + 1.0)
-    X = (a[:, None] * (1.0 - b[None, :])).ravel()
-    Y = np.repeat(b[None, :], n, axis=0).ravel()
-    W = (wa[:, None] * wb[None, :]).ravel() * 0.125
-    return np.stack([X, Y], axis=1), W
-
-
-def _mono2(deg):
-    return [(i, j) for d in range(deg + 1) for j in range(d + 1) for i in [d - j]]
-
-
-def _eval_mono(pts, exps):
-    x, y = pts[:, 0], pts[:, 1]
-    return np.stack([x ** i * y ** j for (i, j) in exps], axis=1)
-
-
-def _eval_mono_grad(pts, exps):
-    x, y = pts[:, 0], pts[:, 1]
-    gx = np.stack([(i * x ** max(i - 1, 0) if i else 0 * x) * y ** j for (i, j) in exps], axis=1)
-    gy = np.stack([x ** i * (j * y ** max(j - 1, 0) if j else 0 * y) for (i, j) in exps], axis=1)
-    return gx, gy
-
-
-def p3_nodes(variant: str = "equispaced"):
-    """Reference nodes of the cubic Lagrange geometry element: 3 vertices, 2 per
-    edge, centroid.  'equispaced' or 'gll' edge-node placement."""
-    a = 1.0 / 3.0 if variant == "equispaced" else 0.5 * (1.0 - 1.0 / np.sqrt(5.0))
-    v = np.array([[0., 0.], [1., 0.], [0., 1.]])
-    nodes = [v[0], v[1], v[2]]
-    for (p, q) in ((0, 1), (1, 2), (2, 0)):
-        nodes.append(v[p] + a * (v[q] - v[p]))
-        nodes.append(v[p] + (1 - a) * (v[q] - v[p]))
-    nodes.append(v.mean(axis=0))
-    return np.array(nodes)
-
-
-class Lagrange:
-    """Nodal scalar Lagrange basis on the reference triangle for given nodes."""
-
-    def __init__(self, nodes, deg):
-        self.exps = _mono2(deg)
-        self.nodes = nodes
-        self.coef = np.linalg.inv(_eval_mono(nodes, self.exps))   # mono -> nodal
-
-    def tab(self, pts):
-        return _eval_mono(pts, self.exps) @ self.coef
-
-    def tab_grad(self, pts):
-        gx, gy = _eval_mono_grad(pts, self.exps)
-        return gx @ self.coef, gy @ self.coef
-
-
-_GAUSS3 = 0.5 * (roots_legendre(3)[0] + 1.0)     # edge dof points, symmetric about 1/2
-_REF_V = np.array([[0., 0.], [1., 0.], [0., 1.]])
-_LOCAL_EDGES = ((0, 1), (1, 2), (2, 0))             # counter-clockwise
-
-
-class BDM2:
-    """BDM degree 2 on the reference triangle: full P2^2, 12 dofs.
-
-    dofs 3e+k (e=0..2, k=0..2): u . n_e |e| at the k-th Gauss point of local edge e
-    (n_e the outward normal) -- the normal flux density, preserved by the
-    contravariant Piola map; dofs 9..11: moments against (1,0), (0,1), (-y,x).
-    """
-
-    def __init__(self):
-        self.exps = _mono2(2)
-        nm = len(self.exps)
-        V = np.zeros((12, 2 * nm))
-        for e, (p, q) in enumerate(_LOCAL_EDGES):
-            t = _REF_V[q] - _REF_V[p]
-            nrm = np.array([t[1], -t[0]])
-            pts = _REF_V[p][None, :] + _GAUSS3[:, None] * t[None, :]
-            m = _eval_mono(pts, self.exps)
-            V[3 * e:3 * e + 3, :nm] = m * nrm[0]
-            V[3 * e:3 * e + 3, nm:] = m * nrm[1]
-        qp, qw = duffy_quadrature(4)
-        m = _eval_mono(qp, self.exps)
-        V[9, :nm] = qw @ m
-        V[10, nm:] = qw @ m
-        V[11, :nm] = qw @ (m * (-qp[:, 1:2]))
-        V[11, nm:] = qw @ (m * qp[:, 0:1])
-        self.coef = np.linalg.inv(V)         # column j = monomial coefficients of basis fn j
-
-    def tab(self, pts):
-        """(nq, 12, 2) values and (nq, 12) reference divergences."""
-        nm = len(self.exps)
-        m = _eval_mono(pts, self.exps)
-        gx, gy = _eval_mono_grad(pts, self.exps)
-        ux = m @ self.coef[:nm]
-        uy = m @ self.coef[nm:]
-        div = gx @ self.coef[:nm] + gy @ self.coef[nm:]
-        return np.stack([ux, uy], axis=2), div
-
-
-# ------------------------------------------------------------------- the operator
-@dataclasses.dataclass
-class SWOperator:
-    ref_level: int
-    degree: int
-    n_u: int
-    n_eta: int
-    n_cells: int
-    K: sp.csr_matrix            # N x N, mixed [u; eta]
-    Mu: sp.csr_matrix           # n_u x n_u SPD
-    Meta_blocks: np.ndarray     # (C,3,3)
-    Meta_inv_blocks: np.ndarray  # (C,3,3)
-    Ddiv: sp.csr_matrix         # n_u x n_u, <div u, div v>
-    cell_u_dofs: np.ndarray     # (C,12) global u dof of each local dof
-    cell_u_sign: np.ndarray     # (C,12) +-1
-    eta_nodes: np.ndarray       # (C,3,3) physical coordinates of the DG1 nodes
-    g: float
-    H: float
-    radius: float
-    Mu_elem: np.ndarray = None  # (C,12,12) signed element mass matrices
-    Kuu_elem: np.ndarray = None  # (C,12,12) signed -Coriolis element matrices
-    Kue_ref: np.ndarray = None  # (12,3) g * <psi_j, div v_i> (unsigned, reference)
-    Keu_ref: np.ndarray = None  # (3,12) -H * <div u_j, psi_i>
-
-    @property
-    def n(self):
-        return self.n_u + self.n_eta
-
-    def Meta(self):
-        nb = self.Meta_blocks.shape[0]
-        return sp.bsr_matrix((self.Meta_blocks, np.arange(nb), np.arange(nb + 1)),
-                             shape=(3 * nb, 3 * nb)).tocsr()
-
-    def M(self):
-        return sp.block_diag([self.Mu, self.Meta()], format="csr")
-
-    def interpolate_eta(self, fn):
-        """Nodal DG1 interpolant of fn(x,y,z) (test_cheby.py:75 style input)."""
-        X = self.eta_nodes.reshape(-1, 3)
-        return fn(X[:, 0], X[:, 1], X[:, 2])
-
-
-def assemble_sw(ref_level: int, degree: int = 3, radius: float = R_EARTH,
-                g: float = GRAV, H: float = H_MEAN, omega: float = OMEGA,
-                c_scaled: bool = False, coriolis: bool = True,
-                nquad=6, p3_variant: str = "equispaced",
-                keep_elem: bool = False) -> SWOperator:
-    """Assemble K, M_u, M_eta, <div,div> for the given mesh.
-
-    c_scaled=True uses c = sqrt(gH) on both coupling terms (test_cheby.py:30,38-42).
-    """
-    if c_scaled:
-        g = H = float(np.sqrt(g * H))
-    V, C = icosahedral_mesh(ref_level, radius)
-    nc = C.shape[0]
-
-    # geometry nodes per cell
-    if degree == 1:
-        geo = Lagrange(_REF_V.copy(), 1)
-        X = V[C]                                             # (C,3,3)
-    elif degree == 3:
-        nodes = p3_nodes(p3_variant)
-        geo = Lagrange(nodes, 3)
-        lin = Lagrange(_REF_V.copy(), 1).tab(nodes)          # (10,3) flat interpolation
-        X = np.einsum('an,cnd->cad', lin, V[C])
-        X *= (radius / np.linalg.norm(X, axis=2))[:, :, None]  # push out to the sphere
-    else:
-        raise ValueError("degree must be 1 or 3")
-
-    bdm = BDM2()
-    dg = Lagrange(_REF_V.copy(), 1)
-    nq_of = nquad if isinstance(nquad, dict) else {}
-    nq_default = nq_of.get("default", 6) if isinstance(nquad, dict) else nquad
-
-    def rule(term):
-        """Quadrature rule + geometry factors for one term of the form."""
-        qp, qw = duffy_quadrature(nq_of.get(term, nq_default))
-        gx, gy = geo.tab_grad(qp)                            # (nq,na)
-        J = np.stack([np.einsum('qa,cad->cqd', gx, X), np.einsum('qa,cad->cqd', gy, X)], axis=3)  # (C,nq,3,2)
-        G = np.einsum('cqdi,cqdj->cqij', J, J)
-        detJ = np.sqrt(G[..., 0, 0] * G[..., 1, 1] - G[..., 0, 1] ** 2)
-        Phi, dPhi = bdm.tab(qp)                              # (nq,12,2), (nq,12)
-        return qp, qw, G, detJ, Phi, dPhi, dg.tab(qp)
-
-    # <u,v>:  u = J u^/detJ  ->  u^T (J^T J) v^ / detJ
-    qp, qw, G, detJ, Phi, dPhi, Psi = rule("mu")
-    Mu_e = np.einsum('cq,qia,cqab,qjb->cij', qw[None, :] / detJ, Phi, G, Phi, optimize=True)
-    # <f k x u, v> = f (u^ x v^) / detJ * detJ
-    qp, qw, G, detJ, Phi, dPhi, Psi = rule("cor")
-    xq = np.einsum('qa,cad->cqd', geo.tab(qp), X)
-    fq = (2.0 * omega * xq[..., 2] / radius) if coriolis else np.zeros_like(detJ)
-    cross = Phi[:, None, :, 0] * Phi[:, :, None, 1] - Phi[:, None, :, 1] * Phi[:, :, None, 0]  # [q,i,j] = u_j x v_i
-    Cor_e = np.einsum('cq,qij->cij', qw[None, :] * fq, cross, optimize=True)
-    # <div u, div v> = div^ u^ div^ v^ / detJ
-    qp, qw, G, detJ, Phi, dPhi, Psi = rule("div")
-    Div_e = np.einsum('cq,qi,qj->cij', qw[None, :] / detJ, dPhi, dPhi, optimize=True)
-    # coupling terms: detJ cancels, exact on the reference cell
-    qp, qw = duffy_quadrature(4)
-    _, dPhi4 = bdm.tab(qp)
-    Psi4 = dg.tab(qp)
-    Kue = g * np.einsum('q,qi,qj->ij', qw, dPhi4, Psi4)      # (12,3)
-    Keu = -H * np.einsum('q,qi,qj->ij', qw, Psi4, dPhi4)     # (3,12)
-    qp, qw, G, detJ, Phi, dPhi, Psi = rule("meta")
-    Meta = np.einsum('q,cq,qi,qj->cij', qw, detJ, Psi, Psi, optimize=True)
-
-    # ---- global numbering: edges discovered in cell order, 3 dofs per edge then 3 interior
-    edge_id = {}
-    cell_dofs = np.empty((nc, 12), dtype=np.int64)
-    cell_sign = np.ones((nc, 12))
-    nxt = 0
-    k3 = np.arange(3)
-    for ci in range(nc):
-        cv = C[ci]
-        for e, (p, q) in enumerate(_LOCAL_EDGES):
-            a, b = int(cv[p]), int(cv[q])
-            key = (a, b) if a < b else (b, a)
-            base = edge_id.get(key)
-            if base is None:
-                base = nxt
-                edge_id[key] = base
-                nxt += 3
-            if a < b:
-                cell_dofs[ci, 3 * e:3 * e + 3] = base + k3
-            else:
-                cell_dofs[ci, 3 * e:3 * e + 3] = base + 2 - k3
-                cell_sign[ci, 3 * e:3 * e + 3] = -1.0
-        cell_dofs[ci, 9:12] = nxt + k3
-        nxt += 3
-    n_u = nxt
-    n_eta = 3 * nc
-    eta_dofs = np.arange(n_eta).reshape(nc, 3)
-
-    ss = cell_sign[:, :, None] * cell_sign[:, None, :]
-    rows = np.repeat(cell_dofs[:, :, None], 12, axis=2)
-    cols = np.repeat(cell_dofs[:, None, :], 12, axis=1)
-
-    def asm(vals, r, c, shape):
-        A = sp.coo_matrix((vals.ravel(), (r.ravel(), c.ravel())), shape=shape).tocsr()
-        A.sum_duplicates()
-        A.sort_indices()
-        return A
-
-    Mu = asm(Mu_e * ss, rows, cols, (n_u, n_u))
-    Ddiv = asm(Div_e * ss, rows, cols, (n_u, n_u))
-    Kuu = asm(-Cor_e * ss, rows, cols, (n_u, n_u))
-    r_ue = np.repeat(cell_dofs[:, :, None], 3, axis=2)
-    c_ue = np.repeat(eta_dofs[:, None, :], 12, axis=1)
-    Kue_g = asm(cell_sign[:, :, None] * Kue[None], r_ue, c_ue, (n_u, n_eta))
-    r_eu = np.repeat(eta_dofs[:, :, None], 12, axis=2)
-    c_eu = np.repeat(cell_dofs[:, None, :], 3, axis=1)
-    Keu_g = asm(cell_sign[:, None, :] * Keu[None], r_eu, c_eu, (n_eta, n_u))
-    K = sp.bmat([[Kuu, Kue_g], [Keu_g, None]], format="csr")
-    K.sort_indices()
-
-    eta_nodes = X[:, :3, :].copy()
-    op = SWOperator(ref_level=ref_level, degree=degree, n_u=n_u, n_eta=n_eta, n_cells=nc,
-                    K=K, Mu=Mu, Meta_blocks=Meta, Meta_inv_blocks=np.linalg.inv(Meta),
-                    Ddiv=Ddiv, cell_u_dofs=cell_dofs, cell_u_sign=cell_sign,
-                    eta_nodes=eta_nodes, g=g, H=H, radius=radius)
-    if keep_elem:
-        op.Mu_elem = Mu_e * ss
-        op.Kuu_elem = -Cor_e * ss
-        op.Kue_ref = Kue
-        op.Keu_ref = Keu
-    return op
-
-
-# ------------------------------------------------------------- spectral bound check
-def largest_imag_eig(op: SWOperator, k: int = 1, tol: float = 1e-12):
-    """Largest |imag| generalised eigenvalue of (K, M)  (L_eigs.py:44-58 recipe:
-    eps_gen_non_hermitian, eps_largest_imaginary).  K is skew in the (gH-weighted)
-    energy inner product, so lambda = i*omega and omega^2 is the largest eigenvalue
-    of the symmetric pencil (K^T M^-1 K, M) after c-scaling; here we work on
-    A = M^-1 K directly through A^2, which has real spectrum -omega^2.
-    """
-    from scipy.sparse.linalg import splu, LinearOperator, eigs
-    M = op.M().tocsc()
-    lu = splu(M)
-    K = op.K
-
-    def A2(v):
-        return lu.solve(K @ lu.solve(K @ v))
-
-    n = op.n
-    vals = eigs(LinearOperator((n, n), matvec=A2, dtype=np.float64), k=k, which="LM",
-                tol=tol, return_eigenvectors=False)
-    return np.sqrt(np.max(-vals.real))
-
-
-def test_pulse(op: SWOperator):
-    """x0 of test_cheby.py:73-75 / test_krylov.py:92-94: u=0, h=exp((x+y+z)/R) xyz/R^3."""
-    R = op.radius
-    eta = op.interpolate_eta(lambda x, y, z: np.exp((x + y + z) / R) * x * y * z / R ** 3)
-    return np.concatenate([np.zeros(op.n_u), eta])
+from krylov_exp_b200.assembly import *          # noqa: F401,F403
+from krylov_exp_b200.assembly import assemble_sw, test_pulse, largest_imag_eig, SWOperator  # noqa: F401
