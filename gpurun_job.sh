@@ -1,10 +1,10 @@
 set -x
 cd /root/repo
-export KEXP_NO_GRAPH=1
-python profiles/run_profile.py 5 64 > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/launches_r1.csv python profiles/run_profile.py 5 64 > gpurun_out/ncu1.log 2>&1
-tail -3 gpurun_out/plain.log
-python profiles/run_profile.py 5 64 > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'cg_update_xr|bsr3_spmm_kernel|cg_update_p' -s 300 -c 6 -o gpurun_out/prof_r1 python profiles/run_profile.py 5 64 > gpurun_out/ncu2.log 2>&1
-tail -3 gpurun_out/ncu2.log
-ls -la gpurun_out/
+timeout 900 python -m pytest tests/test_gpu_cheby.py -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench6.json 2> gpurun_out/bench6.err; echo rc=$?; tail -5 gpurun_out/bench6.err
+python - <<PY
+import json
+d=json.load(open('gpurun_out/bench6.json'))
+print(d['value'], d['config']['mass_solve'], d['gpu_launches'])
+for k,v in d['kernels'].items(): print(k, round(v['avg_us'],1), round(v['gbs'] or 0), round(v['share'],3), v['launches'])
+PY

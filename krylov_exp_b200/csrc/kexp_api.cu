@@ -31,15 +31,16 @@ void free_csr(DevCsr& d) {
 
 // CSR -> BSR(3x3) with 80-byte blocks {9 values row-major, block column in the low word of
 // the 10th double}.  Only kept when padding zeros cost < 40 % (BDM2/DG1 matrices: 0 %).
-static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v) {
+static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v, bool force) {
     if (nrows % 3 || ncols % 3 || nrows == 0) return 0;
     const char* env = getenv("KEXP_NO_BSR");
-    if (env && env[0] == '1') return 0;
+    if (!force && env && env[0] == '1') return 0;
     const int nbr = nrows / 3;
     std::vector<int> browptr((size_t)nbr + 1, 0);
     std::vector<double> blocks;
     blocks.reserve((size_t)(rp[nrows] / 9 + nbr) * 10);
     std::vector<int> cols;
+    int max_bpr = 1;
     for (int b = 0; b < nbr; ++b) {
         cols.clear();
         for (int k = rp[3 * b]; k < rp[3 * b + 3]; ++k) cols.push_back(ci[k] / 3);
@@ -57,18 +58,20 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
                 blocks[base + j * 10 + 3 * i + (ci[k] % 3)] += v[k];
             }
         browptr[b + 1] = browptr[b] + (int)cols.size();
+        max_bpr = std::max(max_bpr, (int)cols.size());
     }
     const int64_t nblocks = browptr[nbr];
-    if ((double)nblocks * 9.0 > 1.4 * (double)rp[nrows]) return 0;
+    if (!force && (double)nblocks * 9.0 > 1.4 * (double)rp[nrows]) return 0;
     KEXP_CUDA(cudaMalloc(&d.browptr, sizeof(int) * (size_t)(nbr + 1)));
     KEXP_CUDA(cudaMalloc(&d.blocks, sizeof(double) * 10 * (size_t)std::max<int64_t>(nblocks, 1)));
     KEXP_CUDA(cudaMemcpy(d.browptr, browptr.data(), sizeof(int) * (size_t)(nbr + 1), cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.blocks, blocks.data(), sizeof(double) * 10 * (size_t)nblocks, cudaMemcpyHostToDevice));
-    d.nbr = nbr; d.nblocks = nblocks;
+    d.nbr = nbr; d.nblocks = nblocks; d.max_bpr = max_bpr;
+    if (max_bpr > kSpmmSmemBlocks) { cudaFree(d.browptr); cudaFree(d.blocks); d.browptr = nullptr; d.blocks = nullptr; }
     return 0;
 }
 
-int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v) {
+int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v, bool force_bsr) {
     free_csr(d);
     d.nrows = nrows; d.ncols = ncols;
     if (nrows == 0 || rp == nullptr) { d.nrows = 0; return 0; }
@@ -81,7 +84,7 @@ int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp
     KEXP_CUDA(cudaMemcpy(d.rowptr, rp, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.col, ci, sizeof(int) * (size_t)d.nnz, cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.val, v, sizeof(double) * (size_t)d.nnz, cudaMemcpyHostToDevice));
-    return build_bsr3(ctx, d, nrows, ncols, rp, ci, v);
+    return build_bsr3(ctx, d, nrows, ncols, rp, ci, v, force_bsr);
 }
 
 }  // namespace kexp
@@ -92,12 +95,13 @@ namespace {
 struct CaptureStats { int64_t launches = 0; };
 
 template <typename K>
-int max_grid(kexp_ctx* ctx, K kernel) {
+int max_grid(kexp_ctx* ctx, K kernel, int dyn_smem = 0) {
     const void* key = (const void*)kernel;
     auto it = ctx->occ_cache.find(key);
     if (it != ctx->occ_cache.end()) return it->second;
+    if (dyn_smem > 0) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, dyn_smem);
     occ = std::max(1, std::min(occ, 8));
     int g = occ * ctx->num_sms;
     ctx->occ_cache[key] = g;
@@ -177,19 +181,23 @@ int ensure_stage(kexp_ctx* ctx, size_t bytes) {
 
 // Y = A X (MODE 0) or the CG product q = A p with the fused p.q reduction (MODE 1); BSR(3x3)
 // kernel when the matrix has that structure, generic CSR kernel otherwise.
+constexpr int kSpmmGB = 5;                 // gathered blocks in flight per block row
+constexpr int kCptVec = 2;                  // sample columns per thread in the streaming vector kernels
+
 template <int W, int MODE>
 void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
     constexpr int LPR = W / 2, RPW = 32 / LPR;
     if (A.bsr()) {
-        auto k = bsr3_spmm_kernel<W, MODE>;
-        constexpr int per_cta = (kThreads / 32) * BsrCfg<W>::BRW;
-        int grid = std::min(max_grid(ctx, k), std::max(1, (A.nbr + per_cta - 1) / per_cta));
-        k<<<grid, kThreads, 0, ctx->stream>>>(A.browptr, A.blocks, X, Y, A.nbr, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+        auto k = bsr3_spmm_kernel<W, MODE, kSpmmGB>;
+        constexpr int per_cta = PanelCfg<W, kSpmmCpt>::BPC;
+        int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
+        k<<<grid, kThreads, kSpmmSmemBytes, ctx->stream>>>(A.browptr, A.blocks, X, Y, A.nbr, A.max_bpr, ctx->T, ctx->d_Pinv,
+                                                               ctx->d_sc, ctx->d_partials, ctx->d_counter);
     } else {
-        auto k = spmm_kernel<W, MODE>;
+        // MODE 1 (the CG product) always has a BSR copy: n_s is a multiple of 3 by contract
+        auto k = csr_spmm_kernel<W>;
         int grid = std::min(max_grid(ctx, k), std::max(1, (A.nrows + RPW * 8 - 1) / (RPW * 8)));
-        if (MODE == 1) grid = std::min(grid, 2 * ctx->num_sms);
-        k<<<grid, kThreads, 0, ctx->stream>>>(A.rowptr, A.col, A.val, X, Y, A.nrows, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+        k<<<grid, kThreads, 0, ctx->stream>>>(A.rowptr, A.col, A.val, X, Y, A.nrows);
     }
 }
 
@@ -197,37 +205,31 @@ void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
 // leaves T (rows needing no solve), X (solved rows). W is a template parameter.
 template <int W>
 void enqueue_operator(kexp_ctx* ctx, const double* in) {
-    constexpr int LPR = W / 2;
+    constexpr int LPB = PanelCfg<W, kCptVec>::LPB;
     cudaStream_t s = ctx->stream;
     const int ns = (int)ctx->n_s;
-    const int red_grid = 2 * ctx->num_sms;      // reduction kernels: few, fat blocks keep the last-block sum short
+    const int red_grid = ctx->red_blocks_per_sm * ctx->num_sms;   // reduction kernels: few, fat blocks keep the last-block sum short
     {   // T = Kt * in
         TimedLaunch tl(ctx, KC_SPMM_K);
         launch_spmm<W, 0>(ctx, ctx->Kt, in, ctx->T);
     }
     const int ntri = ns / 3;
     {
-        auto k = cg_init_kernel<W>;
-        int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPR));
+        auto k = cg_init_kernel<W, kCptVec>;
+        int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
         TimedLaunch tl(ctx, KC_CG_INIT);
         k<<<grid, kThreads, 0, s>>>(ctx->T, ctx->X, ctx->P, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
     }
-    for (int it = 0; it < ctx->max_it; ++it) {
+    for (int it = 0; it < ctx->graph_its; ++it) {
         {
             TimedLaunch tl(ctx, KC_SPMM_CG);
             launch_spmm<W, 1>(ctx, ctx->As, ctx->P, ctx->Q);
         }
         {
-            auto k = cg_update_xr_kernel<W>;
-            int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPR));
+            auto k = cg_update_kernel<W, kCptVec>;
+            int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
             TimedLaunch tl(ctx, KC_CG_XR);
             k<<<grid, kThreads, 0, s>>>(ctx->X, ctx->T, ctx->P, ctx->Q, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
-        }
-        {
-            auto k = cg_update_p_kernel<W>;
-            int grid = std::min(max_grid(ctx, k), blocks_for(ntri, LPR));
-            TimedLaunch tl(ctx, KC_CG_P);
-            k<<<grid, kThreads, 0, s>>>(ctx->T, ctx->P, ctx->d_Pinv, ntri, ctx->d_sc);
         }
     }
     ctx->st_op_apps++;
@@ -238,18 +240,20 @@ void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep 
     constexpr int LPR = W / 2;
     cudaStream_t s = ctx->stream;
     const int ns = (int)ctx->n_s, nb = (int)ctx->n_b, nd = (int)ctx->n_d;
+    ChebStep st2 = st;
+    st2.check_cg = 0;
     {
         auto k = cheb_update_kernel<W, 0>;
         int grid = std::min(max_grid(ctx, k), blocks_for(ns, LPR));
         TimedLaunch tl(ctx, KC_CHEB);
-        k<<<grid, kThreads, 0, s>>>(ctx->X, nullptr, nullptr, nullptr, nullptr, nullptr, S, ctx->Y, ns, coef, ctx->d_tscale, st);
+        k<<<grid, kThreads, 0, s>>>(ctx->X, nullptr, nullptr, nullptr, nullptr, nullptr, S, ctx->Y, ns, coef, ctx->d_tscale, st, ctx->d_sc);
     }
     if (nb > 0) {
         auto k = cheb_update_kernel<W, 1>;
         int grid = std::min(max_grid(ctx, k), blocks_for(nb, LPR));
         const size_t o = (size_t)ns * W;
         TimedLaunch tl(ctx, KC_CHEB);
-        k<<<grid, kThreads, 0, s>>>(ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, S + o, ctx->Y + o, nb, coef, ctx->d_tscale, st);
+        k<<<grid, kThreads, 0, s>>>(ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, S + o, ctx->Y + o, nb, coef, ctx->d_tscale, st2, ctx->d_sc);
     }
     if (nd > 0) {
         const size_t o = (size_t)(ns + nb) * W;
@@ -257,11 +261,11 @@ void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep 
         if (ctx->d_Dblk) {
             auto k = cheb_update_kernel<W, 2>;
             int grid = std::min(max_grid(ctx, k), blocks_for(nd / 3, LPR));
-            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st);
+            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
         } else {
             auto k = cheb_update_kernel<W, 0>;
             int grid = std::min(max_grid(ctx, k), blocks_for(nd, LPR));
-            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st);
+            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
         }
     }
 }
@@ -305,7 +309,7 @@ void enqueue_cheby(kexp_ctx* ctx, int id) {
         double* Sn = (n & 1) ? ctx->S1 : ctx->S0;           // holds S_{n-2}, becomes S_n
         enqueue_operator<W>(ctx, in);
         ChebStep st;
-        st.n = n; st.has_old = (n >= 2) ? 1 : 0; st.cs = (n == 1) ? 1.0 : 2.0;
+        st.n = n; st.has_old = (n >= 2) ? 1 : 0; st.cs = (n == 1) ? 1.0 : 2.0; st.check_cg = 1;
         enqueue_cheb_update<W>(ctx, Sn, tb.d_coef, st);
     }
 }
@@ -345,7 +349,7 @@ int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
     KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
     const ChebTable& tb = ctx->cheb[id];
     ctx->st_op_apps += tb.ncheb;
-    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + 3 * ctx->max_it + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
+    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + 2 * ctx->graph_its + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
     return 0;
 }
 
@@ -358,9 +362,9 @@ void invalidate_graphs(kexp_ctx* ctx) {
 // occupancy queries must not happen during capture: touch every kernel once
 template <int W>
 void warm_occupancy(kexp_ctx* ctx) {
-    max_grid(ctx, spmm_kernel<W, 0>); max_grid(ctx, spmm_kernel<W, 1>);
-    max_grid(ctx, bsr3_spmm_kernel<W, 0>); max_grid(ctx, bsr3_spmm_kernel<W, 1>);
-    max_grid(ctx, cg_init_kernel<W>); max_grid(ctx, cg_update_xr_kernel<W>); max_grid(ctx, cg_update_p_kernel<W>);
+    max_grid(ctx, csr_spmm_kernel<W>);
+    max_grid(ctx, bsr3_spmm_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_spmm_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
+    max_grid(ctx, cg_init_kernel<W, kCptVec>); max_grid(ctx, cg_update_kernel<W, kCptVec>);
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
 }
 
@@ -463,9 +467,10 @@ int kexp_create(kexp_ctx** out, int device) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_sc, sizeof(CgScalars)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_sc, 0, sizeof(CgScalars)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_partials, sizeof(double) * 2 * 8 * (size_t)ctx->num_sms * kMaxW) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_counter, sizeof(unsigned)) == cudaSuccess;
-    ok = ok && cudaMemset(ctx->d_counter, 0, sizeof(unsigned)) == cudaSuccess;
+    // block partials (3 accumulators x up to 8 blocks/SM) + group partials, and the tickets
+    ok = ok && cudaMalloc(&ctx->d_partials, sizeof(double) * 3 * 9 * (size_t)ctx->num_sms * kMaxW + 4096) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counter, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_counter, 0, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_tscale, sizeof(double) * kMaxW) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_w, sizeof(double) * kMaxW) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_pin, sizeof(double) * 2 * kMaxW) == cudaSuccess;
@@ -473,6 +478,10 @@ int kexp_create(kexp_ctx** out, int device) {
     if (!ok) { kexp_destroy(ctx); return 6; }
     const char* g = getenv("KEXP_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
+    const char* rb = getenv("KEXP_RED_BLOCKS");
+    if (rb && atoi(rb) >= 1 && atoi(rb) <= 8) ctx->red_blocks_per_sm = atoi(rb);
+    const char* ad = getenv("KEXP_ADAPTIVE_ITS");
+    if (ad && ad[0] == '0') ctx->adaptive_its = false;
     if (kexp_set_mass_solver(ctx, 1e-12, 60, 3)) { kexp_destroy(ctx); return 7; }
     *out = ctx;
     return 0;
@@ -558,9 +567,10 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
     ctx->have_op = false;
     ctx->n = n; ctx->n_s = n_s; ctx->n_b = n_b; ctx->n_d = n_d;
     ctx->curW = 0;   // panels are re-allocated for the new size
-    if (upload_csr(ctx, ctx->Kt, (int)n, (int)n, Kt_rowptr, Kt_col, Kt_val)) return 1;
-    if (upload_csr(ctx, ctx->As, (int)n_s, (int)n_s, As_rowptr, As_col, As_val)) return 1;
-    if (upload_csr(ctx, ctx->Rt, (int)n_b, (int)n_s, n_b ? Rt_rowptr : nullptr, Rt_col, Rt_val)) return 1;
+    if (upload_csr(ctx, ctx->Kt, (int)n, (int)n, Kt_rowptr, Kt_col, Kt_val, false)) return 1;
+    if (upload_csr(ctx, ctx->As, (int)n_s, (int)n_s, As_rowptr, As_col, As_val, true)) return 1;
+    if (!ctx->As.bsr()) return kexp::fail(ctx, "mass matrix could not be stored as 3x3 blocks");
+    if (upload_csr(ctx, ctx->Rt, (int)n_b, (int)n_s, n_b ? Rt_rowptr : nullptr, Rt_col, Rt_val, false)) return 1;
     ctx->h_As_rowptr.assign(As_rowptr, As_rowptr + n_s + 1);
     ctx->h_As_col.assign(As_col, As_col + As_rowptr[n_s]);
     ctx->h_As_val.assign(As_val, As_val + As_rowptr[n_s]);
@@ -612,6 +622,7 @@ int kexp_set_mass_solver(kexp_ctx* ctx, double rtol, int max_it, int precond) {
     invalidate_graphs(ctx);
     const bool rebuild = ctx->have_op && precond != ctx->precond;
     ctx->rtol = rtol; ctx->max_it = max_it; ctx->precond = precond;
+    ctx->graph_its = max_it; ctx->its_tuned = false;
     if (rebuild) {
         std::vector<double> Pinv;
         if (build_block_jacobi(ctx, ctx->n_s, ctx->h_As_rowptr.data(), ctx->h_As_col.data(), ctx->h_As_val.data(), precond, Pinv)) return 1;
@@ -718,10 +729,39 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
     return 0;
 }
 
+// The CG loop inside the graph has a fixed number of early-exit iterations.  After the
+// first apply it is trimmed to the observed maximum + 2; every apply then checks (one
+// 8-byte read-back) that no solve ran into the trimmed cap and otherwise repeats itself
+// with the full max_it.
+static int read_cg_counters(kexp_ctx* ctx, int* max_iters, int* unconverged) {
+    int h[2];
+    KEXP_CUDA(cudaMemcpyAsync(h, &ctx->d_sc->max_iters, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    *max_iters = h[0]; *unconverged = h[1];
+    return 0;
+}
+
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t) {
     if (!ctx) return 1;
     if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
     if (ctx->timing) drain_events(ctx);
+    if (!ctx->adaptive_its) return 0;
+    int mx = 0, unc = 0;
+    if (read_cg_counters(ctx, &mx, &unc)) return 1;
+    if (unc > ctx->unconverged_seen && ctx->graph_its < ctx->max_it) {
+        // a solve hit the trimmed cap: fall back to the full cap and redo this apply
+        ctx->graph_its = ctx->max_it;
+        ctx->its_tuned = true;              // do not trim again
+        invalidate_graphs(ctx);
+        if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
+        if (ctx->timing) drain_events(ctx);
+        if (read_cg_counters(ctx, &mx, &unc)) return 1;
+    } else if (!ctx->its_tuned && mx > 0) {
+        const int want = std::min(ctx->max_it, mx + 2);
+        if (want < ctx->graph_its) { ctx->graph_its = want; invalidate_graphs(ctx); }
+        ctx->its_tuned = true;
+    }
+    ctx->unconverged_seen = unc;
     return 0;
 }
 

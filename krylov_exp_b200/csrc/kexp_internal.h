@@ -22,6 +22,7 @@ struct DevCsr {
     int* browptr = nullptr;
     double* blocks = nullptr;
     int nbr = 0;
+    int max_bpr = 1;               // most blocks in any block row
     int64_t nblocks = 0;
     bool bsr() const { return blocks != nullptr; }
     double bytes() const {
@@ -69,6 +70,11 @@ struct kexp_ctx {
     double rtol = 1e-12;
     int max_it = 60;
     int precond = 3;
+    int graph_its = 60;            // CG iterations captured per solve (trimmed adaptively, see kexp_cheby_apply_dev)
+    bool its_tuned = false;
+    bool adaptive_its = true;
+    int unconverged_seen = 0;
+    int red_blocks_per_sm = 4;     // grid of the reduction kernels
 
     kexp::ChebTable cheb[KEXP_MAX_CHEBY];
 
@@ -123,7 +129,7 @@ struct kexp_batch {
 
 namespace kexp {
 int fail(kexp_ctx* ctx, const std::string& msg);
-int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v);
+int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp, const int32_t* ci, const double* v, bool force_bsr = false);
 void free_csr(DevCsr& d);
 int pick_W(int B);
 void krylov_free(kexp_ctx* ctx);

@@ -1,12 +1,11 @@
 // kexp_kernels.cuh -- device kernels of the batched Chebyshev exp(sL)v path (sm_100a).
 //
 // Data layout in HBM: a batch "panel" is a row-major [rows][W] array of doubles, W in
-// {2,4,8,16,32,64} sample columns contiguous per dof ("batch-minor").  A group of
-// LPR = W/2 lanes owns one row and each lane one double2 (two sample columns), so a
-// gathered row X[col,:] is one fully coalesced W*8-byte segment (512 B at W = 64) and
-// every matrix entry is used for W columns.  All reductions are two-stage and
-// fixed-order (warp shuffles -> shared memory -> per-block partials -> last block), so
-// results are bit-reproducible for a given panel width and grid.
+// {2,4,8,16,32,64} sample columns contiguous per dof ("batch-minor").  A gathered row
+// X[col,:] is one fully coalesced W*8-byte segment (512 B at W = 64) and every matrix
+// entry is used for W columns.  All reductions are two-stage and fixed-order (warp
+// shuffles -> shared memory -> per-block partials -> last block), so results are
+// bit-reproducible for a given panel width and grid.
 //
 // Reference semantics implemented here (file:line in /root/reference):
 //   operator_solver.solve()  averaged_sw_explicit.py:142-164   -> spmm + batched PCG
@@ -23,7 +22,7 @@ constexpr int kMaxW = 64;
 
 // Per-panel CG scalars, one slot per sample column (device memory).
 struct CgScalars {
-    double rz[kMaxW];      // r . P^-1 r
+    double rz[kMaxW];      // r . P^-1 r of the current residual (measured, not recurred)
     double pq[kMaxW];      // p . A p
     double alpha[kMaxW];
     double beta[kMaxW];
@@ -32,6 +31,8 @@ struct CgScalars {
     int active[kMaxW];     // column still iterating
     int done;              // all columns converged: remaining CG kernels of the graph return at once
     int iters;             // iterations of the current solve
+    int max_iters;         // largest iteration count of any solve since reset
+    int unconverged;       // solves that hit the iteration cap since reset
     unsigned long long total_iters;
     unsigned long long total_solves;
     double max_rel_res;    // of the last solve
@@ -40,79 +41,123 @@ struct CgScalars {
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
-// streaming variants: vectors that are touched once per kernel should not evict the
-// matrix / gathered rows from L1
+// streaming variant: vectors that are touched once per kernel should not displace the
+// gathered rows / matrix blocks in L1
 __device__ __forceinline__ double2 ld2_stream(const double* p) {
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
+    return __ldcs(reinterpret_cast<const double2*>(p));     // ld.global.cs: evict-first
 }
 
-// Sum over the rows handled by one warp (lanes with equal lane % LPR), fixed order.
-template <int LPR>
-__device__ __forceinline__ double2 warp_reduce_rows(double2 v) {
-#pragma unroll
-    for (int off = 16; off >= LPR; off >>= 1) {
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
-        v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
-    }
-    return v;
-}
+// Thread -> column mapping shared by all panel kernels: a group of LPB lanes owns one row
+// block (3 rows: one mesh entity) and each lane CPT = min(W, CPTMAX) sample columns as
+// NV = CPT/2 double2 values; lane l holds column pairs l + LPB*j, so for fixed j the group
+// reads one contiguous LPB*16-byte segment.
+template <int W, int CPTMAX>
+struct PanelCfg {
+    static constexpr int CPT = (W >= CPTMAX) ? CPTMAX : W;
+    static constexpr int LPB = W / CPT;            // lanes per row block
+    static constexpr int BRW = 32 / LPB;           // row blocks per warp
+    static constexpr int NV = CPT / 2;             // double2 per row per thread
+    static constexpr int BPC = (kThreads / 32) * BRW;   // row blocks per CTA pass
+};
 
-// Block partial of NACC per-thread double2 accumulators -> partials[(a*grid + block)*W + col].
-// Returns true in the last block to arrive (which may then read all partials).
-template <int W, int NACC>
-__device__ __forceinline__ bool block_partials(double2 (&acc)[NACC], double* __restrict__ partials,
-                                               unsigned* __restrict__ counter) {
-    constexpr int LPR = W / 2;
-    __shared__ double2 sh[NACC][kThreads / 32][32];
-    __shared__ bool s_last;
+// Deterministic grid-wide column sums in two ticketed levels.
+// Level 1: every block writes its partial; the last block of each group of kGroup
+// consecutive blocks adds the group's partials (fixed order) into a group partial.
+// Level 2: the last group to finish returns true; that block then adds the group partials
+// (final_sums).  The serial tail after the last block is ~gridDim/kGroup values per
+// column instead of gridDim.
+// Layout: partials[0 .. NACC*G*W) block partials, then NACC*NG*W group partials;
+// counters[0] = level-2 ticket, counters[1 + g] = level-1 ticket of group g.
+constexpr int kGroup = 8;
+
+template <int W, int CPTMAX, int NACC>
+__device__ __forceinline__ bool block_partials(double2 (&acc)[NACC][PanelCfg<W, CPTMAX>::NV],
+                                               double* __restrict__ partials, unsigned* __restrict__ counters) {
+    using C = PanelCfg<W, CPTMAX>;
+    constexpr int LPB = C::LPB, NV = C::NV;
+    __shared__ double2 sh[NACC][kThreads / 32][W / 2];
+    __shared__ bool s_flag;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % LPB;
+    const int G = gridDim.x, NG = (G + kGroup - 1) / kGroup;
+    const int grp = blockIdx.x / kGroup;
+    const int gsize = min(kGroup, G - grp * kGroup);
+    double* gpart = partials + (size_t)NACC * G * W;
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) {
-        double2 v = warp_reduce_rows<LPR>(acc[a]);
-        if (lane < LPR) sh[a][warp][lane] = v;
-    }
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            double2 v = acc[a][j];
+#pragma unroll
+            for (int off = 16; off >= LPB; off >>= 1) {
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+                v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+            }
+            if (lane < LPB) sh[a][warp][l + LPB * j] = v;
+        }
     __syncthreads();
-    if (threadIdx.x < LPR * NACC) {
-        const int a = threadIdx.x / LPR, l = threadIdx.x % LPR;
-        double2 s = sh[a][0][l];
+    for (int e = threadIdx.x; e < NACC * (W / 2); e += kThreads) {
+        const int a = e / (W / 2), cp = e % (W / 2);
+        double2 s = sh[a][0][cp];
 #pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w) { s.x += sh[a][w][l].x; s.y += sh[a][w][l].y; }
-        st2(partials + ((size_t)a * gridDim.x + blockIdx.x) * W + 2 * l, s);
+        for (int w = 1; w < kThreads / 32; ++w) { s.x += sh[a][w][cp].x; s.y += sh[a][w][cp].y; }
+        st2(partials + ((size_t)a * G + blockIdx.x) * W + 2 * cp, s);
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned ticket = atomicAdd(counter, 1u);
-        s_last = (ticket == gridDim.x - 1);
-        if (s_last) *counter = 0;          // ready for the next launch
+        const unsigned ticket = atomicAdd(counters + 1 + grp, 1u);
+        s_flag = (ticket == (unsigned)gsize - 1u);
+        if (s_flag) counters[1 + grp] = 0;      // ready for the next launch
     }
     __syncthreads();
-    if (s_last) __threadfence();
-    return s_last;
+    if (!s_flag) return false;
+    __threadfence();
+    for (int e = threadIdx.x; e < NACC * W; e += kThreads) {
+        const int a = e / W, c = e % W;
+        const double* base = partials + ((size_t)a * G + (size_t)grp * kGroup) * W + c;
+        double v[kGroup];
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) v[u] = (u < gsize) ? __ldcg(base + (size_t)u * W) : 0.0;
+        double s = v[0];
+#pragma unroll
+        for (int u = 1; u < kGroup; ++u) s += v[u];
+        gpart[((size_t)a * NG + grp) * W + c] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(counters, 1u);
+        s_flag = (ticket == (unsigned)NG - 1u);
+        if (s_flag) counters[0] = 0;
+    }
+    __syncthreads();
+    if (s_flag) __threadfence();
+    return s_flag;
 }
 
-// Last block: column sums of the per-block partials in fixed order. Result for column c
-// of accumulator a is returned to threads with threadIdx.x == c (c < W) through `out`.
+// Last block: column sums of the group partials in fixed order.  The sum for column c of
+// accumulator a is returned to the thread with threadIdx.x == c (c < W).
 template <int W, int NACC>
 __device__ __forceinline__ void final_sums(const double* __restrict__ partials, double (&out)[NACC]) {
     constexpr int NSPLIT = kThreads / W;
     __shared__ double red[NACC][NSPLIT][W];
     const int c = threadIdx.x % W, part = threadIdx.x / W;
+    const int G = gridDim.x, NG = (G + kGroup - 1) / kGroup;
+    const double* gpart = partials + (size_t)NACC * G * W;
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
         double s = 0.0;
-        const double* base = partials + (size_t)a * gridDim.x * W + c;
+        const double* base = gpart + (size_t)a * NG * W + c;
         int b = part;
-        for (; b + 7 * NSPLIT < (int)gridDim.x; b += 8 * NSPLIT) {   // 8 loads in flight, summed in order
+        for (; b + 7 * NSPLIT < NG; b += 8 * NSPLIT) {   // 8 loads in flight, summed in order
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + (size_t)(b + u * NSPLIT) * W);
 #pragma unroll
             for (int u = 0; u < 8; ++u) s += v[u];
         }
-        for (; b < (int)gridDim.x; b += NSPLIT) s += __ldcg(base + (size_t)b * W);
+        for (; b < NG; b += NSPLIT) s += __ldcg(base + (size_t)b * W);
         red[a][part][c] = s;
     }
     __syncthreads();
@@ -128,25 +173,19 @@ __device__ __forceinline__ void final_sums(const double* __restrict__ partials, 
 }
 
 // ------------------------------------------------------------------------------------
-// CSR SpMM  Y[r,:] = sum_k val[k] * X[col[k],:]   for r in [0,nrows)
-// One LPR-lane group per row; the group loads up to 32 (col,val) pairs of the warp's rows
-// cooperatively and broadcasts them with shuffles; X rows are gathered as double2.
-// MODE 0: plain.  MODE 1 (CG): also accumulates p.q per column, the last block turns the
-// partials into pq and alpha = rz/pq  (the dot product fused into the SpMM epilogue).
+// Generic CSR SpMM  Y[r,:] = sum_k val[k] * X[col[k],:]   (matrices without the 3x3 entity
+// structure).  One W/2-lane group per row; the group loads (col,val) pairs cooperatively
+// and broadcasts them with shuffles; X rows are gathered as double2.
 // ------------------------------------------------------------------------------------
-template <int W, int MODE>
+template <int W>
 __global__ void __launch_bounds__(kThreads)
-spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-            const double* __restrict__ X, double* __restrict__ Y, int nrows,
-            CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
+csr_spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                const double* __restrict__ X, double* __restrict__ Y, int nrows) {
     constexpr int LPR = W / 2, RPW = 32 / LPR;
-    if (MODE == 1 && sc->done) return;
     const int lane = threadIdx.x & 31;
     const int l = lane % LPR, sub = lane / LPR;
     const int gwarp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kThreads) >> 5;
-    double2 dot[1] = {make_double2(0.0, 0.0)};
-
     for (int rowbase = gwarp * RPW; rowbase < nrows; rowbase += nwarps * RPW) {
         const int r = rowbase + sub;
         int k0 = 0, k1 = 0;
@@ -160,40 +199,27 @@ spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const d
             int cc = 0; double aa = 0.0;
             if (kb + l < len) { cc = __ldg(col + kk); aa = __ldg(val + kk); }
             const int cnt = min(LPR, maxlen - kb);
-            if (cnt == LPR) {
-#pragma unroll
-                for (int j = 0; j < LPR; ++j) {
-                    const int c = __shfl_sync(0xffffffffu, cc, j, LPR);
-                    const double a = __shfl_sync(0xffffffffu, aa, j, LPR);
-                    const double2 x = ld2(X + (size_t)c * W + 2 * l);
-                    acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y);
-                }
-            } else {
-                for (int j = 0; j < cnt; ++j) {
-                    const int c = __shfl_sync(0xffffffffu, cc, j, LPR);
-                    const double a = __shfl_sync(0xffffffffu, aa, j, LPR);
-                    const double2 x = ld2(X + (size_t)c * W + 2 * l);
-                    acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y);
-                }
+            for (int j = 0; j < cnt; ++j) {
+                const int c = __shfl_sync(0xffffffffu, cc, j, LPR);
+                const double a = __shfl_sync(0xffffffffu, aa, j, LPR);
+                const double2 x = ld2(X + (size_t)c * W + 2 * l);
+                acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y);
             }
         }
-        if (r < nrows) {
-            st2(Y + (size_t)r * W + 2 * l, acc);
-            if (MODE == 1) {
-                const double2 p = ld2(X + (size_t)r * W + 2 * l);
-                dot[0].x = fma(p.x, acc.x, dot[0].x); dot[0].y = fma(p.y, acc.y, dot[0].y);
-            }
-        }
+        if (r < nrows) st2(Y + (size_t)r * W + 2 * l, acc);
     }
-    if (MODE == 1) {
-        if (block_partials<W, 1>(dot, partials, counter)) {
-            double s[1];
-            final_sums<W, 1>(partials, s);
-            if (threadIdx.x < W) {
-                const int c = threadIdx.x;
-                sc->pq[c] = s[0];
-                sc->alpha[c] = (sc->active[c] && s[0] > 0.0) ? sc->rz[c] / s[0] : 0.0;
-            }
+}
+
+// 3x3 block (row-major, 9 doubles) times three rows of NV double2 values
+template <int NV>
+__device__ __forceinline__ void blk3_mul(const double* __restrict__ B, const double2 (&r)[3][NV], double2 (&z)[3][NV]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double b0 = __ldg(B + 3 * i), b1 = __ldg(B + 3 * i + 1), b2 = __ldg(B + 3 * i + 2);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            z[i][j].x = fma(b0, r[0][j].x, fma(b1, r[1][j].x, b2 * r[2][j].x));
+            z[i][j].y = fma(b0, r[0][j].y, fma(b1, r[1][j].y, b2 * r[2][j].y));
         }
     }
 }
@@ -201,166 +227,175 @@ spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const d
 // ------------------------------------------------------------------------------------
 // BSR(3x3) SpMM -- the layout BDM2/DG1 matrices have naturally (3 dofs per mesh entity).
 // A block is 80 bytes: 9 values row-major + the block-column index in the low word of the
-// 10th double, so one block is five aligned 16-byte broadcast loads.  A group of LPB lanes
-// owns one block row (3 output rows) and each lane CPT = min(W,8) sample columns: every
-// gathered X value feeds 3 FMAs and every matrix value 8, which takes the L1/shared-memory
-// data path off the critical path.  Each CTA walks a CONTIGUOUS range of block rows so the
-// gathered rows of neighbouring mesh entities are re-used out of L1 instead of L2.
-// MODE as in spmm_kernel.
+// 10th double.  Each CTA owns a CONTIGUOUS range of block rows; the blocks of that range
+// are contiguous too and are staged in shared memory first (one coalesced pass), so the
+// per-row work has a short dependency chain: block columns from shared memory -> ALL
+// gathered X rows of up to GB blocks issued at once (plus the row's own p and r in the CG
+// product) -> FMAs with matrix values broadcast from shared memory.  A group of W/2 lanes
+// owns a block row and each lane one double2 (two sample columns), so a gathered row is
+// one coalesced W*8-byte segment and neighbouring mesh entities re-use rows out of L1.
+//
+// MODE 0: Y = A X.
+// MODE 1: the CG product q = A p with the WHOLE scalar work of the iteration fused into
+//   the epilogue.  The group that owns a block row also owns its 3x3 block-Jacobi block,
+//   so it can form, per column,   pq = p.q,   qz = q.P^-1 r,   qPq = q.P^-1 q.
+//   The last block turns the partials into
+//       alpha = rz/pq,   rz' = rz - 2 alpha qz + alpha^2 qPq,   beta = rz'/rz
+//   (rz' is r'.P^-1 r' for r' = r - alpha q, exactly), so a single vector kernel can do
+//   x, r, z and p afterwards: two kernels and two grid-wide reductions per iteration
+//   instead of three.  rz itself is re-measured by that vector kernel every iteration,
+//   so the predicted value is only ever used for one beta and errors do not accumulate.
 // ------------------------------------------------------------------------------------
-template <int W>
-struct BsrCfg {
-    static constexpr int CPT = (W >= 8) ? 8 : W;   // sample columns per thread
-    static constexpr int LPB = W / CPT;            // lanes per block row
-    static constexpr int BRW = 32 / LPB;           // block rows per warp
-    static constexpr int NV = CPT / 2;             // double2 per row per thread
-};
+constexpr int kSpmmSmemBlocks = 520;      // 41 600 B of staged matrix blocks per CTA
+constexpr int kSpmmSmemRows = 128;        // block rows per staged sub-chunk (row pointers + 3x3 preconditioner blocks)
+constexpr int kSpmmSmemBytes = kSpmmSmemBlocks * 80 + kSpmmSmemRows * 72 + (kSpmmSmemRows + 4) * 4;
+constexpr int kSpmmCpt = 2;               // PanelCfg CPTMAX of the SpMM (one double2 per lane)
 
-template <int W, int MODE>
+template <int W, int MODE, int GB>
 __global__ void __launch_bounds__(kThreads, 2)
 bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
-                 const double* __restrict__ X, double* __restrict__ Y, int nbr,
+                 const double* __restrict__ X, double* __restrict__ Y, int nbr, int max_bpr,
+                 const double* __restrict__ R, const double* __restrict__ Pinv,
                  CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
-    using C = BsrCfg<W>;
-    constexpr int LPB = C::LPB, BRW = C::BRW, NV = C::NV;
+    using C = PanelCfg<W, kSpmmCpt>;
+    constexpr int LPB = C::LPB, BRW = C::BRW;
+    extern __shared__ double2 sblk[];        // 5 double2 per staged block
+    double* sP = reinterpret_cast<double*>(sblk + 5 * kSpmmSmemBlocks);          // 9 doubles per staged block row
+    int* sptr = reinterpret_cast<int*>(sP + 9 * kSpmmSmemRows);                  // row pointers relative to the sub-chunk
     if (MODE == 1 && sc->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane % LPB, g = lane / LPB;
     const int per = nbr / gridDim.x, rem = nbr % gridDim.x;
     const int start = blockIdx.x * per + min((int)blockIdx.x, rem);
     const int end = start + per + ((int)blockIdx.x < rem ? 1 : 0);
-    double2 dot[NV];
-#pragma unroll
-    for (int j = 0; j < NV; ++j) dot[j] = make_double2(0.0, 0.0);
+    const int rows_sub = max(1, min(kSpmmSmemRows, kSpmmSmemBlocks / max_bpr));
+    double2 dot[3][1] = {{make_double2(0.0, 0.0)}, {make_double2(0.0, 0.0)}, {make_double2(0.0, 0.0)}};
 
-    for (int base = start; base < end; base += (kThreads / 32) * BRW) {
-        const int br = base + warp * BRW + g;
-        if (br < end) {
-            double2 acc[3][NV];
+    for (int sub = start; sub < end; sub += rows_sub) {
+        const int sub_end = min(sub + rows_sub, end);
+        const int kb0 = __ldg(browptr + sub), kb1 = __ldg(browptr + sub_end);
+        const double2* gsrc = reinterpret_cast<const double2*>(blocks) + (size_t)5 * kb0;
+        for (int i = threadIdx.x; i < 5 * (kb1 - kb0); i += kThreads) sblk[i] = __ldg(gsrc + i);
+        for (int i = threadIdx.x; i <= sub_end - sub; i += kThreads) sptr[i] = __ldg(browptr + sub + i) - kb0;
+        if (MODE == 1)
+            for (int i = threadIdx.x; i < 9 * (sub_end - sub); i += kThreads) sP[i] = __ldg(Pinv + (size_t)9 * sub + i);
+        __syncthreads();
+        for (int base = sub; base < sub_end; base += C::BPC) {
+            const int br = base + warp * BRW + g;
+            if (br < sub_end) {
+                const int k0 = sptr[br - sub], k1 = sptr[br - sub + 1];
+                const size_t o = (size_t)(3 * br) * W + 2 * l;
+                double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+                double2 pv[3], rv[3];
+                if (MODE == 1) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+                    for (int i = 0; i < 3; ++i) { pv[i] = ld2(X + o + (size_t)i * W); rv[i] = ld2_stream(R + o + (size_t)i * W); }
+                }
+                for (int kg = k0; kg < k1; kg += GB) {
+                    double2 x[GB][3];
 #pragma unroll
-                for (int j = 0; j < NV; ++j) acc[i][j] = make_double2(0.0, 0.0);
-            const int k0 = __ldg(browptr + br), k1 = __ldg(browptr + br + 1);
-            for (int k = k0; k < k1; ++k) {
-                const double2* bp = reinterpret_cast<const double2*>(blocks + (size_t)10 * k);
-                const double2 v01 = __ldg(bp), v23 = __ldg(bp + 1), v45 = __ldg(bp + 2), v67 = __ldg(bp + 3), v8c = __ldg(bp + 4);
-                const int c = __double2loint(v8c.y);
-                const double a[3][3] = {{v01.x, v01.y, v23.x}, {v23.y, v45.x, v45.y}, {v67.x, v67.y, v8c.x}};
-                const double* xr = X + (size_t)(3 * c) * W + 2 * l;
+                    for (int j = 0; j < GB; ++j) {
+                        if (kg + j < k1) {
+                            const int c = __double2loint(sblk[5 * (kg + j) + 4].y);
+                            const double* xr = X + (size_t)(3 * c) * W + 2 * l;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    double2 x[NV];
-#pragma unroll
-                    for (int j = 0; j < NV; ++j) x[j] = ld2(xr + (size_t)r * W + 2 * LPB * j);
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < NV; ++j) {
-                            acc[i][j].x = fma(a[i][r], x[j].x, acc[i][j].x);
-                            acc[i][j].y = fma(a[i][r], x[j].y, acc[i][j].y);
+                            for (int r = 0; r < 3; ++r) x[j][r] = ld2(xr + (size_t)r * W);
                         }
+                    }
+#pragma unroll
+                    for (int j = 0; j < GB; ++j) {
+                        if (kg + j < k1) {
+                            const double2* bp = sblk + 5 * (kg + j);
+                            const double2 v01 = bp[0], v23 = bp[1], v45 = bp[2], v67 = bp[3], v8c = bp[4];
+                            const double a[3][3] = {{v01.x, v01.y, v23.x}, {v23.y, v45.x, v45.y}, {v67.x, v67.y, v8c.x}};
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    acc[i].x = fma(a[i][r], x[j][r].x, acc[i].x);
+                                    acc[i].y = fma(a[i][r], x[j][r].y, acc[i].y);
+                                }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) st2(Y + o + (size_t)i * W, acc[i]);
+                if (MODE == 1) {
+                    const double* Pb = sP + 9 * (br - sub);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const double b0 = Pb[3 * i], b1 = Pb[3 * i + 1], b2 = Pb[3 * i + 2];
+                        double2 Pq;     // row i of P^-1 q
+                        Pq.x = fma(b0, acc[0].x, fma(b1, acc[1].x, b2 * acc[2].x));
+                        Pq.y = fma(b0, acc[0].y, fma(b1, acc[1].y, b2 * acc[2].y));
+                        dot[0][0].x = fma(pv[i].x, acc[i].x, dot[0][0].x); dot[0][0].y = fma(pv[i].y, acc[i].y, dot[0][0].y);
+                        dot[1][0].x = fma(Pq.x, rv[i].x, dot[1][0].x);     dot[1][0].y = fma(Pq.y, rv[i].y, dot[1][0].y);
+                        dot[2][0].x = fma(Pq.x, acc[i].x, dot[2][0].x);    dot[2][0].y = fma(Pq.y, acc[i].y, dot[2][0].y);
+                    }
                 }
             }
-            double* yr = Y + (size_t)(3 * br) * W + 2 * l;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < NV; ++j) st2(yr + (size_t)i * W + 2 * LPB * j, acc[i][j]);
-            if (MODE == 1) {
-                const double* pr = X + (size_t)(3 * br) * W + 2 * l;
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < NV; ++j) {
-                        const double2 p = ld2(pr + (size_t)i * W + 2 * LPB * j);
-                        dot[j].x = fma(p.x, acc[i][j].x, dot[j].x);
-                        dot[j].y = fma(p.y, acc[i][j].y, dot[j].y);
-                    }
-            }
         }
+        __syncthreads();
     }
     if (MODE == 1) {
-        // block partial: lanes with equal l across the warp's block rows, then across warps
-        __shared__ double2 sh[kThreads / 32][W / 2];
-        __shared__ bool s_last;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            double2 v = dot[j];
-#pragma unroll
-            for (int off = 16; off >= LPB; off >>= 1) {
-                v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
-                v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
-            }
-            if (lane < LPB) sh[warp][l + LPB * j] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < W / 2) {
-            double2 s = sh[0][threadIdx.x];
-#pragma unroll
-            for (int w = 1; w < kThreads / 32; ++w) { s.x += sh[w][threadIdx.x].x; s.y += sh[w][threadIdx.x].y; }
-            st2(partials + (size_t)blockIdx.x * W + 2 * threadIdx.x, s);
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned ticket = atomicAdd(counter, 1u);
-            s_last = (ticket == gridDim.x - 1);
-            if (s_last) *counter = 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            double s[1];
-            final_sums<W, 1>(partials, s);
+        if (block_partials<W, kSpmmCpt, 3>(dot, partials, counter)) {
+            double s[3];
+            final_sums<W, 3>(partials, s);
             if (threadIdx.x < W) {
                 const int c = threadIdx.x;
+                const double rz = sc->rz[c];
+                double alpha = 0.0, beta = 0.0;
+                if (sc->active[c] && s[0] > 0.0 && rz > 0.0) {
+                    alpha = rz / s[0];
+                    const double rz_new = fma(alpha * alpha, s[2], fma(-2.0 * alpha, s[1], rz));
+                    beta = fmax(rz_new, 0.0) / rz;
+                }
                 sc->pq[c] = s[0];
-                sc->alpha[c] = (sc->active[c] && s[0] > 0.0) ? sc->rz[c] / s[0] : 0.0;
+                sc->alpha[c] = alpha;
+                sc->beta[c] = beta;
             }
         }
-    }
-}
-
-// 3x3 block (row-major, 9 doubles) times three double2 values
-__device__ __forceinline__ void blk3_mul(const double* __restrict__ B, const double2 (&r)[3], double2 (&z)[3]) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double b0 = __ldg(B + 3 * i), b1 = __ldg(B + 3 * i + 1), b2 = __ldg(B + 3 * i + 2);
-        z[i].x = fma(b0, r[0].x, fma(b1, r[1].x, b2 * r[2].x));
-        z[i].y = fma(b0, r[0].y, fma(b1, r[1].y, b2 * r[2].y));
     }
 }
 
 // ------------------------------------------------------------------------------------
 // PCG start:  x = 0, r = b (in place: r aliases b), p = P^-1 r, rz = r.p, bb = r.r
-// One LPR-lane group per dof triple (the 3x3 block-Jacobi unit).
 // ------------------------------------------------------------------------------------
-template <int W>
+template <int W, int CPTMAX>
 __global__ void __launch_bounds__(kThreads)
 cg_init_kernel(const double* __restrict__ r, double* __restrict__ x, double* __restrict__ p,
                const double* __restrict__ Pinv, int ntriples,
                CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
-    constexpr int LPR = W / 2;
-    const int l = threadIdx.x % LPR;
-    const int g0 = (blockIdx.x * kThreads + threadIdx.x) / LPR;
-    const int ng = gridDim.x * kThreads / LPR;
-    double2 acc[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+    using C = PanelCfg<W, CPTMAX>;
+    constexpr int LPB = C::LPB, NV = C::NV;
+    const int l = threadIdx.x % LPB;
+    const int g0 = (blockIdx.x * kThreads + threadIdx.x) / LPB;
+    const int ng = gridDim.x * kThreads / LPB;
+    double2 acc[2][NV];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[a][j] = make_double2(0.0, 0.0);
     for (int g = g0; g < ntriples; g += ng) {
         const size_t o = (size_t)(3 * g) * W + 2 * l;
-        double2 rv[3], z[3];
+        double2 rv[3][NV], z[3][NV];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) rv[i] = ld2_stream(r + o + (size_t)i * W);
-        blk3_mul(Pinv + (size_t)9 * g, rv, z);
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            st2(x + o + (size_t)i * W, make_double2(0.0, 0.0));
-            st2(p + o + (size_t)i * W, z[i]);
-            acc[0].x = fma(rv[i].x, z[i].x, acc[0].x); acc[0].y = fma(rv[i].y, z[i].y, acc[0].y);
-            acc[1].x = fma(rv[i].x, rv[i].x, acc[1].x); acc[1].y = fma(rv[i].y, rv[i].y, acc[1].y);
-        }
+            for (int j = 0; j < NV; ++j) rv[i][j] = ld2_stream(r + o + (size_t)i * W + 2 * LPB * j);
+        blk3_mul<NV>(Pinv + (size_t)9 * g, rv, z);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const size_t oi = o + (size_t)i * W + 2 * LPB * j;
+                st2(x + oi, make_double2(0.0, 0.0));
+                st2(p + oi, z[i][j]);
+                acc[0][j].x = fma(rv[i][j].x, z[i][j].x, acc[0][j].x); acc[0][j].y = fma(rv[i][j].y, z[i][j].y, acc[0][j].y);
+                acc[1][j].x = fma(rv[i][j].x, rv[i][j].x, acc[1][j].x); acc[1][j].y = fma(rv[i][j].y, rv[i][j].y, acc[1][j].y);
+            }
     }
-    if (block_partials<W, 2>(acc, partials, counter)) {
+    if (block_partials<W, CPTMAX, 2>(acc, partials, counter)) {
         double s[2];
         final_sums<W, 2>(partials, s);
         __shared__ int any_active;
@@ -384,43 +419,86 @@ cg_init_kernel(const double* __restrict__ r, double* __restrict__ x, double* __r
 }
 
 // ------------------------------------------------------------------------------------
-// PCG update:  x += alpha p,  r -= alpha q,  z = P^-1 r,  rz' = r.z,  rr = r.r
-// last block: convergence per column, beta = rz'/rz, rz = rz'.
+// PCG vector update, all of it in one pass (alpha and beta are both known, see above):
+//   x += alpha p,  r -= alpha q,  z = P^-1 r,  p = z + beta p;   rz = r.z,  rr = r.r
+// last block: convergence per column, rz <- measured r.z.
+// Columns that have converged are frozen (alpha = 0, p untouched), so a column's result
+// does not depend on which other columns share its batch.
 // ------------------------------------------------------------------------------------
-template <int W>
+template <int W, int CPTMAX>
 __global__ void __launch_bounds__(kThreads)
-cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                    const double* __restrict__ q, const double* __restrict__ Pinv, int ntriples,
-                    CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
-    constexpr int LPR = W / 2;
+cg_update_kernel(double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                 const double* __restrict__ q, const double* __restrict__ Pinv, int ntriples,
+                 CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
+    using C = PanelCfg<W, CPTMAX>;
+    constexpr int LPB = C::LPB, NV = C::NV;
     if (sc->done) return;
-    const int l = threadIdx.x % LPR;
-    const int g0 = (blockIdx.x * kThreads + threadIdx.x) / LPR;
-    const int ng = gridDim.x * kThreads / LPR;
-    const double2 alpha = make_double2(sc->alpha[2 * l], sc->alpha[2 * l + 1]);
-    double2 acc[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+    const int l = threadIdx.x % LPB;
+    const int g0 = (blockIdx.x * kThreads + threadIdx.x) / LPB;
+    const int ng = gridDim.x * kThreads / LPB;
+    double2 alpha[NV], beta[NV];
+    bool act0[NV], act1[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 2 * (l + LPB * j);
+        alpha[j] = make_double2(sc->alpha[c], sc->alpha[c + 1]);
+        beta[j] = make_double2(sc->beta[c], sc->beta[c + 1]);
+        act0[j] = sc->active[c] != 0; act1[j] = sc->active[c + 1] != 0;
+    }
+    double2 acc[2][NV];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[a][j] = make_double2(0.0, 0.0);
     for (int g = g0; g < ntriples; g += ng) {
         const size_t o = (size_t)(3 * g) * W + 2 * l;
-        double2 rv[3], z[3];
+        double2 rv[3][NV], pv[3][NV], qv[3][NV], xv[3][NV], z[3][NV];
+        // phase 1: every load of the triple is issued before anything is stored (12 x 16 B
+        // in flight per thread); the compiler will not hoist loads over the in-place stores
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const size_t oi = o + (size_t)i * W;
-            const double2 pv = ld2_stream(p + oi), qv = ld2_stream(q + oi);
-            double2 xv = ld2_stream(x + oi);
-            rv[i] = ld2_stream(r + oi);
-            xv.x = fma(alpha.x, pv.x, xv.x); xv.y = fma(alpha.y, pv.y, xv.y);
-            rv[i].x = fma(-alpha.x, qv.x, rv[i].x); rv[i].y = fma(-alpha.y, qv.y, rv[i].y);
-            st2(x + oi, xv);
-            st2(r + oi, rv[i]);
-        }
-        blk3_mul(Pinv + (size_t)9 * g, rv, z);
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            acc[0].x = fma(rv[i].x, z[i].x, acc[0].x); acc[0].y = fma(rv[i].y, z[i].y, acc[0].y);
-            acc[1].x = fma(rv[i].x, rv[i].x, acc[1].x); acc[1].y = fma(rv[i].y, rv[i].y, acc[1].y);
-        }
+            for (int j = 0; j < NV; ++j) {
+                const size_t oi = o + (size_t)i * W + 2 * LPB * j;
+                pv[i][j] = ld2_stream(p + oi);
+                qv[i][j] = ld2_stream(q + oi);
+                xv[i][j] = ld2_stream(x + oi);
+                rv[i][j] = ld2_stream(r + oi);
+            }
+        double Pb[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Pb[e] = __ldg(Pinv + (size_t)9 * g + e);
+        // phase 2: arithmetic
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                xv[i][j].x = fma(alpha[j].x, pv[i][j].x, xv[i][j].x); xv[i][j].y = fma(alpha[j].y, pv[i][j].y, xv[i][j].y);
+                rv[i][j].x = fma(-alpha[j].x, qv[i][j].x, rv[i][j].x); rv[i][j].y = fma(-alpha[j].y, qv[i][j].y, rv[i][j].y);
+            }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                z[i][j].x = fma(Pb[3 * i], rv[0][j].x, fma(Pb[3 * i + 1], rv[1][j].x, Pb[3 * i + 2] * rv[2][j].x));
+                z[i][j].y = fma(Pb[3 * i], rv[0][j].y, fma(Pb[3 * i + 1], rv[1][j].y, Pb[3 * i + 2] * rv[2][j].y));
+                acc[0][j].x = fma(rv[i][j].x, z[i][j].x, acc[0][j].x); acc[0][j].y = fma(rv[i][j].y, z[i][j].y, acc[0][j].y);
+                acc[1][j].x = fma(rv[i][j].x, rv[i][j].x, acc[1][j].x); acc[1][j].y = fma(rv[i][j].y, rv[i][j].y, acc[1][j].y);
+                if (act0[j]) pv[i][j].x = fma(beta[j].x, pv[i][j].x, z[i][j].x);
+                if (act1[j]) pv[i][j].y = fma(beta[j].y, pv[i][j].y, z[i][j].y);
+            }
+        // phase 3: stores
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const size_t oi = o + (size_t)i * W + 2 * LPB * j;
+                st2(x + oi, xv[i][j]);
+                st2(r + oi, rv[i][j]);
+                st2(p + oi, pv[i][j]);
+            }
     }
-    if (block_partials<W, 2>(acc, partials, counter)) {
+    if (block_partials<W, CPTMAX, 2>(acc, partials, counter)) {
         double s[2];
         final_sums<W, 2>(partials, s);
         __shared__ int any_active;
@@ -431,9 +509,7 @@ cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double
             const int c = threadIdx.x;
             double rel = 0.0;
             if (sc->active[c]) {
-                const double rz_old = sc->rz[c];
                 sc->rr[c] = s[1];
-                sc->beta[c] = (rz_old > 0.0) ? s[0] / rz_old : 0.0;
                 sc->rz[c] = s[0];
                 if (s[1] <= sc->rtol2 * sc->bb[c]) sc->active[c] = 0;
                 else atomicOr(&any_active, 1);
@@ -448,35 +524,8 @@ cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double
             sc->max_rel_res = sqrt(m);
             sc->iters += 1;
             sc->total_iters += 1ull;
+            if (sc->iters > sc->max_iters) sc->max_iters = sc->iters;
             if (!any_active) sc->done = 1;
-        }
-    }
-}
-
-// p = P^-1 r + beta p   (columns that have converged keep their p; their alpha is 0)
-template <int W>
-__global__ void __launch_bounds__(kThreads)
-cg_update_p_kernel(const double* __restrict__ r, double* __restrict__ p, const double* __restrict__ Pinv,
-                   int ntriples, const CgScalars* __restrict__ sc) {
-    constexpr int LPR = W / 2;
-    if (sc->done) return;
-    const int l = threadIdx.x % LPR;
-    const int g0 = (blockIdx.x * kThreads + threadIdx.x) / LPR;
-    const int ng = gridDim.x * kThreads / LPR;
-    const double2 beta = make_double2(sc->beta[2 * l], sc->beta[2 * l + 1]);
-    const bool a0 = sc->active[2 * l] != 0, a1 = sc->active[2 * l + 1] != 0;
-    for (int g = g0; g < ntriples; g += ng) {
-        const size_t o = (size_t)(3 * g) * W + 2 * l;
-        double2 rv[3], z[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) rv[i] = ld2_stream(r + o + (size_t)i * W);
-        blk3_mul(Pinv + (size_t)9 * g, rv, z);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            double2 pv = ld2(p + o + (size_t)i * W);
-            if (a0) pv.x = fma(beta.x, pv.x, z[i].x);
-            if (a1) pv.y = fma(beta.y, pv.y, z[i].y);
-            st2(p + o + (size_t)i * W, pv);
         }
     }
 }
@@ -494,6 +543,7 @@ cg_update_p_kernel(const double* __restrict__ r, double* __restrict__ p, const d
 struct ChebStep {
     int n;            // term index (coefficient a[n])
     int has_old;      // 0 for n == 1 (S_old not read)
+    int check_cg;     // 1: this launch follows a CG loop; record a solve that hit the cap
     double cs;        // 1 for n == 1, 2 afterwards
 };
 
@@ -503,12 +553,16 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
                    const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
                    const double* __restrict__ blk,
                    double* __restrict__ S, double* __restrict__ Y, int nrows,
-                   const double* __restrict__ coef, const double* __restrict__ tscale, ChebStep st) {
+                   const double* __restrict__ coef, const double* __restrict__ tscale, ChebStep st,
+                   CgScalars* __restrict__ sc) {
     constexpr int LPR = W / 2;
     __shared__ double s_ts[kMaxW];
     __shared__ double s_a;
     if (threadIdx.x < W) s_ts[threadIdx.x] = st.cs * tscale[threadIdx.x];
-    if (threadIdx.x == 0) s_a = coef[st.n];
+    if (threadIdx.x == 0) {
+        s_a = coef[st.n];
+        if (st.check_cg && blockIdx.x == 0 && !sc->done) sc->unconverged += 1;
+    }
     __syncthreads();
     const int l = threadIdx.x % LPR;
     const double2 ts = make_double2(s_ts[2 * l], s_ts[2 * l + 1]);
@@ -519,15 +573,15 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
         const int ntri = nrows / 3;
         for (int g = g0; g < ntri; g += ng) {
             const size_t o = (size_t)(3 * g) * W + 2 * l;
-            double2 tv[3], wv[3];
+            double2 tv[3][1], wv[3][1];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) tv[i] = ld2_stream(src + o + (size_t)i * W);
-            blk3_mul(blk + (size_t)9 * g, tv, wv);
+            for (int i = 0; i < 3; ++i) tv[i][0] = ld2_stream(src + o + (size_t)i * W);
+            blk3_mul<1>(blk + (size_t)9 * g, tv, wv);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const size_t oi = o + (size_t)i * W;
                 double2 s = st.has_old ? ld2_stream(S + oi) : make_double2(0.0, 0.0);
-                s.x = fma(ts.x, wv[i].x, s.x); s.y = fma(ts.y, wv[i].y, s.y);
+                s.x = fma(ts.x, wv[i][0].x, s.x); s.y = fma(ts.y, wv[i][0].y, s.y);
                 double2 y = ld2_stream(Y + oi);
                 y.x = fma(an, s.x, y.x); y.y = fma(an, s.y, y.y);
                 st2(S + oi, s); st2(Y + oi, y);
@@ -579,12 +633,12 @@ op_finish_kernel(const double* __restrict__ src, const double* __restrict__ xs,
     if (SRC == 2) {
         for (int g = g0; g < nrows / 3; g += ng) {
             const size_t o = (size_t)(3 * g) * W + 2 * l;
-            double2 tv[3], wv[3];
+            double2 tv[3][1], wv[3][1];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) tv[i] = ld2(src + o + (size_t)i * W);
-            blk3_mul(blk + (size_t)9 * g, tv, wv);
+            for (int i = 0; i < 3; ++i) tv[i][0] = ld2(src + o + (size_t)i * W);
+            blk3_mul<1>(blk + (size_t)9 * g, tv, wv);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) st2(out + o + (size_t)i * W, wv[i]);
+            for (int i = 0; i < 3; ++i) st2(out + o + (size_t)i * W, wv[i][0]);
         }
     } else {
         for (int r = g0; r < nrows; r += ng) {
@@ -613,7 +667,6 @@ __global__ void pack_kernel(const double* __restrict__ src, int64_t ld, int shar
                             const int* __restrict__ perm, double* __restrict__ dst, int n) {
     __shared__ double tile[W][33];
     const int i0 = blockIdx.x * 32;
-    // read: threads along i (coalesced in the host layout)
     for (int k = threadIdx.y; k < W; k += blockDim.y) {
         const int i = i0 + threadIdx.x;
         double v = 0.0;
@@ -621,7 +674,6 @@ __global__ void pack_kernel(const double* __restrict__ src, int64_t ld, int shar
         tile[k][threadIdx.x] = v;
     }
     __syncthreads();
-    // write: threads along k (coalesced in the panel layout)
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
     for (int e = tid; e < 32 * W; e += nt) {
         const int ii = e / W, k = e % W, i = i0 + ii;
