@@ -1,19 +1,360 @@
 // kexp_krylov.cu -- shift-and-invert Arnoldi (krylov_exp.py:50-109) on the device.
+//
+//   beta = ||x||_M, V_0 = x/beta                                     krylov_exp.py:58-64
+//   for j < its:  w = (M + gamma K)^-1 M V_j                         :70-71  (BiCGStab on the eta-eliminated system)
+//                 MGS in the M inner product, H(:,j)                  :73-80  (one cooperative kernel)
+//                 Hinv, H1 = (Hinv - I)/gamma, expm(-H1 s t) e1       :87-99  (one CTA)
+//   y = beta sum_j u_j V_j                                            :102-109
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
 #include "kexp_internal.h"
+#include "kexp_krylov_kernels.cuh"
 
 namespace kexp {
-struct KrylovState {};
-void krylov_free(kexp_ctx* ctx) { delete ctx->kry; ctx->kry = nullptr; }
+
+struct KrylovState {
+    double gamma = 0.0;
+    double rtol = 1e-13;
+    int max_it = 2000;
+    int64_t n = 0, n_u = 0;
+    DevCsr Ash, Brhs, Eback, M;
+    double* d_Pinv = nullptr;          // 3x3 block-Jacobi of Ash
+    // Arnoldi basis
+    int kdim = 0;
+    double *V = nullptr, *Z = nullptr; // (kdim+1) x n
+    double *w = nullptr, *mw = nullptr, *tmp = nullptr;
+    // BiCGStab work (n_u)
+    double *b = nullptr, *x = nullptr, *r = nullptr, *r0 = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr, *y = nullptr, *z = nullptr;
+    // scalars
+    double* d_dots = nullptr;          // 4
+    double* h_dots = nullptr;          // pinned 4
+    double* d_partials = nullptr;
+    unsigned* d_counter = nullptr;
+    double* d_H = nullptr;             // (kdim+1) x kdim row-major
+    double* d_small = nullptr;         // dense scratch
+    double* d_u = nullptr;
+    double* d_fac = nullptr;
+    double* d_svals = nullptr;
+    int grid = 148;
+    int coop_grid = 148;
+};
+
+static void free_state(KrylovState* k) {
+    if (!k) return;
+    free_csr(k->Ash); free_csr(k->Brhs); free_csr(k->Eback); free_csr(k->M);
+    double* bufs[] = {k->d_Pinv, k->V, k->Z, k->w, k->mw, k->tmp, k->b, k->x, k->r, k->r0, k->p, k->v, k->s, k->t, k->y, k->z,
+                      k->d_dots, k->d_partials, k->d_H, k->d_small, k->d_u, k->d_fac, k->d_svals};
+    for (double* b : bufs) cudaFree(b);
+    cudaFree(k->d_counter);
+    if (k->h_dots) cudaFreeHost(k->h_dots);
+    delete k;
+}
+
+void krylov_free(kexp_ctx* ctx) {
+    free_state(ctx->kry);
+    ctx->kry = nullptr;
+}
+
 }  // namespace kexp
 
+using namespace kexp;
+
+namespace {
+
+inline int grid_for(int n, int cap) { return std::max(1, std::min(cap, (n + kKryThreads - 1) / kKryThreads)); }
+
+void spmv(kexp_ctx* ctx, const DevCsr& A, const double* x, double* y) {
+    KrylovState* k = ctx->kry;
+    const int grid = std::max(1, std::min(8 * k->grid, (A.nrows + 7) / 8));
+    spmv_warp_kernel<<<grid, kKryThreads, 0, ctx->stream>>>(A.rowptr, A.col, A.val, x, y, A.nrows);
+    ctx->st_launches++;
+}
+
+void lincomb(kexp_ctx* ctx, double* out, double a, const double* x, double b, const double* y, double c, const double* z, int n) {
+    lincomb3_kernel<<<grid_for(n, 4 * ctx->kry->grid), kKryThreads, 0, ctx->stream>>>(out, a, x, b, y, c, z, n);
+    ctx->st_launches++;
+}
+
+// up to 4 dots, result on the host (one stream sync)
+int dots(kexp_ctx* ctx, int count, const double* const* a, const double* const* b, const int* n, double* out) {
+    KrylovState* k = ctx->kry;
+    DotArgs args;
+    memset(&args, 0, sizeof(args));
+    args.count = count;
+    for (int i = 0; i < count; ++i) { args.a[i] = a[i]; args.b[i] = b[i]; args.n[i] = n[i]; }
+    multidot_kernel<<<k->grid, kKryThreads, 0, ctx->stream>>>(args, k->d_partials, k->d_counter, k->d_dots);
+    ctx->st_launches++;
+    KEXP_CUDA(cudaMemcpyAsync(k->h_dots, k->d_dots, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < count; ++i) out[i] = k->h_dots[i];
+    return 0;
+}
+
+int dot1(kexp_ctx* ctx, const double* a, const double* b, int n, double* out) {
+    const double* aa[1] = {a}; const double* bb[1] = {b}; int nn[1] = {n};
+    return dots(ctx, 1, aa, bb, nn, out);
+}
+
+// w <- (M + gamma K)^-1 M v : right-preconditioned BiCGStab on the eliminated system
+int shifted_solve(kexp_ctx* ctx, const double* vin, double* wout) {
+    KrylovState* k = ctx->kry;
+    const int nu = (int)k->n_u, n = (int)k->n;
+    const int nblk = nu / 3;
+    auto precond = [&](const double* in, double* out) {
+        blk3_apply_kernel<<<grid_for(nblk, 4 * k->grid), kKryThreads, 0, ctx->stream>>>(k->d_Pinv, in, out, nblk);
+        ctx->st_launches++;
+    };
+    spmv(ctx, k->Brhs, vin, k->b);                                   // b = M_u v_u - gamma K_ue v_eta
+    KEXP_CUDA(cudaMemsetAsync(k->x, 0, sizeof(double) * nu, ctx->stream));
+    KEXP_CUDA(cudaMemcpyAsync(k->r, k->b, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+    KEXP_CUDA(cudaMemcpyAsync(k->r0, k->b, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+    KEXP_CUDA(cudaMemsetAsync(k->p, 0, sizeof(double) * nu, ctx->stream));
+    KEXP_CUDA(cudaMemsetAsync(k->v, 0, sizeof(double) * nu, ctx->stream));
+    double bb = 0.0;
+    if (dot1(ctx, k->b, k->b, nu, &bb)) return 1;
+    double rho = 1.0, alpha = 1.0, omega = 1.0, rho_new = bb;         // r0.r = b.b at the start
+    const double tol2 = k->rtol * k->rtol * bb;
+    if (bb > 0.0) {
+        int it = 0;
+        for (; it < k->max_it; ++it) {
+            if (rho_new == 0.0 || omega == 0.0) return kexp::fail(ctx, "BiCGStab breakdown in the shifted solve");
+            const double beta = (rho_new / rho) * (alpha / omega);
+            lincomb(ctx, k->p, 1.0, k->r, beta, k->p, -beta * omega, k->v, nu);      // p = r + beta (p - omega v)
+            precond(k->p, k->y);
+            spmv(ctx, k->Ash, k->y, k->v);
+            double r0v = 0.0;
+            if (dot1(ctx, k->r0, k->v, nu, &r0v)) return 1;
+            alpha = rho_new / r0v;
+            lincomb(ctx, k->s, 1.0, k->r, -alpha, k->v, 0.0, nullptr, nu);           // s = r - alpha v
+            precond(k->s, k->z);
+            spmv(ctx, k->Ash, k->z, k->t);
+            double d3[3];
+            const double* a3[3] = {k->t, k->t, k->s};
+            const double* b3[3] = {k->s, k->t, k->s};
+            int n3[3] = {nu, nu, nu};
+            if (dots(ctx, 3, a3, b3, n3, d3)) return 1;
+            ctx->st_bicg++;
+            if (d3[2] <= tol2) {                                                       // s already small enough
+                lincomb(ctx, k->x, 1.0, k->x, alpha, k->y, 0.0, nullptr, nu);
+                break;
+            }
+            omega = (d3[1] > 0.0) ? d3[0] / d3[1] : 0.0;
+            lincomb(ctx, k->x, 1.0, k->x, alpha, k->y, omega, k->z, nu);             // x += alpha y + omega z
+            lincomb(ctx, k->r, 1.0, k->s, -omega, k->t, 0.0, nullptr, nu);           // r = s - omega t
+            rho = rho_new;
+            double d2[2];
+            const double* a2[2] = {k->r0, k->r};
+            const double* b2[2] = {k->r, k->r};
+            int n2[2] = {nu, nu};
+            if (dots(ctx, 2, a2, b2, n2, d2)) return 1;
+            rho_new = d2[0];
+            if (d2[1] <= tol2) break;
+        }
+        if (it >= k->max_it) return kexp::fail(ctx, "shifted solve did not converge (raise solve_max_it)");
+    }
+    // w_u = x ; w_eta = v_eta + Eback w_u
+    KEXP_CUDA(cudaMemcpyAsync(wout, k->x, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+    spmv(ctx, k->Eback, k->x, k->tmp);
+    lincomb(ctx, wout + nu, 1.0, vin + nu, 1.0, k->tmp, 0.0, nullptr, n - nu);
+    return 0;
+}
+
+int alloc_d(kexp_ctx* ctx, double** p, size_t count) {
+    KEXP_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1)));
+    return 0;
+}
+
+}  // namespace
+
 extern "C" {
-int kexp_set_krylov_operator(kexp_ctx* ctx, double, const int32_t*, const int32_t*, const double*,
-                             const int32_t*, const int32_t*, const double*, const int32_t*, const int32_t*, const double*,
-                             const int32_t*, const int32_t*, const double*, double, int) {
-    return kexp::fail(ctx, "krylov path not built yet");
+
+int kexp_set_krylov_operator(kexp_ctx* ctx, double gamma,
+                             const int32_t* Ash_rowptr, const int32_t* Ash_col, const double* Ash_val,
+                             const int32_t* Brhs_rowptr, const int32_t* Brhs_col, const double* Brhs_val,
+                             const int32_t* Eback_rowptr, const int32_t* Eback_col, const double* Eback_val,
+                             const int32_t* M_rowptr, const int32_t* M_col, const double* M_val,
+                             double solve_rtol, int solve_max_it) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (!ctx->have_op) return kexp::fail(ctx, "set the operator first (kexp_set_operator)");
+    if (!Ash_rowptr || !Brhs_rowptr || !Eback_rowptr || !M_rowptr) return kexp::fail(ctx, "null matrix");
+    if (!(gamma != 0.0) || !(solve_rtol > 0.0) || solve_max_it < 1) return kexp::fail(ctx, "bad shifted-solve parameters");
+    krylov_free(ctx);
+    KrylovState* k = new KrylovState();
+    ctx->kry = k;
+    k->gamma = gamma; k->rtol = solve_rtol; k->max_it = solve_max_it;
+    k->n = ctx->n;
+    // n_u from the shapes: Ash is n_u x n_u; the caller passes consistent CSR arrays
+    int64_t nu = 0;
+    {   // Brhs has n_u rows and n columns: find n_u as the largest r with a valid rowptr is not possible
+        // without the size, so Eback (n_eta x n_u) and M (n x n) fix it: n_u = n - n_eta, n_eta = 3*cells
+        // is not known here either -> n_u is derived from the plan: rows solved + rows back-substituted.
+        nu = ctx->n_s + ctx->n_b;
+    }
+    k->n_u = nu;
+    const int64_t ne = k->n - nu;
+    if (nu % 3) { krylov_free(ctx); return kexp::fail(ctx, "n_u must be a multiple of 3"); }
+    if (upload_csr(ctx, k->Ash, (int)nu, (int)nu, Ash_rowptr, Ash_col, Ash_val) ||
+        upload_csr(ctx, k->Brhs, (int)nu, (int)k->n, Brhs_rowptr, Brhs_col, Brhs_val) ||
+        upload_csr(ctx, k->Eback, (int)ne, (int)nu, Eback_rowptr, Eback_col, Eback_val) ||
+        upload_csr(ctx, k->M, (int)k->n, (int)k->n, M_rowptr, M_col, M_val)) { krylov_free(ctx); return 1; }
+    // 3x3 block-Jacobi of Ash
+    std::vector<double> Pinv((size_t)nu * 3, 0.0);
+    for (int64_t b = 0; b < nu / 3; ++b) {
+        double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int i = 0; i < 3; ++i)
+            for (int q = Ash_rowptr[3 * b + i]; q < Ash_rowptr[3 * b + i + 1]; ++q) {
+                const int64_t c = Ash_col[q];
+                if (c >= 3 * b && c < 3 * b + 3) A[i][c - 3 * b] += Ash_val[q];
+            }
+        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        if (!(fabs(det) > 0.0)) { krylov_free(ctx); return kexp::fail(ctx, "singular diagonal block in the shifted operator"); }
+        double* P = &Pinv[(size_t)b * 9];
+        P[0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det; P[1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / det; P[2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
+        P[3] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / det; P[4] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det; P[5] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / det;
+        P[6] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det; P[7] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det; P[8] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+    }
+    bool bad = alloc_d(ctx, &k->d_Pinv, Pinv.size());
+    if (!bad) bad = cudaMemcpy(k->d_Pinv, Pinv.data(), sizeof(double) * Pinv.size(), cudaMemcpyHostToDevice) != cudaSuccess;
+    double** un[] = {&k->b, &k->x, &k->r, &k->r0, &k->p, &k->v, &k->s, &k->t, &k->y, &k->z};
+    for (auto pp : un) bad = bad || alloc_d(ctx, pp, (size_t)nu);
+    bad = bad || alloc_d(ctx, &k->w, (size_t)k->n) || alloc_d(ctx, &k->mw, (size_t)k->n) || alloc_d(ctx, &k->tmp, (size_t)k->n);
+    k->grid = ctx->num_sms;
+    bad = bad || alloc_d(ctx, &k->d_dots, 4) || alloc_d(ctx, &k->d_partials, (size_t)8 * ctx->num_sms * 4 + 64);
+    bad = bad || cudaMalloc(&k->d_counter, sizeof(unsigned)) != cudaSuccess || cudaMemset(k->d_counter, 0, sizeof(unsigned)) != cudaSuccess;
+    bad = bad || cudaMallocHost(&k->h_dots, sizeof(double) * 4) != cudaSuccess;
+    bad = bad || alloc_d(ctx, &k->d_small, 12 * 64 * 64) || alloc_d(ctx, &k->d_u, 64) || alloc_d(ctx, &k->d_fac, 8) || alloc_d(ctx, &k->d_svals, 8);
+    if (bad) { krylov_free(ctx); return kexp::fail(ctx, "out of memory in kexp_set_krylov_operator"); }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_sweep_kernel, kKryThreads, 0);
+    k->coop_grid = std::max(1, occ) * ctx->num_sms;
+    return 0;
 }
-int kexp_krylov_apply(kexp_ctx* ctx, const double*, double*, double, int, int, double*, double*, double*) {
-    return kexp::fail(ctx, "krylov path not built yet");
+
+int kexp_dense_expm(kexp_ctx* ctx, const double* A, int m, double* E) {
+    if (!ctx || !A || !E) return 1;
+    cudaSetDevice(ctx->device);
+    if (m < 1 || m > 64) return kexp::fail(ctx, "dense expm supports 1 <= m <= 64");
+    double* d = nullptr;
+    KEXP_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)m * m * 10));
+    KEXP_CUDA(cudaMemcpyAsync(d, A, sizeof(double) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+    dense_expm_kernel<<<1, kDenseThreads, 0, ctx->stream>>>(d, d + m * m, d + 2 * m * m, m);
+    ctx->st_launches++;
+    cudaError_t e = cudaMemcpyAsync(E, d + m * m, sizeof(double) * m * m, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return kexp::fail(ctx, cudaGetErrorString(e));
+    return 0;
 }
-int kexp_dense_expm(kexp_ctx* ctx, const double*, int, double*) { return kexp::fail(ctx, "krylov path not built yet"); }
+
+int kexp_krylov_apply(kexp_ctx* ctx, const double* x, double* y, double t, int kdim, int its,
+                      double* H_out, double* u_out, double* residuals_out) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    KrylovState* k = ctx->kry;
+    if (!k) return kexp::fail(ctx, "krylov operator not set (kexp_set_krylov_operator)");
+    if (!x || !y) return kexp::fail(ctx, "null vector");
+    if (x == y) return kexp::fail(ctx, "x and y must not alias");
+    if (kdim < 1 || kdim > 63) return kexp::fail(ctx, "kdim must be in 1..63");
+    if (its < 0) its = kdim;                                         // krylov_exp.py:66-67
+    if (its > kdim) return kexp::fail(ctx, "its <= kdim violated (krylov_exp.py:68)");
+    if (its < 1) return kexp::fail(ctx, "its must be >= 1");
+    const int n = (int)k->n;
+    if (k->kdim < kdim) {
+        cudaFree(k->V); cudaFree(k->Z); cudaFree(k->d_H);
+        k->V = k->Z = k->d_H = nullptr;
+        if (alloc_d(ctx, &k->V, (size_t)(kdim + 1) * n) || alloc_d(ctx, &k->Z, (size_t)(kdim + 1) * n) ||
+            alloc_d(ctx, &k->d_H, (size_t)(kdim + 1) * kdim)) return 1;
+        k->kdim = kdim;
+    }
+    const int ldh = kdim;
+    KEXP_CUDA(cudaMemsetAsync(k->d_H, 0, sizeof(double) * (size_t)(kdim + 1) * kdim, ctx->stream));
+    std::vector<double> Hh((size_t)(kdim + 1) * kdim, 0.0);
+    // beta = ||x||_M, V0 = x / beta, Z0 = M V0
+    KEXP_CUDA(cudaMemcpyAsync(k->w, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    spmv(ctx, k->M, k->w, k->mw);
+    double xmx = 0.0;
+    if (dot1(ctx, k->w, k->mw, n, &xmx)) return 1;
+    if (!(xmx > 0.0)) {                                              // zero input: exp(.) 0 = 0
+        memset(y, 0, sizeof(double) * n);
+        if (H_out) memset(H_out, 0, sizeof(double) * (size_t)(kdim + 1) * kdim);
+        if (u_out) memset(u_out, 0, sizeof(double) * its);
+        if (residuals_out) memset(residuals_out, 0, sizeof(double) * its);
+        return 0;
+    }
+    const double beta = sqrt(xmx);
+    lincomb(ctx, k->V, 1.0 / beta, k->w, 0.0, nullptr, 0.0, nullptr, n);
+    lincomb(ctx, k->Z, 1.0 / beta, k->mw, 0.0, nullptr, 0.0, nullptr, n);
+    const double svals[3] = {1.0 / 3.0, 2.0 / 3.0, 1.0};            // krylov_exp.py:90
+    KEXP_CUDA(cudaMemcpyAsync(k->d_svals, svals, sizeof(svals), cudaMemcpyHostToDevice, ctx->stream));
+    kexp_batch *bi = nullptr, *bo = nullptr;
+    if (residuals_out) {
+        if (kexp_batch_create(ctx, 1, &bi) || kexp_batch_create(ctx, 1, &bo)) return 1;
+    }
+    int rc = 0;
+    for (int j = 0; j < its && !rc; ++j) {
+        const double* Vj = k->V + (size_t)j * n;
+        if (shifted_solve(ctx, Vj, k->w)) { rc = 1; break; }
+        {   // modified Gram-Schmidt sweep (cooperative launch: grid-wide barriers inside)
+            const int slice = kKryThreads * kMgsPerThread;
+            int grid = (n + slice - 1) / slice;
+            if (grid > k->coop_grid) { rc = kexp::fail(ctx, "vector too long for the cooperative MGS sweep"); break; }
+            double* wv = k->w; const double* Vb = k->V; const double* Zb = k->Z; int nn = n; int64_t ldv = n; int jj = j;
+            double* parts = k->d_partials; double* Hcol = k->d_small + 11 * 64 * 64;     // its+1 doubles
+            void* args[] = {&wv, &Vb, &Zb, &nn, &ldv, &jj, &parts, &Hcol};
+            cudaError_t e = cudaLaunchCooperativeKernel((void*)mgs_sweep_kernel, dim3(grid), dim3(kKryThreads), args, 0, ctx->stream);
+            if (e != cudaSuccess) { rc = kexp::fail(ctx, std::string("cooperative MGS launch: ") + cudaGetErrorString(e)); break; }
+            ctx->st_launches++;
+            // H(0..j, j)
+            e = cudaMemcpy2DAsync(k->d_H + j, sizeof(double) * ldh, Hcol, sizeof(double), sizeof(double), j + 1, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e != cudaSuccess) { rc = kexp::fail(ctx, cudaGetErrorString(e)); break; }
+        }
+        spmv(ctx, k->M, k->w, k->mw);
+        double wmw = 0.0;
+        if (dot1(ctx, k->w, k->mw, n, &wmw)) { rc = 1; break; }
+        const double hn = sqrt(std::max(wmw, 0.0));                  // H[j+1,j] = ||w||_M  (krylov_exp.py:78)
+        if (cudaMemcpyAsync(k->d_H + (size_t)(j + 1) * ldh + j, &hn, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = 1; break; }
+        if (!(hn > 0.0)) { rc = kexp::fail(ctx, "Arnoldi breakdown (invariant subspace reached)"); break; }
+        lincomb(ctx, k->V + (size_t)(j + 1) * n, 1.0 / hn, k->w, 0.0, nullptr, 0.0, nullptr, n);
+        lincomb(ctx, k->Z + (size_t)(j + 1) * n, 1.0 / hn, k->mw, 0.0, nullptr, 0.0, nullptr, n);
+        const bool last = (j == its - 1);
+        if (residuals_out || last) {
+            // small dense part on one CTA: inv(H), expm(-H1 s t) e1 for s = 1/3, 2/3, 1
+            hessenberg_exp_kernel<<<1, kDenseThreads, 0, ctx->stream>>>(k->d_H, ldh, j + 1, k->gamma, t, k->d_svals, 3, k->d_u, k->d_fac, k->d_small);
+            ctx->st_launches++;
+        }
+        if (residuals_out) {
+            // C = || M^-1 K w ||_M  with w the orthogonalised, unnormalised vector (krylov_exp.py:92-94)
+            cudaStreamSynchronize(ctx->stream);
+            std::vector<double> hw((size_t)n), how((size_t)n);
+            if (cudaMemcpy(hw.data(), k->w, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = 1; break; }
+            if (kexp_batch_upload(bi, hw.data(), n, 0) || kexp_operator_apply_dev(ctx, bi, bo) || kexp_batch_download(bo, how.data(), n)) { rc = 1; break; }
+            if (cudaMemcpyAsync(k->tmp, how.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = 1; break; }
+            spmv(ctx, k->M, k->tmp, k->mw);
+            double c2 = 0.0;
+            if (dot1(ctx, k->tmp, k->mw, n, &c2)) { rc = 1; break; }
+            double fac[3];
+            if (cudaMemcpy(fac, k->d_fac, sizeof(fac), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = 1; break; }
+            const double C = sqrt(std::max(c2, 0.0));
+            double res = 0.0;
+            for (int q = 0; q < 3; ++q) res = std::max(res, fabs(C / k->gamma * fac[q]));   // krylov_exp.py:99-100
+            residuals_out[j] = res;
+        }
+    }
+    if (bi) kexp_batch_destroy(bi);
+    if (bo) kexp_batch_destroy(bo);
+    if (rc) return rc;
+    combine_kernel<<<grid_for(n, 4 * k->grid), kKryThreads, 0, ctx->stream>>>(k->V, n, k->d_u, its, beta, k->tmp, n);
+    ctx->st_launches++;
+    KEXP_CUDA(cudaMemcpyAsync(y, k->tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (H_out) KEXP_CUDA(cudaMemcpyAsync(H_out, k->d_H, sizeof(double) * (size_t)(kdim + 1) * kdim, cudaMemcpyDeviceToHost, ctx->stream));
+    if (u_out) KEXP_CUDA(cudaMemcpyAsync(u_out, k->d_u, sizeof(double) * its, cudaMemcpyDeviceToHost, ctx->stream));
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    KEXP_CUDA(cudaGetLastError());
+    return 0;
 }
+
+}  // extern "C"
