@@ -1,0 +1,90 @@
+"""Sample-time ("ensemble") parallelism across GPUs.
+
+The reference gives every averaging sample s_k its own MPI ensemble member
+(Ensemble(COMM_WORLD, space_parallel), /root/reference/averaged_sw_explicit.py:37,233-235)
+and joins them with one `ensemble.allreduce` per averaged evaluation
+(timestepping_methods.py:10-11).  Here the members are the columns of a device batch; the
+Mbar columns are split into contiguous blocks, one block per GPU/process, the weighted
+sum over the local block is a kernel, and the sum over GPUs is one all-reduce of n doubles
+(NCCL over NVLink; gloo in the CPU tests).
+"""
+import numpy as np
+
+from .samples import sample_times_weights
+
+
+def block_partition(Mbar, world):
+    """Contiguous blocks k in [offsets[g], offsets[g+1]) -- as even as possible."""
+    base, extra = divmod(int(Mbar), int(world))
+    sizes = [base + (1 if g < extra else 0) for g in range(world)]
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(int)
+
+
+class SampleEnsemble:
+    def __init__(self, Mbar, rank=None, world=None):
+        try:
+            import torch.distributed as dist
+            self._dist = dist if dist.is_available() and dist.is_initialized() else None
+        except Exception:                      # torch not importable: single process
+            self._dist = None
+        if rank is None:
+            rank = self._dist.get_rank() if self._dist else 0
+        if world is None:
+            world = self._dist.get_world_size() if self._dist else 1
+        self.Mbar, self.rank, self.world = int(Mbar), int(rank), int(world)
+        self.offsets = block_partition(self.Mbar, self.world)
+        self._lib_comm = None
+
+    @property
+    def local_slice(self):
+        return slice(int(self.offsets[self.rank]), int(self.offsets[self.rank + 1]))
+
+    @property
+    def n_local(self):
+        return int(self.offsets[self.rank + 1] - self.offsets[self.rank])
+
+    def local_times_weights(self, dt, rho):
+        t, w = sample_times_weights(self.Mbar, dt, rho)
+        return np.ascontiguousarray(t[self.local_slice]), np.ascontiguousarray(w[self.local_slice])
+
+    # ---- the one collective of the path
+    def allreduce(self, v):
+        """Sum v over the ensemble in place (numpy array or torch tensor)."""
+        if self.world == 1 or self._dist is None:
+            return v
+        import torch
+        if isinstance(v, np.ndarray):
+            tv = torch.from_numpy(v)
+            if self._dist.get_backend() == "nccl":
+                tv = tv.cuda()
+                self._dist.all_reduce(tv)
+                v[...] = tv.cpu().numpy()
+            else:
+                self._dist.all_reduce(tv)
+            return v
+        self._dist.all_reduce(v)
+        return v
+
+    def init_library_comm(self, op):
+        """NCCL communicator inside libkexp.so (kexp_comm_init): the all-reduce then runs on the
+        library's own stream right behind the weighted column sum, without going through torch."""
+        import ctypes as C
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            rc = op.lib.kexp_comm_unique_id(uid.ctypes.data_as(C.c_void_p))
+            if rc:
+                raise RuntimeError(f"kexp_comm_unique_id failed ({rc})")
+        if self._dist is not None and self.world > 1:
+            box = [uid.tobytes()]
+            self._dist.broadcast_object_list(box, src=0)
+            uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+        op._check(op.lib.kexp_comm_init(op.ctx, uid.ctypes.data_as(C.c_void_p), self.rank, self.world), "kexp_comm_init")
+        self._lib_comm = op
+
+    def averaged_apply(self, cheby, X_local, t_local, w_local, shared=False):
+        """sum over ALL ranks and samples of w_k exp(t_k L) X_k  (timestepping_methods.py:9-11)."""
+        use_lib = self._lib_comm is cheby.op and self.world > 1
+        v = cheby.apply_average(X_local, t_local, w_local, shared=shared, allreduce=use_lib)
+        if not use_lib:
+            self.allreduce(v)
+        return v
