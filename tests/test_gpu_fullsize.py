@@ -1,0 +1,93 @@
+"""GPU: BASELINE.json's full size (icosahedral ref 5, 64 samples) through the C ABI.
+The SciPy oracle is too slow here for 64 columns, so parity is checked against the C/OpenMP
+port on a few columns and through size-independent properties on all of them."""
+import numpy as np
+import pytest
+
+from conftest import get_sw
+
+pytestmark = pytest.mark.gpu
+
+DT, RHO = 900.0, 1.0
+
+
+@pytest.fixture(scope="module")
+def setup5():
+    import krylov_exp_b200 as kx
+    from oracle.assemble_sw import test_pulse
+    sw = get_sw(5)
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-12, max_it=50)
+    L = kx.EIGS[2] * DT * RHO
+    ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L)
+    assert ce.ncheb == 29                                   # qjrms setup
+    t, w = kx.sample_times_weights(64, DT, RHO)
+    x = test_pulse(sw)
+    X = np.empty((64, sw.n))
+    amp = 1e-3 * np.abs(x).max()
+    for k in range(64):
+        rng = np.random.default_rng(1234 + k)               # M1 inputs
+        X[k] = x
+        X[k, sw.n_u:] += amp * rng.standard_normal(sw.n_eta)
+        X[k, :sw.n_u] += amp * np.sqrt(sw.g / sw.H) * sw.radius / 32 * rng.standard_normal(sw.n_u)
+    yield sw, op, ce, L, t, w, x, X
+    op.close()
+
+
+def _relM(M, a, b):
+    d = a - b
+    return np.sqrt((d @ (M @ d)) / (b @ (M @ b)))
+
+
+def test_ref5_against_cpu_port(setup5):
+    """Same algorithm on the host (oracle/cpu_cheby.c, CG to 1e-13): <= 1e-10 in the calculate_norm.py norms."""
+    from oracle import coeffs, norms
+    from oracle.cpu_port import CpuCheby
+    sw, op, ce, L, t, w, x, X = setup5
+    Y = ce.apply_batch(X, -t)
+    cols = [0, 17, 63]
+    c, n = coeffs.cheby_coeffs(10000, 1e-8, L)
+    a = coeffs.real_recurrence_coeffs(c, n)
+    cpu = CpuCheby(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13)
+    ref, _ = cpu.apply_batch(a, n, L, X[cols], -t[cols])
+    for i, k in enumerate(cols):
+        e, h, l2 = norms.calculate_norm(sw, Y[k], ref[i])   # eta L2, u H(div), u L2 (calculate_norm.py:94-96)
+        assert max(e, h, l2) < 1e-10, (k, e, h, l2)
+    st = op.stats()
+    assert st["last_max_rel_residual"] <= 1e-12
+
+
+def test_ref5_forward_backward_roundtrip(setup5):
+    """exp(-tL) exp(tL) = I up to the Chebyshev truncation (tol 1e-8), all 64 sample times."""
+    sw, op, ce, L, t, w, x, X = setup5
+    M = sw.M()
+    F = ce.apply_batch(x, t, shared=True)
+    Bk = ce.apply_batch(F, -t)
+    for k in range(0, 64, 7):
+        assert _relM(M, Bk[k], x) < 2e-7
+
+
+def test_ref5_linearity_and_average(setup5):
+    sw, op, ce, L, t, w, x, X = setup5
+    M = sw.M()
+    Y = ce.apply_batch(X, -t)
+    Z = ce.apply_batch(2.5 * X, -t)
+    assert _relM(M, Z[5], 2.5 * Y[5]) < 1e-11
+    v = ce.apply_average(X, -t, w)
+    assert _relM(M, v, w @ Y) < 1e-12
+    # energy H<u,u> + g<eta,eta> is conserved by exp(tL) (test_krylov.py:97-110), to truncation
+    nu = sw.n_u
+    E = lambda z: sw.H * (z[:nu] @ (sw.Mu @ z[:nu])) + sw.g * (z[nu:] @ (sw.Meta() @ z[nu:]))
+    assert abs(E(Y[9]) / E(X[9]) - 1) < 1e-6
+
+
+def test_ref5_batch_composition_independence(setup5):
+    """A column's result does not depend on which other columns share the batch (converged columns
+    are frozen), and B = 1 (panel width 2) agrees with the 64-wide panel to round-off."""
+    sw, op, ce, L, t, w, x, X = setup5
+    M = sw.M()
+    Y = ce.apply_batch(X, -t)
+    y1 = np.empty(sw.n)
+    ce.apply(X[11], y1, -t[11])
+    assert _relM(M, y1, Y[11]) < 1e-11
+    Y9 = ce.apply_batch(X[:9], -t[:9])                     # natural Mbar of the qjrms setup
+    assert _relM(M, Y9[3], Y[3]) < 1e-11
