@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkexp.so")
+LIB_PATH = os.environ.get("KEXP_LIB", os.path.join(_HERE, "libkexp.so"))     # KEXP_LIB: kernel-variant experiments
 
 
 class KexpError(RuntimeError):

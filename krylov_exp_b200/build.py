@@ -24,12 +24,14 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    extra = os.environ.get("KEXP_NVCC_EXTRA", "").split()
+    out = os.environ.get("KEXP_LIB_OUT", LIB)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

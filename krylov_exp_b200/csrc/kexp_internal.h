@@ -7,6 +7,7 @@
 #include <vector>
 #include "../../include/kexp.h"
 #include "kexp_kernels.cuh"
+#include "kexp_spmm_tma.cuh"
 
 namespace kexp {
 
@@ -24,6 +25,13 @@ struct DevCsr {
     int nbr = 0;
     int max_bpr = 1;               // most blocks in any block row
     int64_t nblocks = 0;
+    // chunked copy for the TMA-staged CG product (kexp_spmm_tma.cuh)
+    int* ccolptr = nullptr;
+    int* ccols = nullptr;
+    double* lblocks = nullptr;
+    int nchunks = 0;
+    TmaStageLayout lay{0, 0, 0};
+    bool tma() const { return lblocks != nullptr; }
     bool bsr() const { return blocks != nullptr; }
     double bytes() const {
         return bsr() ? 80.0 * (double)nblocks + 4.0 * (double)(nbr + 1) : 12.0 * (double)nnz + 4.0 * (double)(nrows + 1);
@@ -96,6 +104,8 @@ struct kexp_ctx {
     // graphs keyed by (cheby id, W)
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
     bool use_graph = true;
+    bool use_tma = false;          // shared-memory-staged CG product for 64-column panels (KEXP_STAGED_SPMM=1): slower, see profiles/
+    bool tma_attr_set = false;
 
     // timing / stats
     bool timing = false;

@@ -251,8 +251,11 @@ constexpr int kSpmmSmemRows = 128;        // block rows per staged sub-chunk (ro
 constexpr int kSpmmSmemBytes = kSpmmSmemBlocks * 80 + kSpmmSmemRows * 72 + (kSpmmSmemRows + 4) * 4;
 constexpr int kSpmmCpt = 2;               // PanelCfg CPTMAX of the SpMM (one double2 per lane)
 
+#ifndef KEXP_SPMM_MINB
+#define KEXP_SPMM_MINB 2
+#endif
 template <int W, int MODE, int GB>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                  const double* __restrict__ X, double* __restrict__ Y, int nbr, int max_bpr,
                  const double* __restrict__ R, const double* __restrict__ Pinv,
