@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--cg-rtol", type=float, default=1e-11,
                     help="relative residual of the batched mass CG; 1e-11 gives 1.7e-12 parity error at ref 5 (profiles/)")
     ap.add_argument("--max-it", type=int, default=40)
+    ap.add_argument("--solver", default="chebyshev", choices=["chebyshev", "cg"],
+                    help="mass solve: Chebyshev semi-iteration (one fused kernel per iteration) or batched PCG")
     ap.add_argument("--no-condense", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -199,7 +201,7 @@ def main():
     w = np.ascontiguousarray(w_all[rank * B:(rank + 1) * B])
 
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, device=local_rank, condense=not args.no_condense,
-                     rtol=args.cg_rtol, max_it=args.max_it)
+                     rtol=args.cg_rtol, max_it=args.max_it, solver=args.solver)
     ce = kx.cheby_exp(op, None, None, NCHEB0, TOL, L)
     n = op.n
 
@@ -300,7 +302,9 @@ def main():
             executed = cs["launches"]
             if name in ("spmm_cg", "cg_update_xr", "cg_update_p"):
                 executed = st_t["cg_iterations"]      # launches after convergence return at once
-            bytes_launch = cs["bytes_per_col"] * B + cs["matrix_bytes"]
+                if args.solver == "chebyshev":        # K iterations per solve = 1 start kernel + K-1 fused kernels
+                    executed = (st_t["cg_iterations"] - st_t["cg_solves"]) if name == "spmm_cg" else 0
+            bytes_launch = cs["bytes_per_col"] * (B / b_bwd_in.num_panels) + cs["matrix_bytes"]
             if name == "cheb_update":                 # three row-range launches form one pass
                 executed = st_t["op_applications"]
             avg_ms = cs["ms"] / max(executed, 1)
@@ -342,9 +346,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name, "ncheb": int(ce.ncheb), "L": L, "N": int(n), "applications_per_step": apps_per_step,
                        "l2": "working set ~0.6 GB per GPU (> 126 MB L2), no explicit flush",
-                       "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi PCG rtol {args.cg_rtol:g}, "
+                       "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi {'Chebyshev iteration' if args.solver == 'chebyshev' else 'PCG'} rtol {args.cg_rtol:g}, "
                                      f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}",
-                       "parallelism": f"samples sharded, {B}/GPU"},
+                       "parallelism": f"samples sharded, {B}/GPU", "panels_per_batch": b_bwd_in.num_panels},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "timing": {"device_ms": ms_dev, "host_ms": ms_host},

@@ -76,6 +76,10 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
  * iteration cap (the whole apply is one CUDA graph with max_it early-exit iterations),
  * precond: 1 = point Jacobi, 3 = 3x3 block Jacobi. */
 int kexp_set_mass_solver(kexp_ctx* ctx, double rtol, int max_it, int precond);
+/* Same solve by Chebyshev semi-iteration on the block-Jacobi preconditioned system: spectrum of
+ * P^-1 S enclosed by [lmin, lmax] (host estimate); no inner products, one fused kernel per
+ * iteration; the residual of every solve is still measured against rtol. */
+int kexp_set_mass_solver_chebyshev(kexp_ctx* ctx, double rtol, double lmin, double lmax, int max_it);
 
 /* ---- Chebyshev:  cheby_exp.__init__ hands over a_n = Re(c_n (-i)^n), n = 0..ncheb,
  * and L (cheby_exp.py:51-98).  id selects one of KEXP_MAX_CHEBY tables (cheby, cheby2). */
@@ -99,6 +103,7 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
 typedef struct kexp_batch kexp_batch;
 int kexp_batch_create(kexp_ctx* ctx, int B, kexp_batch** out);
 int kexp_batch_destroy(kexp_batch* b);
+int kexp_batch_num_panels(kexp_batch* b);     /* a batch is stored as panels of <= 64 (or 32) sample columns */
 int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared);   /* host -> HBM */
 int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy);                        /* HBM -> host */
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t);

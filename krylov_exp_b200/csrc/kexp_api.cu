@@ -159,6 +159,21 @@ int max_grid(kexp_ctx* ctx, K kernel, int dyn_smem = 0) {
     return g;
 }
 
+// Launch on the active lane's stream; with PDL on (and outside timing mode) the kernel may begin its
+// predecessor-independent prologue while the previous kernel drains (see pdl_wait in the kernels).
+template <typename... KArgs, typename... Args>
+void launch_k(kexp_ctx* ctx, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (ctx->use_pdl && !ctx->timing) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 inline int blocks_for(int64_t groups, int lpr) {   // blocks needed so every group has one thread set
     int64_t per_block = kThreads / lpr;
     return (int)std::max<int64_t>(1, (groups + per_block - 1) / per_block);
@@ -199,6 +214,39 @@ void drain_events(kexp_ctx* ctx) {
     }
     ctx->ev_pending.clear();
     ctx->ev_used = 0;
+}
+
+void lane_store_cur(kexp_ctx* ctx, LaneState& L) {
+    L.stream = ctx->stream; L.curW = ctx->curW;
+    L.S0 = ctx->S0; L.S1 = ctx->S1; L.Y = ctx->Y; L.T = ctx->T; L.X = ctx->X; L.P = ctx->P; L.Q = ctx->Q;
+    L.d_sc = ctx->d_sc; L.d_partials = ctx->d_partials; L.d_counter = ctx->d_counter; L.d_tscale = ctx->d_tscale;
+    L.h_pin = ctx->h_pin; L.graphs.swap(ctx->graphs);
+    L.base_iters = ctx->base_iters; L.base_solves = ctx->base_solves;
+}
+
+void lane_load(kexp_ctx* ctx, LaneState& L) {
+    ctx->stream = L.stream; ctx->curW = L.curW;
+    ctx->S0 = L.S0; ctx->S1 = L.S1; ctx->Y = L.Y; ctx->T = L.T; ctx->X = L.X; ctx->P = L.P; ctx->Q = L.Q;
+    ctx->d_sc = L.d_sc; ctx->d_partials = L.d_partials; ctx->d_counter = L.d_counter; ctx->d_tscale = L.d_tscale;
+    ctx->h_pin = L.h_pin; ctx->graphs.swap(L.graphs);
+    ctx->base_iters = L.base_iters; ctx->base_solves = L.base_solves;
+}
+
+int alloc_lane_scalars(kexp_ctx* ctx);      // below (uses the active-lane fields)
+
+// Make lane i the active one (allocating its stream / scalars on first use).
+int swap_lane(kexp_ctx* ctx, int i) {
+    if (i == ctx->cur_lane) return 0;
+    lane_store_cur(ctx, ctx->lane_store[ctx->cur_lane]);
+    LaneState& L = ctx->lane_store[i];
+    const bool fresh = !L.allocated;
+    lane_load(ctx, L);
+    ctx->cur_lane = i;
+    if (fresh) {
+        L.allocated = true;
+        if (alloc_lane_scalars(ctx)) return 1;
+    }
+    return 0;
 }
 
 int ensure_panels(kexp_ctx* ctx, int W) {
@@ -256,8 +304,8 @@ void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
         auto k = bsr3_spmm_kernel<W, MODE, kSpmmGB>;
         constexpr int per_cta = PanelCfg<W, kSpmmCpt>::BPC;
         int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
-        k<<<grid, kThreads, kSpmmSmemBytes, ctx->stream>>>(A.browptr, A.blocks, X, Y, A.nbr, A.max_bpr, ctx->T, ctx->d_Pinv,
-                                                               ctx->d_sc, ctx->d_partials, ctx->d_counter);
+        launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, X, Y, A.nbr, A.max_bpr, ctx->T, ctx->d_Pinv,
+                 ctx->d_sc, ctx->d_partials, ctx->d_counter);
     } else {
         // MODE 1 (the CG product) always has a BSR copy: n_s is a multiple of 3 by contract
         auto k = csr_spmm_kernel<W>;
@@ -279,11 +327,48 @@ void enqueue_operator(kexp_ctx* ctx, const double* in) {
         launch_spmm<W, 0>(ctx, ctx->Kt, in, ctx->T);
     }
     const int ntri = ns / 3;
+    if (ctx->solver == 1) {
+        // Chebyshev semi-iteration: one fused kernel per iteration, no inner products
+        const double theta = 0.5 * (ctx->cheb_hi + ctx->cheb_lo), delta = 0.5 * (ctx->cheb_hi - ctx->cheb_lo);
+        const double sigma1 = theta / delta;
+        const int K = ctx->graph_its;
+        double* xa = ((K - 1) % 2 == 0) ? ctx->X : ctx->P;       // x_1 lands here; after K-1 swaps the result is in X
+        double* xb = (xa == ctx->X) ? ctx->P : ctx->X;
+        {
+            auto k = cheb_solve_init_kernel<W, kCptVec>;
+            int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
+            TimedLaunch tl(ctx, KC_CG_INIT);
+            launch_k(ctx, k, grid, kThreads, 0, ctx->T, xa, ctx->Q, ctx->d_Pinv, ntri, 1.0 / theta, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+        }
+        double rho = 1.0 / sigma1;
+        const DevCsr& A = ctx->As;
+        constexpr int per_cta = PanelCfg<W, kSpmmCpt>::BPC;
+        for (int it = 1; it < K; ++it) {
+            const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+            const double c1 = rho_new * rho, c2 = 2.0 * rho_new / delta;
+            rho = rho_new;
+            TimedLaunch tl(ctx, KC_SPMM_CG);
+            if (it == K - 1) {
+                auto k = bsr3_cheb_iter_kernel<W, 1, kSpmmGB>;
+                int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
+                launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xa, xb, ctx->T, ctx->Q, ctx->d_Pinv, A.nbr, A.max_bpr,
+                         c1, c2, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+            } else {
+                auto k = bsr3_cheb_iter_kernel<W, 0, kSpmmGB>;
+                int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
+                launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xa, xb, ctx->T, ctx->Q, ctx->d_Pinv, A.nbr, A.max_bpr,
+                         c1, c2, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+            }
+            std::swap(xa, xb);
+        }
+        ctx->st_op_apps++;
+        return;
+    }
     {
         auto k = cg_init_kernel<W, kCptVec>;
         int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
         TimedLaunch tl(ctx, KC_CG_INIT);
-        k<<<grid, kThreads, 0, s>>>(ctx->T, ctx->X, ctx->P, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+        launch_k(ctx, k, grid, kThreads, 0, ctx->T, ctx->X, ctx->P, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
     }
     for (int it = 0; it < ctx->graph_its; ++it) {
         {
@@ -294,7 +379,7 @@ void enqueue_operator(kexp_ctx* ctx, const double* in) {
             auto k = cg_update_kernel<W, kCptVec>;
             int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
             TimedLaunch tl(ctx, KC_CG_XR);
-            k<<<grid, kThreads, 0, s>>>(ctx->X, ctx->T, ctx->P, ctx->Q, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+            launch_k(ctx, k, grid, kThreads, 0, ctx->X, ctx->T, ctx->P, ctx->Q, ctx->d_Pinv, ntri, ctx->d_sc, ctx->d_partials, ctx->d_counter);
         }
     }
     ctx->st_op_apps++;
@@ -311,14 +396,14 @@ void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep 
         auto k = cheb_update_kernel<W, 0>;
         int grid = std::min(max_grid(ctx, k), blocks_for(ns, LPR));
         TimedLaunch tl(ctx, KC_CHEB);
-        k<<<grid, kThreads, 0, s>>>(ctx->X, nullptr, nullptr, nullptr, nullptr, nullptr, S, ctx->Y, ns, coef, ctx->d_tscale, st, ctx->d_sc);
+        launch_k(ctx, k, grid, kThreads, 0, ctx->X, nullptr, nullptr, nullptr, nullptr, nullptr, S, ctx->Y, ns, coef, ctx->d_tscale, st, ctx->d_sc);
     }
     if (nb > 0) {
         auto k = cheb_update_kernel<W, 1>;
         int grid = std::min(max_grid(ctx, k), blocks_for(nb, LPR));
         const size_t o = (size_t)ns * W;
         TimedLaunch tl(ctx, KC_CHEB);
-        k<<<grid, kThreads, 0, s>>>(ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, S + o, ctx->Y + o, nb, coef, ctx->d_tscale, st2, ctx->d_sc);
+        launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, S + o, ctx->Y + o, nb, coef, ctx->d_tscale, st2, ctx->d_sc);
     }
     if (nd > 0) {
         const size_t o = (size_t)(ns + nb) * W;
@@ -326,11 +411,11 @@ void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep 
         if (ctx->d_Dblk) {
             auto k = cheb_update_kernel<W, 2>;
             int grid = std::min(max_grid(ctx, k), blocks_for(nd / 3, LPR));
-            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
+            launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
         } else {
             auto k = cheb_update_kernel<W, 0>;
             int grid = std::min(max_grid(ctx, k), blocks_for(nd, LPR));
-            k<<<grid, kThreads, 0, s>>>(ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
+            launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
         }
     }
 }
@@ -367,7 +452,7 @@ void enqueue_cheby(kexp_ctx* ctx, int id) {
     {
         TimedLaunch tl(ctx, KC_CHEB);
         int grid = (int)std::min<size_t>((size_t)8 * ctx->num_sms, (nelem2 + kThreads - 1) / kThreads);
-        cheb_init_kernel<W><<<std::max(grid, 1), kThreads, 0, ctx->stream>>>(ctx->S0, ctx->Y, nelem2, tb.d_coef);
+        launch_k(ctx, cheb_init_kernel<W>, std::max(grid, 1), kThreads, 0, ctx->S0, ctx->Y, nelem2, tb.d_coef);
     }
     for (int n = 1; n <= tb.ncheb; ++n) {
         const double* in = (n & 1) ? ctx->S0 : ctx->S1;     // S_{n-1}
@@ -414,7 +499,7 @@ int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
     KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
     const ChebTable& tb = ctx->cheb[id];
     ctx->st_op_apps += tb.ncheb;
-    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + 2 * ctx->graph_its + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
+    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + (ctx->solver == 1 ? ctx->graph_its - 1 : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
     return 0;
 }
 
@@ -422,6 +507,12 @@ void invalidate_graphs(kexp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
     ctx->graphs.clear();
+    LaneState& other = ctx->lane_store[1 - ctx->cur_lane];
+    if (other.allocated) {
+        if (other.stream) cudaStreamSynchronize(other.stream);
+        for (auto& g : other.graphs) cudaGraphExecDestroy(g.second);
+        other.graphs.clear();
+    }
 }
 
 // occupancy queries must not happen during capture: touch every kernel once
@@ -430,6 +521,8 @@ void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, csr_spmm_kernel<W>);
     max_grid(ctx, bsr3_spmm_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_spmm_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cg_init_kernel<W, kCptVec>); max_grid(ctx, cg_update_kernel<W, kCptVec>);
+    max_grid(ctx, cheb_solve_init_kernel<W, kCptVec>);
+    max_grid(ctx, bsr3_cheb_iter_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
 }
 
@@ -502,6 +595,36 @@ int colsum_panel(kexp_ctx* ctx, const double* Ypanel, const double* w, int col0,
 
 }  // namespace
 
+namespace {
+int alloc_lane_scalars(kexp_ctx* ctx) {
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_sc, sizeof(CgScalars)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_sc, 0, sizeof(CgScalars)) == cudaSuccess;
+    // block partials (3 accumulators x up to 8 blocks/SM) + group partials, and the tickets
+    ok = ok && cudaMalloc(&ctx->d_partials, sizeof(double) * 3 * 9 * (size_t)ctx->num_sms * kMaxW + 4096) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counter, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_counter, 0, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_tscale, sizeof(double) * kMaxW) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_pin, sizeof(double) * 2 * kMaxW) == cudaSuccess;
+    const double r2 = ctx->rtol * ctx->rtol;
+    ok = ok && cudaMemcpy(&ctx->d_sc->rtol2, &r2, sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    ctx->curW = 0;
+    if (!ok) return kexp::fail(ctx, "out of memory allocating lane state");
+    return 0;
+}
+
+template <typename F>
+int for_each_lane(kexp_ctx* ctx, F f) {     // run f with every allocated lane active, end on lane 0
+    int rc = 0;
+    for (int i = 1; i >= 0; --i) {
+        if (!ctx->lane_store[i].allocated && i != ctx->cur_lane) continue;
+        if (swap_lane(ctx, i)) return 1;
+        rc |= f();
+    }
+    return rc;
+}
+}  // namespace
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -529,22 +652,22 @@ int kexp_create(kexp_ctx** out, int device) {
         delete ctx;
         return 5;
     }
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_sc, sizeof(CgScalars)) == cudaSuccess;
-    ok = ok && cudaMemset(ctx->d_sc, 0, sizeof(CgScalars)) == cudaSuccess;
-    // block partials (3 accumulators x up to 8 blocks/SM) + group partials, and the tickets
-    ok = ok && cudaMalloc(&ctx->d_partials, sizeof(double) * 3 * 9 * (size_t)ctx->num_sms * kMaxW + 4096) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_counter, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
-    ok = ok && cudaMemset(ctx->d_counter, 0, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_tscale, sizeof(double) * kMaxW) == cudaSuccess;
+    ctx->lane_store[0].allocated = true;
+    bool ok = alloc_lane_scalars(ctx) == 0;
     ok = ok && cudaMalloc(&ctx->d_w, sizeof(double) * kMaxW) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ctx->h_pin, sizeof(double) * 2 * kMaxW) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { kexp_destroy(ctx); return 6; }
     const char* g = getenv("KEXP_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
     const char* tm = getenv("KEXP_STAGED_SPMM");
     if (tm && tm[0] == '1') ctx->use_tma = true;
+    const char* ln = getenv("KEXP_LANES");
+    if (ln && ln[0] == '1') { ctx->nlanes = 1; ctx->panel_cap = 64; }
+    if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
+    const char* pd = getenv("KEXP_PDL");
+    if (pd && pd[0] == '1') ctx->use_pdl = true;
     const char* rb = getenv("KEXP_RED_BLOCKS");
     if (rb && atoi(rb) >= 1 && atoi(rb) <= 8) ctx->red_blocks_per_sm = atoi(rb);
     const char* ad = getenv("KEXP_ADAPTIVE_ITS");
@@ -557,10 +680,21 @@ int kexp_create(kexp_ctx** out, int device) {
 int kexp_destroy(kexp_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
+    swap_lane(ctx, 0);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
+    invalidate_graphs(ctx);
     if (ctx->tmp_in) { kexp_batch_destroy(ctx->tmp_in); kexp_batch_destroy(ctx->tmp_out); ctx->tmp_in = ctx->tmp_out = nullptr; }
     kexp::krylov_free(ctx);
+    {
+        LaneState& L = ctx->lane_store[1];
+        if (L.allocated) {
+            double* lb[] = {L.S0, L.S1, L.Y, L.T, L.X, L.P, L.Q, L.d_partials, L.d_tscale};
+            for (double* b : lb) cudaFree(b);
+            cudaFree(L.d_sc); cudaFree(L.d_counter);
+            if (L.h_pin) cudaFreeHost(L.h_pin);
+            if (L.stream) cudaStreamDestroy(L.stream);
+        }
+    }
     free_csr(ctx->Kt); free_csr(ctx->As); free_csr(ctx->Rt);
     double* bufs[] = {ctx->S0, ctx->S1, ctx->Y, ctx->T, ctx->X, ctx->P, ctx->Q, ctx->d_Dblk, ctx->d_Pinv,
                       ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_v};
@@ -574,6 +708,8 @@ int kexp_destroy(kexp_ctx* ctx) {
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->nccl_comm && ctx->nccl_lib) {
         typedef int (*destroy_t)(void*);
         destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
@@ -634,6 +770,7 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
     ctx->have_op = false;
     ctx->n = n; ctx->n_s = n_s; ctx->n_b = n_b; ctx->n_d = n_d;
     ctx->curW = 0;   // panels are re-allocated for the new size
+    ctx->lane_store[1 - ctx->cur_lane].curW = 0;
     if (upload_csr(ctx, ctx->Kt, (int)n, (int)n, Kt_rowptr, Kt_col, Kt_val, false)) return 1;
     if (upload_csr(ctx, ctx->As, (int)n_s, (int)n_s, As_rowptr, As_col, As_val, true)) return 1;
     if (!ctx->As.bsr()) return kexp::fail(ctx, "mass matrix could not be stored as 3x3 blocks");
@@ -689,7 +826,7 @@ int kexp_set_mass_solver(kexp_ctx* ctx, double rtol, int max_it, int precond) {
     invalidate_graphs(ctx);
     const bool rebuild = ctx->have_op && precond != ctx->precond;
     ctx->rtol = rtol; ctx->max_it = max_it; ctx->precond = precond;
-    ctx->graph_its = max_it; ctx->its_tuned = false;
+    ctx->graph_its = max_it; ctx->its_tuned = false; ctx->solver = 0;
     if (rebuild) {
         std::vector<double> Pinv;
         if (build_block_jacobi(ctx, ctx->n_s, ctx->h_As_rowptr.data(), ctx->h_As_col.data(), ctx->h_As_val.data(), precond, Pinv)) return 1;
@@ -697,6 +834,24 @@ int kexp_set_mass_solver(kexp_ctx* ctx, double rtol, int max_it, int precond) {
     }
     const double r2 = rtol * rtol;
     KEXP_CUDA(cudaMemcpy(&ctx->d_sc->rtol2, &r2, sizeof(double), cudaMemcpyHostToDevice));
+    LaneState& other = ctx->lane_store[1 - ctx->cur_lane];
+    if (other.allocated) KEXP_CUDA(cudaMemcpy(&other.d_sc->rtol2, &r2, sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Chebyshev semi-iteration for the mass solve.  [lmin, lmax] must enclose the spectrum of P^-1 S
+// (P the 3x3 block-Jacobi); the iteration count follows from 1/T_k(sigma) <= rtol and is raised
+// (up to max_it) if the measured residual of a solve misses rtol.
+int kexp_set_mass_solver_chebyshev(kexp_ctx* ctx, double rtol, double lmin, double lmax, int max_it) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (!(rtol > 0.0) || !(lmin > 0.0) || !(lmax > lmin) || max_it < 2) return kexp::fail(ctx, "bad Chebyshev mass solver parameters");
+    if (kexp_set_mass_solver(ctx, rtol, max_it, 3)) return 1;
+    const double sigma1 = (lmax + lmin) / (lmax - lmin);
+    int K = (int)std::ceil(std::acosh(1.0 / rtol) / std::acosh(sigma1)) + 1;
+    K = std::max(2, std::min(K, max_it));
+    ctx->solver = 1; ctx->cheb_lo = lmin; ctx->cheb_hi = lmax;
+    ctx->graph_its = K; ctx->its_tuned = true;      // fixed length; only ever grows
     return 0;
 }
 
@@ -722,8 +877,10 @@ int kexp_batch_create(kexp_ctx* ctx, int B, kexp_batch** out) {
     if (B < 1) return kexp::fail(ctx, "B must be >= 1");
     kexp_batch* b = new kexp_batch();
     b->ctx = ctx; b->B = B;
-    for (int c0 = 0; c0 < B; c0 += kMaxW) {
-        const int W = pick_W(std::min(B - c0, kMaxW));
+    const int cap = (B > ctx->panel_cap) ? ctx->panel_cap : kMaxW;   // split only what does not fit one panel of the cap
+    b->stride = cap;
+    for (int c0 = 0; c0 < B; c0 += cap) {
+        const int W = pick_W(std::min(B - c0, cap));
         double* p = nullptr;
         if (cudaMalloc(&p, sizeof(double) * (size_t)ctx->n * W) != cudaSuccess) {
             kexp_batch_destroy(b);
@@ -734,6 +891,8 @@ int kexp_batch_create(kexp_ctx* ctx, int B, kexp_batch** out) {
     *out = b;
     return 0;
 }
+
+int kexp_batch_num_panels(kexp_batch* b) { return b ? (int)b->panel.size() : 0; }
 
 int kexp_batch_destroy(kexp_batch* b) {
     if (!b) return 0;
@@ -754,7 +913,7 @@ int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shar
     KEXP_CUDA(cudaMemcpy2DAsync(ctx->d_stage, sizeof(double) * ctx->n, X, sizeof(double) * (x_is_shared ? ctx->n : ldx),
                                 sizeof(double) * ctx->n, nvec, cudaMemcpyHostToDevice, ctx->stream));
     for (size_t p = 0; p < b->panel.size(); ++p)
-        if (pack_panel(ctx, ctx->d_stage, ctx->n, x_is_shared, b->B, (int)p * kMaxW, b->panelW[p], b->panel[p])) return 1;
+        if (pack_panel(ctx, ctx->d_stage, ctx->n, x_is_shared, b->B, (int)p * b->stride, b->panelW[p], b->panel[p])) return 1;
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -766,7 +925,7 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
     if (ldy < ctx->n) return kexp::fail(ctx, "ldy < n");
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
     for (size_t p = 0; p < b->panel.size(); ++p)
-        if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * kMaxW, b->panelW[p])) return 1;
+        if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * b->stride, b->panelW[p])) return 1;
     KEXP_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, ctx->d_stage, sizeof(double) * ctx->n, sizeof(double) * ctx->n, b->B,
                                 cudaMemcpyDeviceToHost, ctx->stream));
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -779,20 +938,40 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
     if (in == out) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
     if (in->B != out->B) return kexp::fail(ctx, "batch sizes differ");
     cudaSetDevice(ctx->device);
+    if (in->stride != out->stride || in->panelW != out->panelW) return kexp::fail(ctx, "batches have different panel layouts");
     int maxW = 0;
     for (int W : in->panelW) maxW = std::max(maxW, W);
-    if (ensure_panels(ctx, maxW)) return 1;
     for (int W : in->panelW) DISPATCH_W(W, warm_occupancy<kW>(ctx));
+    const int np = (int)in->panel.size();
+    const bool two = ctx->nlanes == 2 && !ctx->timing && np >= 2;
+    if (swap_lane(ctx, 0)) return 1;
     if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-    for (size_t p = 0; p < in->panel.size(); ++p) {
+    if (two) KEXP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    bool lane1_used = false;
+    for (int p = 0; p < np; ++p) {
+        const int lane = two ? (p & 1) : 0;
+        if (swap_lane(ctx, lane)) return 1;
+        if (lane == 1 && !lane1_used) {                 // lane 1 starts after everything already queued on lane 0
+            KEXP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0));
+            lane1_used = true;
+        }
         const int W = in->panelW[p];
+        if (ensure_panels(ctx, W)) return 1;
         const size_t bytes = sizeof(double) * (size_t)ctx->n * W;
-        if (set_tscale(ctx, id, t, (int)p * kMaxW, in->B, W)) return 1;
+        if (set_tscale(ctx, id, t, p * in->stride, in->B, W)) return 1;
         KEXP_CUDA(cudaMemcpyAsync(ctx->S0, in->panel[p], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         if (run_cheby_panel(ctx, id, W)) return 1;
         KEXP_CUDA(cudaMemcpyAsync(out->panel[p], ctx->Y, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    if (lane1_used) {
+        if (swap_lane(ctx, 1)) return 1;
+        KEXP_CUDA(cudaEventRecord(ctx->ev_join, ctx->stream));
+        if (swap_lane(ctx, 0)) return 1;
+        KEXP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
+    if (swap_lane(ctx, 0)) return 1;
     if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    (void)maxW;
     return 0;
 }
 
@@ -801,11 +980,14 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
 // 8-byte read-back) that no solve ran into the trimmed cap and otherwise repeats itself
 // with the full max_it.
 static int read_cg_counters(kexp_ctx* ctx, int* max_iters, int* unconverged) {
-    int h[2];
-    KEXP_CUDA(cudaMemcpyAsync(h, &ctx->d_sc->max_iters, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
-    *max_iters = h[0]; *unconverged = h[1];
-    return 0;
+    *max_iters = 0; *unconverged = 0;
+    return for_each_lane(ctx, [&]() -> int {
+        int h[2];
+        KEXP_CUDA(cudaMemcpyAsync(h, &ctx->d_sc->max_iters, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+        *max_iters = std::max(*max_iters, h[0]); *unconverged += h[1];
+        return 0;
+    });
 }
 
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t) {
@@ -816,8 +998,8 @@ int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out,
     int mx = 0, unc = 0;
     if (read_cg_counters(ctx, &mx, &unc)) return 1;
     if (unc > ctx->unconverged_seen && ctx->graph_its < ctx->max_it) {
-        // a solve hit the trimmed cap: fall back to the full cap and redo this apply
-        ctx->graph_its = ctx->max_it;
+        // a solve hit the trimmed cap (CG) or missed rtol with the fixed length (Chebyshev): raise it and redo
+        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 4) : ctx->max_it;
         ctx->its_tuned = true;              // do not trim again
         invalidate_graphs(ctx);
         if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
@@ -874,7 +1056,7 @@ int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev) {
     kexp_ctx* ctx = b->ctx;
     cudaSetDevice(ctx->device);
     for (size_t p = 0; p < b->panel.size(); ++p)
-        if (colsum_panel(ctx, b->panel[p], w, (int)p * kMaxW, b->B, b->panelW[p], v_dev, p > 0)) return 1;
+        if (colsum_panel(ctx, b->panel[p], w, (int)p * b->stride, b->B, b->panelW[p], v_dev, p > 0)) return 1;
     return 0;
 }
 
@@ -993,8 +1175,8 @@ int kexp_get_class_stats(kexp_ctx* ctx, int cls, double* ms, int64_t* launches, 
         switch (cls) {
             case KC_SPMM_K: b = 16.0 * n; break;
             case KC_CG_INIT: b = 24.0 * ns; break;
-            case KC_SPMM_CG: b = 16.0 * ns; break;
-            case KC_CG_XR: b = 48.0 * ns; break;
+            case KC_SPMM_CG: b = (ctx->solver == 1 ? 40.0 : 24.0) * ns; break;
+            case KC_CG_XR: b = 56.0 * ns; break;
             case KC_CG_P: b = 24.0 * ns; break;
             case KC_CHEB: b = 40.0 * n; break;
             default: b = 0.0;
@@ -1025,18 +1207,22 @@ int kexp_get_class_matrix_bytes(kexp_ctx* ctx, int cls, double* bytes) {
 int kexp_stats(kexp_ctx* ctx, kexp_stats_t* out) {
     if (!ctx || !out) return 1;
     cudaSetDevice(ctx->device);
-    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
-    CgScalars sc;
-    KEXP_CUDA(cudaMemcpy(&sc, ctx->d_sc, sizeof(CgScalars), cudaMemcpyDeviceToHost));
     memset(out, 0, sizeof(*out));
     out->n = ctx->n;
     out->n_solve = ctx->n_s;
-    out->cg_solves = (int64_t)(sc.total_solves - ctx->base_solves);
-    out->cg_iterations = (int64_t)(sc.total_iters - ctx->base_iters);
+    int rc = for_each_lane(ctx, [&]() -> int {
+        KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+        CgScalars sc;
+        KEXP_CUDA(cudaMemcpy(&sc, ctx->d_sc, sizeof(CgScalars), cudaMemcpyDeviceToHost));
+        out->cg_solves += (int64_t)(sc.total_solves - ctx->base_solves);
+        out->cg_iterations += (int64_t)(sc.total_iters - ctx->base_iters);
+        out->last_max_rel_residual = std::max(out->last_max_rel_residual, sc.max_rel_res);
+        return 0;
+    });
+    if (rc) return rc;
     out->op_applications = ctx->st_op_apps;
     out->kernel_launches = ctx->st_launches;
     out->bicg_iterations = ctx->st_bicg;
-    out->last_max_rel_residual = sc.max_rel_res;
     out->spmm_cg_launches = out->cg_iterations;
     out->spmm_cg_bytes = 0.0;     // per-column figures: see kexp_get_class_stats
     out->model_bytes = 0.0;
@@ -1046,10 +1232,14 @@ int kexp_stats(kexp_ctx* ctx, kexp_stats_t* out) {
 int kexp_stats_reset(kexp_ctx* ctx) {
     if (!ctx) return 1;
     cudaSetDevice(ctx->device);
-    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
-    CgScalars sc;
-    KEXP_CUDA(cudaMemcpy(&sc, ctx->d_sc, sizeof(CgScalars), cudaMemcpyDeviceToHost));
-    ctx->base_iters = sc.total_iters; ctx->base_solves = sc.total_solves;
+    int rc = for_each_lane(ctx, [&]() -> int {
+        KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+        CgScalars sc;
+        KEXP_CUDA(cudaMemcpy(&sc, ctx->d_sc, sizeof(CgScalars), cudaMemcpyDeviceToHost));
+        ctx->base_iters = sc.total_iters; ctx->base_solves = sc.total_solves;
+        return 0;
+    });
+    if (rc) return rc;
     ctx->st_op_apps = 0; ctx->st_launches = 0; ctx->st_bicg = 0;
     for (int i = 0; i < KC_COUNT; ++i) ctx->cls[i] = ClassStat();
     return 0;

@@ -55,6 +55,23 @@ struct ChebTable {
 
 struct KrylovState;               // kexp_krylov.cu
 
+// Everything one in-flight panel needs: its stream, work panels, CG scalars, reduction scratch and
+// captured graphs.  The context's own fields are the ACTIVE lane; swap_lane() exchanges them with a
+// stored set, so the enqueue code is lane-agnostic (host code is single-threaded per context).
+struct LaneState {
+    bool allocated = false;
+    cudaStream_t stream = nullptr;
+    int curW = 0;
+    double *S0 = nullptr, *S1 = nullptr, *Y = nullptr, *T = nullptr, *X = nullptr, *P = nullptr, *Q = nullptr;
+    CgScalars* d_sc = nullptr;
+    double* d_partials = nullptr;
+    unsigned* d_counter = nullptr;
+    double* d_tscale = nullptr;
+    double* h_pin = nullptr;
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    unsigned long long base_iters = 0, base_solves = 0;
+};
+
 }  // namespace kexp
 
 struct kexp_ctx {
@@ -78,6 +95,8 @@ struct kexp_ctx {
     double rtol = 1e-12;
     int max_it = 60;
     int precond = 3;
+    int solver = 0;                // 0: PCG, 1: Chebyshev semi-iteration (kexp_set_mass_solver_chebyshev)
+    double cheb_lo = 0.0, cheb_hi = 0.0;
     int graph_its = 60;            // CG iterations captured per solve (trimmed adaptively, see kexp_cheby_apply_dev)
     bool its_tuned = false;
     bool adaptive_its = true;
@@ -104,6 +123,7 @@ struct kexp_ctx {
     // graphs keyed by (cheby id, W)
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
     bool use_graph = true;
+    bool use_pdl = false;          // programmatic dependent launch between the kernels of the graph (KEXP_PDL=1): no measurable gain
     bool use_tma = false;          // shared-memory-staged CG product for 64-column panels (KEXP_STAGED_SPMM=1): slower, see profiles/
     bool tma_attr_set = false;
 
@@ -121,6 +141,14 @@ struct kexp_ctx {
     unsigned long long base_iters = 0, base_solves = 0;
     std::map<const void*, int> occ_cache;
 
+    // lanes: two half-width panels of one batch can be in flight on two streams, so that the
+    // latency-bound CG product of one overlaps the bandwidth-bound vector update of the other
+    kexp::LaneState lane_store[2];
+    int cur_lane = 0;
+    int nlanes = 1;
+    int panel_cap = 64;            // widest panel a new batch gets (32 with two lanes)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
     // krylov
     kexp::KrylovState* kry = nullptr;
 
@@ -135,6 +163,7 @@ struct kexp_batch {
     int B = 0;
     std::vector<int> panelW;       // width of each panel
     std::vector<double*> panel;    // [n][W] device buffers, internal order
+    int stride = 64;               // first column of panel p is p*stride
 };
 
 namespace kexp {

@@ -110,10 +110,31 @@ class CondensedPlan:
         self.order = order
 
 
-class Operator:
-    """Device-resident M^-1 K.  `condense=True` uploads the statically condensed plan."""
+def block_jacobi_spectrum(As, safety=1.03):
+    """Enclosure [lmin, lmax] of the spectrum of P^-1 S, P the 3x3 block-Jacobi of the SPD matrix S
+    (host, once; SciPy Lanczos on the symmetrised L^-1 S L^-T, D = L L^T)."""
+    from scipy.sparse.linalg import eigsh, splu
+    As = _csr(As)
+    n = As.shape[0]
+    nb = n // 3
+    B = As.tobsr(blocksize=(3, 3))
+    rows = np.repeat(np.arange(nb), np.diff(B.indptr))
+    D = B.data[B.indices == rows]
+    Li = np.linalg.inv(np.linalg.cholesky(D))
+    LiM = sp.bsr_matrix((Li, np.arange(nb), np.arange(nb + 1)), shape=(n, n)).tocsr()
+    Sym = (LiM @ As @ LiM.T).tocsc()
+    lmax = float(eigsh(Sym, k=1, which="LA", return_eigenvectors=False, tol=1e-5)[0])
+    lmin = float(eigsh(Sym, k=1, sigma=0.0, which="LM", return_eigenvectors=False, tol=1e-5)[0])
+    return lmin / safety, lmax * safety
 
-    def __init__(self, K, Mu, Meta_inv_blocks, device=0, condense=True, rtol=1e-12, max_it=60, precond=3):
+
+class Operator:
+    """Device-resident M^-1 K.  `condense=True` uploads the statically condensed plan.
+    solver: "cg" (batched block-Jacobi PCG) or "chebyshev" (Chebyshev semi-iteration on the same
+    preconditioned system, spectrum bounds estimated here on the host)."""
+
+    def __init__(self, K, Mu, Meta_inv_blocks, device=0, condense=True, rtol=1e-12, max_it=60, precond=3,
+                 solver="cg", spectrum=None):
         self.lib = _lib.load()
         self._ctx = C.c_void_p()
         rc = self.lib.kexp_create(C.byref(self._ctx), int(device))
@@ -145,6 +166,7 @@ class Operator:
             self.condensed = True
             self.n_solve = plan.n_s
             self.nnz = {"Kt": plan.Kt.nnz, "As": plan.As.nnz, "Rt": plan.Rt.nnz}
+            As_host = plan.As
         else:
             k, m = _csr_args(K), _csr_args(Mu)
             self._check(self.lib.kexp_set_operator(
@@ -153,6 +175,15 @@ class Operator:
                 "kexp_set_operator")
             self.n_solve = self.n_u
             self.nnz = {"Kt": K.nnz, "As": Mu.nnz, "Rt": 0}
+            As_host = Mu
+        self.solver = solver
+        self.spectrum = None
+        if solver == "chebyshev":
+            self.spectrum = tuple(spectrum) if spectrum is not None else block_jacobi_spectrum(As_host)
+            self._check(self.lib.kexp_set_mass_solver_chebyshev(self._ctx, rtol, self.spectrum[0], self.spectrum[1], max_it),
+                        "kexp_set_mass_solver_chebyshev")
+        elif solver != "cg":
+            raise ValueError("solver must be 'cg' or 'chebyshev'")
         self._next_cheby_id = 0
 
     # -- plumbing
@@ -248,6 +279,10 @@ class DeviceBatch:
         self.op, self.B = op, int(B)
         self.handle = C.c_void_p()
         op._check(op.lib.kexp_batch_create(op.ctx, self.B, C.byref(self.handle)), "kexp_batch_create")
+
+    @property
+    def num_panels(self):
+        return int(self.op.lib.kexp_batch_num_panels(self.handle))
 
     def upload(self, X, shared=False):
         X = np.asarray(X, dtype=np.float64)

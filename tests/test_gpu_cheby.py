@@ -38,9 +38,10 @@ def ops(sw3):
     import krylov_exp_b200 as kx
     plain = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=False, rtol=1e-13, max_it=120)
     cond = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=True, rtol=1e-13, max_it=80)
-    assert cond.condensed and not plain.condensed
-    yield plain, cond
-    plain.close(); cond.close()
+    cheb = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=True, rtol=1e-13, max_it=80, solver="chebyshev")
+    assert cond.condensed and not plain.condensed and cheb.spectrum[1] / cheb.spectrum[0] < 8
+    yield plain, cond, cheb
+    plain.close(); cond.close(); cheb.close()
 
 
 @pytest.mark.parametrize("B", [1, 2, 3, 8, 17, 64, 70])
@@ -51,7 +52,7 @@ def test_spmm_K_matches_scipy(sw3, ops, B):
     assert np.abs(Y - ref).max() <= 1e-13 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("which", [0, 1, 2])
 @pytest.mark.parametrize("B", [1, 5, 64])
 def test_operator_apply_matches_oracle(sw3, ops, which, B):
     _, X = _inputs(sw3, B)
@@ -63,7 +64,7 @@ def test_operator_apply_matches_oracle(sw3, ops, which, B):
     assert st["last_max_rel_residual"] <= 1e-13
 
 
-@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("which", [0, 1, 2])
 def test_cheby_apply_matches_oracle(sw3, ops, which):
     import krylov_exp_b200 as kx
     from oracle import coeffs, cheby_ref
@@ -103,8 +104,8 @@ def test_cheby_golden_from_reference(golden):
     M = sp.csr_matrix((g["op_M_data"], g["op_M_indices"], g["op_M_indptr"]), shape=(n, n))
     Mu = M[:nu][:, :nu].tocsr()
     Meta = M[nu:][:, nu:].tobsr(blocksize=(3, 3)).data
-    for condense in (False, True):
-        op = kx.Operator(K, Mu, np.linalg.inv(Meta), condense=condense, rtol=1e-14, max_it=150)
+    for condense, solver in ((False, "cg"), (True, "cg"), (True, "chebyshev"), (False, "chebyshev")):
+        op = kx.Operator(K, Mu, np.linalg.inv(Meta), condense=condense, rtol=1e-14, max_it=150, solver=solver)
         T, L, nc = g["apply_meta"]
         ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L)
         assert ce.ncheb == int(nc)

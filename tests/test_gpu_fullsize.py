@@ -16,7 +16,7 @@ def setup5():
     import krylov_exp_b200 as kx
     from oracle.assemble_sw import test_pulse
     sw = get_sw(5)
-    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-12, max_it=50)
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-12, max_it=50, solver="chebyshev")
     L = kx.EIGS[2] * DT * RHO
     ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L)
     assert ce.ncheb == 29                                   # qjrms setup
