@@ -384,12 +384,13 @@ bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blo
 // Chebyshev semi-iteration for the mass system S w = b with the 3x3 block-Jacobi P:
 // the eigenvalues of P^-1 S lie in [lmin, lmax] (kappa ~ 5.2, mesh independent; estimated once
 // on the host), so
-//     z_k = P^-1 (b - S x_k),   d_k = c1_k d_{k-1} + c2_k z_k,   x_{k+1} = x_k + d_k
-// with host-side scalars c1_k, c2_k (Saad, Alg. 12.1) converges like CG (31 vs 29 iterations
-// for 1e-12) but needs NO inner products: the whole iteration is block-row local after the
-// sparse product and runs as ONE kernel -- gather x_k, stream b and d, write d and x_{k+1}
-// (40 n_s B bytes instead of CG's 80 n_s B in two kernels with two grid-wide reductions).
-// x ping-pongs between two panels because neighbours still gather x_k while x_{k+1} is written.
+//     z_k = P^-1 (b - S x_k),   x_{k+1} = x_{k-1} + omega_{k+1} (x_k + alpha z_k - x_{k-1})
+// (three-term Chebyshev acceleration, alpha = 2/(lmax+lmin), omega from the host) converges
+// like CG (31 vs 29 iterations for 1e-12) but needs NO inner products: the whole iteration is
+// block-row local after the sparse product and runs as ONE kernel -- gather x_k, stream b and
+// the own rows of x_{k-1}, overwrite them with x_{k+1} (32 n_s B bytes instead of CG's 80 n_s B
+// in two kernels with two grid-wide reductions).  Neighbours only ever gather x_k, which lives
+// in the other panel, so the in-place update of the x_{k-1} panel is race free.
 // LAST = 1 additionally accumulates ||b - S x_k||^2 per column (the residual one step behind,
 // hence conservative) for the convergence check of the fixed-length iteration.
 // Structure of the product as in bsr3_spmm_kernel.
@@ -398,8 +399,8 @@ template <int W, int LAST, int GB>
 __global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                       const double* __restrict__ Xold, double* __restrict__ Xnew, const double* __restrict__ Bv,
-                      double* __restrict__ D, const double* __restrict__ Pinv, int nbr, int max_bpr,
-                      double c1, double c2, int iters_done,
+                      const double* __restrict__ Pinv, int nbr, int max_bpr,
+                      double omega, double alpha, int iters_done,
                       CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
     using C = PanelCfg<W, kSpmmCpt>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -430,12 +431,12 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
                 const int k0 = sptr[br - sub], k1 = sptr[br - sub + 1];
                 const size_t o = (size_t)(3 * br) * W + 2 * l;
                 double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
-                double2 xo[3], bv[3], dv[3];
+                double2 xo[3], bv[3], xm[3];          // x_k (own rows), b, x_{k-1} (own rows; Xnew still holds it)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     xo[i] = ld2(Xold + o + (size_t)i * W);
                     bv[i] = ld2_stream(Bv + o + (size_t)i * W);
-                    dv[i] = ld2_stream(D + o + (size_t)i * W);
+                    xm[i] = ld2_stream(Xnew + o + (size_t)i * W);
                 }
                 for (int kg = k0; kg < k1; kg += GB) {
                     double2 x[GB][3];
@@ -476,10 +477,10 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
                     double2 z;
                     z.x = fma(Pb[3 * i], rv[0].x, fma(Pb[3 * i + 1], rv[1].x, Pb[3 * i + 2] * rv[2].x));
                     z.y = fma(Pb[3 * i], rv[0].y, fma(Pb[3 * i + 1], rv[1].y, Pb[3 * i + 2] * rv[2].y));
-                    dv[i].x = fma(c1, dv[i].x, c2 * z.x); dv[i].y = fma(c1, dv[i].y, c2 * z.y);
-                    xo[i].x += dv[i].x; xo[i].y += dv[i].y;
-                    st2(D + o + (size_t)i * W, dv[i]);
-                    st2(Xnew + o + (size_t)i * W, xo[i]);
+                    double2 xn;
+                    xn.x = fma(omega, fma(alpha, z.x, xo[i].x) - xm[i].x, xm[i].x);
+                    xn.y = fma(omega, fma(alpha, z.y, xo[i].y) - xm[i].y, xm[i].y);
+                    st2(Xnew + o + (size_t)i * W, xn);
                 }
             }
         }
@@ -518,11 +519,11 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
     }
 }
 
-// Chebyshev start (x_0 = 0):  d_0 = P^-1 b / theta,  x_1 = d_0,  bb = ||b||^2
+// Chebyshev start:  x_0 = 0,  x_1 = alpha P^-1 b,  bb = ||b||^2
 template <int W, int CPTMAX>
 __global__ void __launch_bounds__(kThreads)
-cheb_solve_init_kernel(const double* __restrict__ b, double* __restrict__ x, double* __restrict__ d,
-                       const double* __restrict__ Pinv, int ntriples, double inv_theta,
+cheb_solve_init_kernel(const double* __restrict__ b, double* __restrict__ x1, double* __restrict__ x0,
+                       const double* __restrict__ Pinv, int ntriples, double alpha,
                        CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
     using C = PanelCfg<W, CPTMAX>;
     constexpr int LPB = C::LPB, NV = C::NV;
@@ -547,9 +548,9 @@ cheb_solve_init_kernel(const double* __restrict__ b, double* __restrict__ x, dou
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const size_t oi = o + (size_t)i * W + 2 * LPB * j;
-                z[i][j].x *= inv_theta; z[i][j].y *= inv_theta;
-                st2(x + oi, z[i][j]);
-                st2(d + oi, z[i][j]);
+                z[i][j].x *= alpha; z[i][j].y *= alpha;
+                st2(x1 + oi, z[i][j]);
+                st2(x0 + oi, make_double2(0.0, 0.0));
                 acc[0][j].x = fma(rv[i][j].x, rv[i][j].x, acc[0][j].x); acc[0][j].y = fma(rv[i][j].y, rv[i][j].y, acc[0][j].y);
             }
     }

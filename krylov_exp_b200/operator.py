@@ -110,7 +110,7 @@ class CondensedPlan:
         self.order = order
 
 
-def block_jacobi_spectrum(As, safety=1.03):
+def block_jacobi_spectrum(As, safety=1.015):
     """Enclosure [lmin, lmax] of the spectrum of P^-1 S, P the 3x3 block-Jacobi of the SPD matrix S
     (host, once; SciPy Lanczos on the symmetrised L^-1 S L^-T, D = L L^T)."""
     from scipy.sparse.linalg import eigsh, splu
@@ -134,7 +134,7 @@ class Operator:
     preconditioned system, spectrum bounds estimated here on the host)."""
 
     def __init__(self, K, Mu, Meta_inv_blocks, device=0, condense=True, rtol=1e-12, max_it=60, precond=3,
-                 solver="cg", spectrum=None):
+                 solver="chebyshev", spectrum=None):
         self.lib = _lib.load()
         self._ctx = C.c_void_p()
         rc = self.lib.kexp_create(C.byref(self._ctx), int(device))

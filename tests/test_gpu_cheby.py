@@ -36,8 +36,8 @@ def _inputs(sw, B, seed=1234):
 @pytest.fixture(scope="module")
 def ops(sw3):
     import krylov_exp_b200 as kx
-    plain = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=False, rtol=1e-13, max_it=120)
-    cond = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=True, rtol=1e-13, max_it=80)
+    plain = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=False, rtol=1e-13, max_it=120, solver="cg")
+    cond = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=True, rtol=1e-13, max_it=80, solver="cg")
     cheb = kx.Operator(sw3.K, sw3.Mu, sw3.Meta_inv_blocks, condense=True, rtol=1e-13, max_it=80, solver="chebyshev")
     assert cond.condensed and not plain.condensed and cheb.spectrum[1] / cheb.spectrum[0] < 8
     yield plain, cond, cheb
