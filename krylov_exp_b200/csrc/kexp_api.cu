@@ -666,7 +666,7 @@ int kexp_create(kexp_ctx** out, int device) {
     if (ln && ln[0] == '1') { ctx->nlanes = 1; ctx->panel_cap = 64; }
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
     const char* pd = getenv("KEXP_PDL");
-    if (pd && pd[0] == '1') ctx->use_pdl = true;
+    if (pd && pd[0] == '0') ctx->use_pdl = false;
     const char* rb = getenv("KEXP_RED_BLOCKS");
     if (rb && atoi(rb) >= 1 && atoi(rb) <= 8) ctx->red_blocks_per_sm = atoi(rb);
     const char* ad = getenv("KEXP_ADAPTIVE_ITS");
@@ -847,7 +847,7 @@ int kexp_set_mass_solver_chebyshev(kexp_ctx* ctx, double rtol, double lmin, doub
     if (!(rtol > 0.0) || !(lmin > 0.0) || !(lmax > lmin) || max_it < 2) return kexp::fail(ctx, "bad Chebyshev mass solver parameters");
     if (kexp_set_mass_solver(ctx, rtol, max_it, 3)) return 1;
     const double sigma1 = (lmax + lmin) / (lmax - lmin);
-    int K = (int)std::ceil(std::acosh(1.0 / rtol) / std::acosh(sigma1));     // the measured residual is the arbiter (adaptive +4)
+    int K = (int)std::ceil(std::acosh(1.0 / rtol) / std::acosh(sigma1)) + 1;     // the measured residual is the arbiter (adaptive +2)
     K = std::max(2, std::min(K, max_it));
     ctx->solver = 1; ctx->cheb_lo = lmin; ctx->cheb_hi = lmax;
     ctx->graph_its = K; ctx->its_tuned = true;      // fixed length; only ever grows
@@ -998,8 +998,9 @@ int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out,
     if (read_cg_counters(ctx, &mx, &unc)) return 1;
     if (unc > ctx->unconverged_seen && ctx->graph_its < ctx->max_it) {
         // a solve hit the trimmed cap (CG) or missed rtol with the fixed length (Chebyshev): raise it and redo
-        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 4) : ctx->max_it;
+        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 2) : ctx->max_it;
         ctx->its_tuned = true;              // do not trim again
+        ctx->unconverged_seen = unc;
         invalidate_graphs(ctx);
         if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
         if (ctx->timing) drain_events(ctx);
@@ -1120,12 +1121,23 @@ int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     int maxW = 0;
     for (int W : in->panelW) maxW = std::max(maxW, W);
     if (ensure_panels(ctx, maxW)) return 1;
-    KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-    for (size_t p = 0; p < in->panel.size(); ++p) {
-        const int W = in->panelW[p];
-        DISPATCH_W(W, launch_operator_full<kW>(ctx, in->panel[p], out->panel[p]));
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+        bool ok = true;
+        for (size_t p = 0; p < in->panel.size(); ++p) {
+            const int W = in->panelW[p];
+            DISPATCH_W(W, launch_operator_full<kW>(ctx, in->panel[p], out->panel[p]));
+            int done = 1;          // the mass solve of this panel met rtol?
+            KEXP_CUDA(cudaMemcpyAsync(&done, &ctx->d_sc->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+            ok = ok && done;
+        }
+        KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+        if (ok || ctx->graph_its >= ctx->max_it) break;
+        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 2) : ctx->max_it;
+        ctx->its_tuned = true;
+        invalidate_graphs(ctx);
     }
-    KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
     KEXP_CUDA(cudaGetLastError());
     if (ctx->timing) drain_events(ctx);
     return 0;
