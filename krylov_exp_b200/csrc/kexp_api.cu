@@ -154,6 +154,7 @@ int max_grid(kexp_ctx* ctx, K kernel, int dyn_smem = 0) {
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, dyn_smem);
     occ = std::max(1, std::min(occ, 8));
+    if (dyn_smem > 0 && ctx->spmm_blocks_per_sm > 0) occ = std::min(occ, ctx->spmm_blocks_per_sm);   // experiment knob
     int g = occ * ctx->num_sms;
     ctx->occ_cache[key] = g;
     return g;
@@ -347,7 +348,20 @@ void enqueue_operator(kexp_ctx* ctx, const double* in) {
         for (int it = 1; it < K; ++it) {
             omega = (it == 1) ? 1.0 / (1.0 - 0.5 * mu * mu) : 1.0 / (1.0 - 0.25 * mu * mu * omega);
             TimedLaunch tl(ctx, KC_SPMM_CG);
-            if (it == K - 1) {
+            if (ctx->cheb_scalar_lanes) {
+                constexpr int per1 = LaneCfg<W>::BPC;
+                if (it == K - 1) {
+                    auto k = bsr3_cheb_iter1_kernel<W, 1, kSpmmGB>;
+                    int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per1 - 1) / per1));
+                    launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
+                             omega, alpha, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                } else {
+                    auto k = bsr3_cheb_iter1_kernel<W, 0, kSpmmGB>;
+                    int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per1 - 1) / per1));
+                    launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
+                             omega, alpha, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                }
+            } else if (it == K - 1) {
                 auto k = bsr3_cheb_iter_kernel<W, 1, kSpmmGB>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
@@ -522,6 +536,7 @@ void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, cg_init_kernel<W, kCptVec>); max_grid(ctx, cg_update_kernel<W, kCptVec>);
     max_grid(ctx, cheb_solve_init_kernel<W, kCptVec>);
     max_grid(ctx, bsr3_cheb_iter_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
+    max_grid(ctx, bsr3_cheb_iter1_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter1_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
 }
 
@@ -665,6 +680,10 @@ int kexp_create(kexp_ctx** out, int device) {
     const char* ln = getenv("KEXP_LANES");
     if (ln && ln[0] == '1') { ctx->nlanes = 1; ctx->panel_cap = 64; }
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
+    const char* sl = getenv("KEXP_SCALAR_LANES");
+    if (sl) ctx->cheb_scalar_lanes = (sl[0] == '1');
+    const char* sb = getenv("KEXP_SPMM_BLOCKS");
+    if (sb && atoi(sb) >= 1) ctx->spmm_blocks_per_sm = atoi(sb);
     const char* pd = getenv("KEXP_PDL");
     if (pd && pd[0] == '0') ctx->use_pdl = false;
     const char* rb = getenv("KEXP_RED_BLOCKS");
@@ -803,6 +822,14 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
     }
     cudaFree(ctx->d_v); ctx->d_v = nullptr;
     KEXP_CUDA(cudaMalloc(&ctx->d_v, sizeof(double) * (size_t)n));
+    {   // panels of 32 columns when that makes the mass-solve working set (3 panels of n_s rows) L2 resident
+        int l2 = 0;
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
+        const double ws32 = 3.0 * 8.0 * 32.0 * (double)n_s, ws64 = 2.0 * ws32;
+        if (!getenv("KEXP_LANES") && !getenv("KEXP_PANEL_CAP")) ctx->panel_cap = (ws64 > 0.75 * l2 && ws32 <= 0.75 * l2) ? 32 : 64;
+        const char* pc = getenv("KEXP_PANEL_CAP");
+        if (pc && (atoi(pc) == 32 || atoi(pc) == 64 || atoi(pc) == 16)) ctx->panel_cap = atoi(pc);
+    }
     ctx->have_op = true;
     return 0;
 }

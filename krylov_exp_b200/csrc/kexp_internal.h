@@ -101,6 +101,8 @@ struct kexp_ctx {
     bool its_tuned = false;
     bool adaptive_its = true;
     int unconverged_seen = 0;
+    int spmm_blocks_per_sm = 0;    // 0: from occupancy
+    bool cheb_scalar_lanes = false; // one column per lane in the Chebyshev iteration kernel (64 registers, 32 warps/SM)
     int red_blocks_per_sm = 4;     // grid of the reduction kernels
 
     kexp::ChebTable cheb[KEXP_MAX_CHEBY];
