@@ -1,10 +1,9 @@
+set -x
 cd /root/repo
-for cfg in "KEXP_SCALAR_LANES=0" "KEXP_SCALAR_LANES=1" "KEXP_SCALAR_LANES=1 KEXP_PANEL_CAP=64"; do
-env $cfg timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2>gpurun_out/b.err || tail -5 gpurun_out/b.err
-python - <<PY
-import json
-d=json.load(open('gpurun_out/b.json'))
-print('[$cfg]', round(d['value'],1), 'iter kernel us', round(d['kernels']['spmm_cg']['avg_us'],1), 'gbs', round(d['kernels']['spmm_cg']['gbs']), 'panels', d['config']['panels_per_batch'])
-PY
-done
-KEXP_SCALAR_LANES=1 timeout 600 python -m pytest tests/test_gpu_cheby.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -3
+export KEXP_NO_GRAPH=1
+python profiles/run_profile.py 5 64 > gpurun_out/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 400 --csv --log-file gpurun_out/launches_r1c.csv python profiles/run_profile.py 5 64 > gpurun_out/ncu1.log 2>&1
+tail -2 gpurun_out/plain.log
+python profiles/run_profile.py 5 64 > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'bsr3_cheb_iter_kernel|bsr3_spmm_kernel|cheb_update_kernel' -s 40 -c 8 -o gpurun_out/prof_r1c python profiles/run_profile.py 5 64 > gpurun_out/ncu2.log 2>&1
+tail -3 gpurun_out/ncu2.log
