@@ -345,7 +345,9 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name, "ncheb": int(ce.ncheb), "L": L, "N": int(n), "applications_per_step": apps_per_step,
-                       "l2": "working set ~0.6 GB per GPU (> 126 MB L2), no explicit flush",
+                       "l2": "inputs/outputs of a step ~0.9 GB per GPU (>> 126 MB L2), no explicit flush; inside one mass solve "
+                             "the 32-column panel (3 x 23.6 MB + matrix) is deliberately kept L2 resident, so the roofline "
+                             "figure is effective (algorithmic) bandwidth",
                        "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi {'Chebyshev iteration' if args.solver == 'chebyshev' else 'PCG'} rtol {args.cg_rtol:g}, "
                                      f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}",
                        "parallelism": f"samples sharded, {B}/GPU", "panels_per_batch": b_bwd_in.num_panels},
