@@ -467,6 +467,11 @@ void enqueue_cheby(kexp_ctx* ctx, int id) {
         int grid = (int)std::min<size_t>((size_t)8 * ctx->num_sms, (nelem2 + kThreads - 1) / kThreads);
         launch_k(ctx, cheb_init_kernel<W>, std::max(grid, 1), kThreads, 0, ctx->S0, ctx->Y, nelem2, tb.d_coef);
     }
+    const int bgrid = std::max(1, std::min(4 * ctx->num_sms, (int)((ctx->n + kThreads - 1) / kThreads)));
+    if (ctx->capture_basis) {
+        TimedLaunch tl(ctx, KC_MISC);
+        launch_k(ctx, basis_store_kernel<W>, bgrid, kThreads, 0, ctx->S0, (int)ctx->n, ctx->d_basis, ctx->basis_ld, 0);
+    }
     for (int n = 1; n <= tb.ncheb; ++n) {
         const double* in = (n & 1) ? ctx->S0 : ctx->S1;     // S_{n-1}
         double* Sn = (n & 1) ? ctx->S1 : ctx->S0;           // holds S_{n-2}, becomes S_n
@@ -474,6 +479,10 @@ void enqueue_cheby(kexp_ctx* ctx, int id) {
         ChebStep st;
         st.n = n; st.has_old = (n >= 2) ? 1 : 0; st.cs = (n == 1) ? 1.0 : 2.0; st.check_cg = 1;
         enqueue_cheb_update<W>(ctx, Sn, tb.d_coef, st);
+        if (ctx->capture_basis) {
+            TimedLaunch tl(ctx, KC_MISC);
+            launch_k(ctx, basis_store_kernel<W>, bgrid, kThreads, 0, Sn, (int)ctx->n, ctx->d_basis, ctx->basis_ld, n);
+        }
     }
 }
 
@@ -494,7 +503,7 @@ int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
         KEXP_CUDA(cudaGetLastError());
         return 0;
     }
-    auto key = std::make_pair(id, W);
+    auto key = std::make_pair(id + (ctx->capture_basis ? 1000 : 0), W);
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
         // warm the occupancy cache outside capture
@@ -512,7 +521,8 @@ int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
     KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
     const ChebTable& tb = ctx->cheb[id];
     ctx->st_op_apps += tb.ncheb;
-    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + (ctx->solver == 1 ? ctx->graph_its - 1 : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
+    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + (ctx->solver == 1 ? ctx->graph_its - 1 : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0))
+                        + (ctx->capture_basis ? tb.ncheb + 1 : 0);
     return 0;
 }
 
@@ -610,6 +620,15 @@ int colsum_panel(kexp_ctx* ctx, const double* Ypanel, const double* w, int col0,
 }  // namespace
 
 namespace {
+template <int W>
+void launch_combine(kexp_ctx* ctx, int nb, const double* D, double* Y) {
+    auto k = basis_combine_kernel<W>;
+    const size_t smem = sizeof(double) * (size_t)nb * W;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = std::min(8 * ctx->num_sms, blocks_for(ctx->n, W / 2));
+    k<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_basis, ctx->basis_ld, nb, D, Y, (int)ctx->n);
+}
+
 int alloc_lane_scalars(kexp_ctx* ctx) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_sc, sizeof(CgScalars)) == cudaSuccess;
@@ -682,6 +701,8 @@ int kexp_create(kexp_ctx** out, int device) {
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
     const char* sl = getenv("KEXP_SCALAR_LANES");
     if (sl) ctx->cheb_scalar_lanes = (sl[0] == '1');
+    const char* shb = getenv("KEXP_SHARED_BASIS");
+    if (shb && shb[0] == '0') ctx->use_shared_basis = false;
     const char* sb = getenv("KEXP_SPMM_BLOCKS");
     if (sb && atoi(sb) >= 1) ctx->spmm_blocks_per_sm = atoi(sb);
     const char* pd = getenv("KEXP_PDL");
@@ -715,7 +736,7 @@ int kexp_destroy(kexp_ctx* ctx) {
     }
     free_csr(ctx->Kt); free_csr(ctx->As); free_csr(ctx->Rt);
     double* bufs[] = {ctx->S0, ctx->S1, ctx->Y, ctx->T, ctx->X, ctx->P, ctx->Q, ctx->d_Dblk, ctx->d_Pinv,
-                      ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_v};
+                      ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_v, ctx->d_basis, ctx->d_D};
     for (double* b : bufs) cudaFree(b);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sc); cudaFree(ctx->d_counter);
     for (int i = 0; i < KEXP_MAX_CHEBY; ++i) cudaFree(ctx->cheb[i].d_coef);
@@ -892,6 +913,7 @@ int kexp_set_cheby(kexp_ctx* ctx, int id, const double* a, int ncheb, double L) 
     KEXP_CUDA(cudaMalloc(&tb.d_coef, sizeof(double) * (size_t)(ncheb + 1)));
     KEXP_CUDA(cudaMemcpy(tb.d_coef, a, sizeof(double) * (size_t)(ncheb + 1), cudaMemcpyHostToDevice));
     tb.ncheb = ncheb; tb.L = L;
+    tb.h_coef.assign(a, a + ncheb + 1);
     return 0;
 }
 
@@ -925,6 +947,7 @@ int kexp_batch_destroy(kexp_batch* b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     for (double* p : b->panel) cudaFree(p);
+    cudaFree(b->shared_vec);
     delete b;
     return 0;
 }
@@ -938,8 +961,15 @@ int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shar
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * nvec)) return 1;
     KEXP_CUDA(cudaMemcpy2DAsync(ctx->d_stage, sizeof(double) * ctx->n, X, sizeof(double) * (x_is_shared ? ctx->n : ldx),
                                 sizeof(double) * ctx->n, nvec, cudaMemcpyHostToDevice, ctx->stream));
-    for (size_t p = 0; p < b->panel.size(); ++p)
-        if (pack_panel(ctx, ctx->d_stage, ctx->n, x_is_shared, b->B, (int)p * b->stride, b->panelW[p], b->panel[p])) return 1;
+    b->is_shared = x_is_shared != 0;
+    if (b->is_shared && ctx->use_shared_basis) {
+        // one vector only: the forward pass runs the recurrence for a single column (see basis_combine_kernel)
+        if (!b->shared_vec) KEXP_CUDA(cudaMalloc(&b->shared_vec, sizeof(double) * 2 * (size_t)ctx->n));
+        if (pack_panel(ctx, ctx->d_stage, ctx->n, 1, 1, 0, 2, b->shared_vec)) return 1;
+    } else {
+        for (size_t p = 0; p < b->panel.size(); ++p)
+            if (pack_panel(ctx, ctx->d_stage, ctx->n, x_is_shared, b->B, (int)p * b->stride, b->panelW[p], b->panel[p])) return 1;
+    }
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -949,6 +979,7 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
     kexp_ctx* ctx = b->ctx;
     cudaSetDevice(ctx->device);
     if (ldy < ctx->n) return kexp::fail(ctx, "ldy < n");
+    if (b->is_shared && ctx->use_shared_basis) return kexp::fail(ctx, "a shared-input batch holds one vector; nothing to download");
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
     for (size_t p = 0; p < b->panel.size(); ++p)
         if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * b->stride, b->panelW[p])) return 1;
@@ -958,8 +989,94 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
     return 0;
 }
 
+// Combination coefficients of the shared-input path: D[m][k] = sum_n a_n E_nm(s_k), where
+// S_n(s b) = sum_m E_nm(s) S_m(b).  Multiplication by b in the S basis: b S_0 = S_1,
+// b S_m = (S_{m+1} - S_{m-1}) / 2; then E_0 = e_0, E_1 = s shift(E_0), E_n = 2 s shift(E_{n-1}) + E_{n-2}.
+static void expansion_column(const std::vector<double>& a, double s, double* Dcol, int stride) {
+    const int nb = (int)a.size();
+    std::vector<double> e0((size_t)nb + 2, 0.0), e1((size_t)nb + 2, 0.0), e2((size_t)nb + 2, 0.0), sh((size_t)nb + 2, 0.0);
+    auto shift = [&](const std::vector<double>& e, std::vector<double>& o) {
+        std::fill(o.begin(), o.end(), 0.0);
+        o[1] += e[0];
+        for (int m = 1; m <= nb; ++m) { o[m + 1] += 0.5 * e[m]; o[m - 1] -= 0.5 * e[m]; }
+    };
+    e0[0] = 1.0;
+    for (int m = 0; m < nb; ++m) Dcol[(size_t)m * stride] = a[0] * e0[m];
+    if (nb == 1) return;
+    shift(e0, sh);
+    for (int m = 0; m <= nb; ++m) e1[m] = s * sh[m];
+    for (int m = 0; m < nb; ++m) Dcol[(size_t)m * stride] += a[1] * e1[m];
+    for (int n = 2; n < nb; ++n) {
+        shift(e1, sh);
+        for (int m = 0; m <= nb; ++m) e2[m] = 2.0 * s * sh[m] + e0[m];
+        for (int m = 0; m < nb; ++m) Dcol[(size_t)m * stride] += a[n] * e2[m];
+        e0.swap(e1); e1.swap(e2);
+    }
+}
+
+// Forward half of an averaged evaluation: one input for all sample times.
+static int cheby_apply_shared(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
+    const ChebTable& tb = ctx->cheb[id];
+    const int nb = tb.ncheb + 1;
+    const int B = in->B;
+    double tstar = 0.0;
+    for (int k = 0; k < B; ++k) tstar = std::max(tstar, std::fabs(t[k]));
+    if (tstar == 0.0) tstar = 1.0;
+    const int ld = (nb + 3) & ~3;
+    if (ctx->basis_ld < ld) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_basis); ctx->d_basis = nullptr; ctx->basis_ld = 0;
+        KEXP_CUDA(cudaMalloc(&ctx->d_basis, sizeof(double) * (size_t)ctx->n * ld));
+        ctx->basis_ld = ld;
+        invalidate_graphs(ctx);
+    }
+    // coefficients for every output panel, panel p at offset nb * (sum of earlier widths)
+    size_t totW = 0;
+    for (int W : out->panelW) totW += (size_t)W;
+    std::vector<double> D((size_t)nb * totW, 0.0);
+    {
+        size_t off = 0;
+        for (size_t p = 0; p < out->panel.size(); ++p) {
+            const int W = out->panelW[p];
+            for (int c = 0; c < W; ++c) {
+                const int k = (int)p * out->stride + c;
+                if (k < B) expansion_column(tb.h_coef, t[k] / tstar, &D[off + c], W);
+            }
+            off += (size_t)nb * W;
+        }
+    }
+    if (swap_lane(ctx, 0)) return 1;
+    cudaStreamSynchronize(ctx->stream);              // d_D reuse
+    cudaFree(ctx->d_D); ctx->d_D = nullptr;
+    KEXP_CUDA(cudaMalloc(&ctx->d_D, sizeof(double) * D.size()));
+    KEXP_CUDA(cudaMemcpy(ctx->d_D, D.data(), sizeof(double) * D.size(), cudaMemcpyHostToDevice));
+    if (ensure_panels(ctx, 2)) return 1;
+    warm_occupancy<2>(ctx);
+    max_grid(ctx, basis_store_kernel<2>);
+    if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    if (set_tscale(ctx, id, &tstar, 0, 1, 2)) return 1;
+    KEXP_CUDA(cudaMemcpyAsync(ctx->S0, in->shared_vec, sizeof(double) * 2 * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->capture_basis = true;
+    const int rc = run_cheby_panel(ctx, id, 2);
+    ctx->capture_basis = false;
+    if (rc) return 1;
+    size_t off = 0;
+    for (size_t p = 0; p < out->panel.size(); ++p) {
+        const int W = out->panelW[p];
+        TimedLaunch tl(ctx, KC_MISC);
+        DISPATCH_W(W, launch_combine<kW>(ctx, nb, ctx->d_D + off, out->panel[p]));
+        off += (size_t)nb * W;
+    }
+    KEXP_CUDA(cudaGetLastError());
+    if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    return 0;
+}
+
 static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
     if (check_ready(ctx, id)) return 1;
+    if (in && out && t && in != out && in->B == out->B && in->is_shared && in->shared_vec && ctx->use_shared_basis &&
+        (size_t)(ctx->cheb[id].ncheb + 1) * 64 * sizeof(double) <= 160 * 1024)
+        return cheby_apply_shared(ctx, id, in, out, t, time_it);
     if (!in || !out || !t) return kexp::fail(ctx, "null argument");
     if (in == out) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
     if (in->B != out->B) return kexp::fail(ctx, "batch sizes differ");

@@ -51,6 +51,7 @@ struct ChebTable {
     int ncheb = -1;
     double L = 0.0;
     double* d_coef = nullptr;      // ncheb+1 doubles
+    std::vector<double> h_coef;    // host copy (shared-input expansion coefficients)
 };
 
 struct KrylovState;               // kexp_krylov.cu
@@ -121,6 +122,11 @@ struct kexp_ctx {
     double* h_stage = nullptr;     // pinned host staging
     size_t h_stage_bytes = 0;
     double* d_v = nullptr;         // n doubles (average result)
+    double* d_basis = nullptr;     // n x basis_ld: U_m of the shared-input path
+    int basis_ld = 0;
+    double* d_D = nullptr;         // (ncheb+1) x 64 combination coefficients
+    bool use_shared_basis = true;  // KEXP_SHARED_BASIS=0: treat shared-input batches as 64 independent columns
+    bool capture_basis = false;    // enqueue_cheby stores every S_m (column 0) into d_basis
 
     // graphs keyed by (cheby id, W)
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
@@ -166,6 +172,8 @@ struct kexp_batch {
     std::vector<int> panelW;       // width of each panel
     std::vector<double*> panel;    // [n][W] device buffers, internal order
     int stride = 64;               // first column of panel p is p*stride
+    double* shared_vec = nullptr;  // [n][2] panel holding the one input of a shared-input batch (column 1 = 0)
+    bool is_shared = false;
 };
 
 namespace kexp {

@@ -987,6 +987,47 @@ cheb_init_kernel(const double* __restrict__ S0, double* __restrict__ Y, size_t n
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Shared-input batches (the forward half of an averaged evaluation: every ensemble member starts
+// from the same U, timestepping_methods.py:7).  All columns then live in one polynomial space:
+// with U_m = S_m((t*/L) A) x for t* = max|t_k|, and s_k = t_k/t*,
+//     y_k = sum_n a_n S_n(s_k (t*/L) A) x = sum_m D[m][k] U_m,
+// because S_n(s b) = sum_m E_nm(s) S_m(b) with |E_nm| <= 1 for |s| <= 1 (host recurrence).
+// So the recurrence runs for ONE column and the 64 results are a small dense combination.
+// basis_store: column 0 of a panel -> basis[:, m];  basis_combine: Y[i,k] = sum_m basis[i][m] D[m][k].
+// ------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+basis_store_kernel(const double* __restrict__ S, int n, double* __restrict__ basis, int ld, int m) {
+    pdl_wait();
+    pdl_trigger();
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+        basis[(size_t)i * ld + m] = S[(size_t)i * W];
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+basis_combine_kernel(const double* __restrict__ basis, int ld, int nb, const double* __restrict__ D,
+                     double* __restrict__ Y, int n) {
+    constexpr int LPR = W / 2;
+    extern __shared__ double sD[];                   // nb x W
+    for (int e = threadIdx.x; e < nb * W; e += kThreads) sD[e] = D[e];
+    __syncthreads();
+    const int l = threadIdx.x % LPR;
+    const int g0 = (blockIdx.x * kThreads + threadIdx.x) / LPR;
+    const int ng = gridDim.x * kThreads / LPR;
+    for (int i = g0; i < n; i += ng) {
+        const double* bi = basis + (size_t)i * ld;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int m = 0; m < nb; ++m) {
+            const double u = __ldg(bi + m);
+            acc.x = fma(u, sD[m * W + 2 * l], acc.x);
+            acc.y = fma(u, sD[m * W + 2 * l + 1], acc.y);
+        }
+        st2(Y + (size_t)i * W + 2 * l, acc);
+    }
+}
+
 // Plain W = op output without recurrence (operator_apply): rows as in cheb_update, out = Wv
 template <int W, int SRC>
 __global__ void __launch_bounds__(kThreads)
