@@ -332,6 +332,12 @@ def main():
             bytes_launch = cs["bytes_per_col"] * (B / b_bwd_in.num_panels) + cs["matrix_bytes"]
             if name == "cheb_update":                 # three row-range launches form one pass
                 executed = st_t["op_applications"]
+            if name == "spmm_cg" and args.solver == "chebyshev" and cs["launches"] == st_t["cg_solves"] and cs["launches"] > 0:
+                # cooperative kernel: ONE launch per mass solve = start + (K-1) iterations, matrix staged once
+                executed = cs["launches"]
+                K = st_t["cg_iterations"] / st_t["cg_solves"]
+                Wp = B / b_bwd_in.num_panels
+                bytes_launch = ((K - 1) * 32.0 + 24.0) * op.n_solve * Wp + cs["matrix_bytes"]
             avg_ms = cs["ms"] / max(executed, 1)
             kernels[name] = {"ms_total": cs["ms"], "launches": int(executed), "avg_us": avg_ms * 1e3,
                              "algorithmic_bytes": bytes_launch, "gbs": bytes_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None}

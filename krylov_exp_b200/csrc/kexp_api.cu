@@ -336,6 +336,27 @@ void enqueue_operator(kexp_ctx* ctx, const double* in) {
         // x_1 in xk, x_0 = 0 in xm; iteration k overwrites x_{k-1} with x_{k+1}; x_K must end up in ctx->X
         double* xk = (K % 2 == 1) ? ctx->X : ctx->P;
         double* xm = (xk == ctx->X) ? ctx->P : ctx->X;
+        {   // one cooperative kernel for the whole solve when every CTA's row range fits its shared-memory stage
+            const DevCsr& A = ctx->As;
+            auto k = cheb_solve_coop_kernel<W, kSpmmGB>;
+            constexpr int per_cta0 = PanelCfg<W, kSpmmCpt>::BPC;
+            const int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta0 - 1) / per_cta0));
+            const int rows_cta = (A.nbr + grid - 1) / grid;
+            if (ctx->use_coop && K >= 2 && rows_cta <= kSpmmSmemRows && (int64_t)rows_cta * A.max_bpr <= kSpmmSmemBlocks && !ctx->timing_split) {
+                TimedLaunch tl(ctx, KC_SPMM_CG);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads);
+                cfg.dynamicSmemBytes = kSpmmSmemBytes; cfg.stream = ctx->stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeCooperative;
+                attr[0].val.cooperative = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                cudaLaunchKernelEx(&cfg, k, (const int*)A.browptr, (const double*)A.blocks, (const double*)ctx->T, xk, xm,
+                                   (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                ctx->st_op_apps++;
+                return;
+            }
+        }
         {
             auto k = cheb_solve_init_kernel<W, kCptVec>;
             int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
@@ -521,7 +542,7 @@ int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
     KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
     const ChebTable& tb = ctx->cheb[id];
     ctx->st_op_apps += tb.ncheb;
-    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + (ctx->solver == 1 ? ctx->graph_its - 1 : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0))
+    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0))
                         + (ctx->capture_basis ? tb.ncheb + 1 : 0);
     return 0;
 }
@@ -545,6 +566,7 @@ void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, bsr3_spmm_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_spmm_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cg_init_kernel<W, kCptVec>); max_grid(ctx, cg_update_kernel<W, kCptVec>);
     max_grid(ctx, cheb_solve_init_kernel<W, kCptVec>);
+    max_grid(ctx, cheb_solve_coop_kernel<W, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, bsr3_cheb_iter_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, bsr3_cheb_iter1_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter1_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
@@ -701,6 +723,8 @@ int kexp_create(kexp_ctx** out, int device) {
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
     const char* sl = getenv("KEXP_SCALAR_LANES");
     if (sl) ctx->cheb_scalar_lanes = (sl[0] == '1');
+    const char* co = getenv("KEXP_COOP");
+    if (co) ctx->use_coop = (co[0] == '1');
     const char* shb = getenv("KEXP_SHARED_BASIS");
     if (shb && shb[0] == '0') ctx->use_shared_basis = false;
     const char* sb = getenv("KEXP_SPMM_BLOCKS");

@@ -12,6 +12,7 @@
 //   three-term recurrence    cheby_exp.py:138-165              -> cheb_* kernels
 //   DU *= wt; allreduce      timestepping_methods.py:10-11     -> weighted_colsum
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -522,6 +523,169 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
                 if (iters_done > sc->max_iters) sc->max_iters = iters_done;
                 sc->done = bad ? 0 : 1;        // cheb_update records an unconverged solve when done == 0
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// The whole Chebyshev mass solve as ONE cooperative kernel: every CTA stages the matrix blocks,
+// row pointers and preconditioner blocks of its contiguous row range in shared memory once and
+// keeps them for all K-1 iterations; iterations are separated by a grid-wide barrier instead of a
+// kernel boundary (no relaunch, no re-staging of the 12 MB matrix per iteration).  The barrier is
+// followed by __threadfence(), whose gpu-scope fence invalidates L1 (CCTL.IVALL), so the gathered
+// rows written by other SMs in the previous iteration are re-fetched while re-use inside an
+// iteration still hits L1.  Needs (rows per CTA) <= kSpmmSmemRows and their blocks <= kSpmmSmemBlocks
+// (checked on the host; otherwise one kernel per iteration, bsr3_cheb_iter_kernel).
+// ------------------------------------------------------------------------------------
+template <int W, int GB>
+__global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
+cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
+                       const double* __restrict__ Bv, double* xk, double* xm,
+                       const double* __restrict__ Pinv, int nbr, int K, double alpha, double mu,
+                       CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
+    namespace cg = cooperative_groups;
+    using C = PanelCfg<W, kSpmmCpt>;
+    constexpr int LPB = C::LPB, BRW = C::BRW;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double2 sblk[];
+    double* sP = reinterpret_cast<double*>(sblk + 5 * kSpmmSmemBlocks);
+    int* sptr = reinterpret_cast<int*>(sP + 9 * kSpmmSmemRows);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % LPB, g = lane / LPB;
+    const int per = nbr / gridDim.x, rem = nbr % gridDim.x;
+    const int start = blockIdx.x * per + min((int)blockIdx.x, rem);
+    const int end = start + per + ((int)blockIdx.x < rem ? 1 : 0);
+    {
+        const int kb0 = __ldg(browptr + start), kb1 = __ldg(browptr + end);
+        const double2* gsrc = reinterpret_cast<const double2*>(blocks) + (size_t)5 * kb0;
+        for (int i = threadIdx.x; i < 5 * (kb1 - kb0); i += kThreads) sblk[i] = __ldg(gsrc + i);
+        for (int i = threadIdx.x; i <= end - start; i += kThreads) sptr[i] = __ldg(browptr + start + i) - kb0;
+        for (int i = threadIdx.x; i < 9 * (end - start); i += kThreads) sP[i] = __ldg(Pinv + (size_t)9 * start + i);
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    double2 acc2[2][1] = {{make_double2(0.0, 0.0)}, {make_double2(0.0, 0.0)}};     // ||r||^2 (last iteration), ||b||^2
+    // start: x_0 = 0 (xm), x_1 = alpha P^-1 b (xk)
+    for (int base = start; base < end; base += C::BPC) {
+        const int br = base + warp * BRW + g;
+        if (br < end) {
+            const size_t o = (size_t)(3 * br) * W + 2 * l;
+            double2 bv[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                bv[i] = ld2(Bv + o + (size_t)i * W);
+                acc2[1][0].x = fma(bv[i].x, bv[i].x, acc2[1][0].x); acc2[1][0].y = fma(bv[i].y, bv[i].y, acc2[1][0].y);
+            }
+            const double* Pb = sP + 9 * (br - start);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double2 z;
+                z.x = alpha * fma(Pb[3 * i], bv[0].x, fma(Pb[3 * i + 1], bv[1].x, Pb[3 * i + 2] * bv[2].x));
+                z.y = alpha * fma(Pb[3 * i], bv[0].y, fma(Pb[3 * i + 1], bv[1].y, Pb[3 * i + 2] * bv[2].y));
+                st2(xk + o + (size_t)i * W, z);
+                st2(xm + o + (size_t)i * W, make_double2(0.0, 0.0));
+            }
+        }
+    }
+    grid.sync();
+    __threadfence();
+    double omega = 1.0;
+    for (int it = 1; it < K; ++it) {
+        omega = (it == 1) ? 1.0 / (1.0 - 0.5 * mu * mu) : 1.0 / (1.0 - 0.25 * mu * mu * omega);
+        const bool last = (it == K - 1);
+        for (int base = start; base < end; base += C::BPC) {
+            const int br = base + warp * BRW + g;
+            if (br < end) {
+                const int k0 = sptr[br - start], k1 = sptr[br - start + 1];
+                const size_t o = (size_t)(3 * br) * W + 2 * l;
+                double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+                double2 xo[3], bv[3], xmv[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    xo[i] = ld2(xk + o + (size_t)i * W);
+                    bv[i] = ld2(Bv + o + (size_t)i * W);
+                    xmv[i] = ld2(xm + o + (size_t)i * W);
+                }
+                for (int kg = k0; kg < k1; kg += GB) {
+                    double2 x[GB][3];
+#pragma unroll
+                    for (int j = 0; j < GB; ++j) {
+                        if (kg + j < k1) {
+                            const int c = __double2loint(sblk[5 * (kg + j) + 4].y);
+                            const double* xr = xk + (size_t)(3 * c) * W + 2 * l;
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) x[j][r] = ld2(xr + (size_t)r * W);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < GB; ++j) {
+                        if (kg + j < k1) {
+                            const double2* bp = sblk + 5 * (kg + j);
+                            const double2 v01 = bp[0], v23 = bp[1], v45 = bp[2], v67 = bp[3], v8c = bp[4];
+                            const double a[3][3] = {{v01.x, v01.y, v23.x}, {v23.y, v45.x, v45.y}, {v67.x, v67.y, v8c.x}};
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    acc[i].x = fma(a[i][r], x[j][r].x, acc[i].x);
+                                    acc[i].y = fma(a[i][r], x[j][r].y, acc[i].y);
+                                }
+                        }
+                    }
+                }
+                double2 rv[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    rv[i].x = bv[i].x - acc[i].x; rv[i].y = bv[i].y - acc[i].y;
+                    if (last) { acc2[0][0].x = fma(rv[i].x, rv[i].x, acc2[0][0].x); acc2[0][0].y = fma(rv[i].y, rv[i].y, acc2[0][0].y); }
+                }
+                const double* Pb = sP + 9 * (br - start);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    double2 z, xn;
+                    z.x = fma(Pb[3 * i], rv[0].x, fma(Pb[3 * i + 1], rv[1].x, Pb[3 * i + 2] * rv[2].x));
+                    z.y = fma(Pb[3 * i], rv[0].y, fma(Pb[3 * i + 1], rv[1].y, Pb[3 * i + 2] * rv[2].y));
+                    xn.x = fma(omega, fma(alpha, z.x, xo[i].x) - xmv[i].x, xmv[i].x);
+                    xn.y = fma(omega, fma(alpha, z.y, xo[i].y) - xmv[i].y, xmv[i].y);
+                    st2(xm + o + (size_t)i * W, xn);
+                }
+            }
+        }
+        if (!last) {
+            grid.sync();
+            __threadfence();
+        }
+        double* tsw = xk; xk = xm; xm = tsw;
+    }
+    if (block_partials<W, kSpmmCpt, 2>(acc2, partials, counter)) {
+        double s[2];
+        final_sums<W, 2>(partials, s);
+        __shared__ int bad;
+        __shared__ double max_rel[kMaxW];
+        if (threadIdx.x == 0) bad = 0;
+        __syncthreads();
+        if (threadIdx.x < W) {
+            const int c = threadIdx.x;
+            sc->rr[c] = s[0]; sc->bb[c] = s[1];
+            sc->active[c] = (s[1] > 0.0) ? 1 : 0;
+            double rel = 0.0;
+            if (s[1] > 0.0) {
+                rel = s[0] / s[1];
+                if (s[0] > sc->rtol2 * s[1]) atomicOr(&bad, 1);
+            }
+            max_rel[c] = rel;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            for (int c = 0; c < W; ++c) m = fmax(m, max_rel[c]);
+            sc->max_rel_res = sqrt(m);
+            sc->iters = K;
+            sc->total_iters += (unsigned long long)K;
+            sc->total_solves += 1ull;
+            if (K > sc->max_iters) sc->max_iters = K;
+            sc->done = bad ? 0 : 1;
         }
     }
 }
