@@ -318,7 +318,7 @@ void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
 // ---- one batched application of M^-1 K on the work panels: input `in` (n x W),
 // leaves T (rows needing no solve), X (solved rows). W is a template parameter.
 template <int W>
-void enqueue_operator(kexp_ctx* ctx, const double* in) {
+void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
     constexpr int LPB = PanelCfg<W, kCptVec>::LPB;
     cudaStream_t s = ctx->stream;
     const int ns = (int)ctx->n_s;
@@ -332,7 +332,10 @@ void enqueue_operator(kexp_ctx* ctx, const double* in) {
         // Chebyshev semi-iteration: one fused kernel per iteration, no inner products
         const double alpha = 2.0 / (ctx->cheb_hi + ctx->cheb_lo);
         const double mu = (ctx->cheb_hi - ctx->cheb_lo) / (ctx->cheb_hi + ctx->cheb_lo);
-        const int K = ctx->graph_its;
+        // relaxed tolerance of this Chebyshev term (see kexp_set_cheby): rtol*relax needs ln(relax)/acosh(sigma) fewer iterations
+        const double sigma1 = (ctx->cheb_hi + ctx->cheb_lo) / (ctx->cheb_hi - ctx->cheb_lo);
+        const int K = std::max(2, ctx->graph_its - (int)std::floor(std::log(relax) / std::acosh(sigma1)));
+        const double rtol2 = (ctx->rtol * relax) * (ctx->rtol * relax);
         // x_1 in xk, x_0 = 0 in xm; iteration k overwrites x_{k-1} with x_{k+1}; x_K must end up in ctx->X
         double* xk = (K % 2 == 1) ? ctx->X : ctx->P;
         double* xm = (xk == ctx->X) ? ctx->P : ctx->X;
@@ -352,7 +355,7 @@ void enqueue_operator(kexp_ctx* ctx, const double* in) {
                 attr[0].val.cooperative = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
                 cudaLaunchKernelEx(&cfg, k, (const int*)A.browptr, (const double*)A.blocks, (const double*)ctx->T, xk, xm,
-                                   (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                                   (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
                 ctx->st_op_apps++;
                 return;
             }
@@ -375,23 +378,23 @@ void enqueue_operator(kexp_ctx* ctx, const double* in) {
                     auto k = bsr3_cheb_iter1_kernel<W, 1, kSpmmGB>;
                     int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per1 - 1) / per1));
                     launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                             omega, alpha, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                             omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
                 } else {
                     auto k = bsr3_cheb_iter1_kernel<W, 0, kSpmmGB>;
                     int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per1 - 1) / per1));
                     launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                             omega, alpha, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                             omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
                 }
             } else if (it == K - 1) {
                 auto k = bsr3_cheb_iter_kernel<W, 1, kSpmmGB>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                         omega, alpha, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                         omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
             } else {
                 auto k = bsr3_cheb_iter_kernel<W, 0, kSpmmGB>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                         omega, alpha, K, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                         omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
             }
             std::swap(xk, xm);
         }
@@ -496,7 +499,7 @@ void enqueue_cheby(kexp_ctx* ctx, int id) {
     for (int n = 1; n <= tb.ncheb; ++n) {
         const double* in = (n & 1) ? ctx->S0 : ctx->S1;     // S_{n-1}
         double* Sn = (n & 1) ? ctx->S1 : ctx->S0;           // holds S_{n-2}, becomes S_n
-        enqueue_operator<W>(ctx, in);
+        enqueue_operator<W>(ctx, in, (ctx->use_relax && ctx->solver == 1) ? tb.h_relax[n] : 1.0);
         ChebStep st;
         st.n = n; st.has_old = (n >= 2) ? 1 : 0; st.cs = (n == 1) ? 1.0 : 2.0; st.check_cg = 1;
         enqueue_cheb_update<W>(ctx, Sn, tb.d_coef, st);
@@ -723,6 +726,8 @@ int kexp_create(kexp_ctx** out, int device) {
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
     const char* sl = getenv("KEXP_SCALAR_LANES");
     if (sl) ctx->cheb_scalar_lanes = (sl[0] == '1');
+    const char* rl = getenv("KEXP_RELAX");
+    if (rl) ctx->use_relax = (rl[0] == '1');
     const char* co = getenv("KEXP_COOP");
     if (co) ctx->use_coop = (co[0] == '1');
     const char* shb = getenv("KEXP_SHARED_BASIS");
@@ -938,6 +943,21 @@ int kexp_set_cheby(kexp_ctx* ctx, int id, const double* a, int ncheb, double L) 
     KEXP_CUDA(cudaMemcpy(tb.d_coef, a, sizeof(double) * (size_t)(ncheb + 1), cudaMemcpyHostToDevice));
     tb.ncheb = ncheb; tb.L = L;
     tb.h_coef.assign(a, a + ncheb + 1);
+    // Tolerance relaxation per term: an error introduced in the mass solve of term n reaches y only through
+    // sum_{m>=n} a_m U_{m-n}(B) e with ||U_k|| <= k+1 on the spectrum, i.e. with weight w_n = sum_{m>=n} |a_m| (m-n+1).
+    // The a_m decay super-exponentially beyond m ~ L, so late terms tolerate rtol * w_max / w_n (capped).
+    tb.h_relax.assign((size_t)ncheb + 1, 1.0);
+    {
+        std::vector<double> wgt((size_t)ncheb + 1, 0.0);
+        double wmax = 0.0;
+        for (int n = 1; n <= ncheb; ++n) {
+            double w = 0.0;
+            for (int m = n; m <= ncheb; ++m) w += std::fabs(a[m]) * (double)(m - n + 1);
+            wgt[n] = w; wmax = std::max(wmax, w);
+        }
+        for (int n = 1; n <= ncheb; ++n)
+            if (wgt[n] > 0.0) tb.h_relax[n] = std::min(1e6, std::max(1.0, wmax / wgt[n]));
+    }
     return 0;
 }
 

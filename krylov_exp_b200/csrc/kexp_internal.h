@@ -52,6 +52,7 @@ struct ChebTable {
     double L = 0.0;
     double* d_coef = nullptr;      // ncheb+1 doubles
     std::vector<double> h_coef;    // host copy (shared-input expansion coefficients)
+    std::vector<double> h_relax;   // per-term tolerance relaxation factor of the mass solve (>= 1)
 };
 
 struct KrylovState;               // kexp_krylov.cu
@@ -103,6 +104,7 @@ struct kexp_ctx {
     bool adaptive_its = true;
     int unconverged_seen = 0;
     int spmm_blocks_per_sm = 0;    // 0: from occupancy
+    bool use_relax = true;         // relax the mass-solve tolerance of late Chebyshev terms (KEXP_RELAX=0: uniform rtol)
     bool use_coop = true;          // whole Chebyshev mass solve as one cooperative kernel (KEXP_COOP=0: one kernel per iteration)
     bool timing_split = false;     // reserved
     bool cheb_scalar_lanes = false; // one column per lane in the Chebyshev iteration kernel (64 registers, 32 warps/SM)

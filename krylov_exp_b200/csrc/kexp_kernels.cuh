@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                       const double* __restrict__ Xold, double* __restrict__ Xnew, const double* __restrict__ Bv,
                       const double* __restrict__ Pinv, int nbr, int max_bpr,
-                      double omega, double alpha, int iters_done,
+                      double omega, double alpha, int iters_done, double rtol2,
                       CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
     using C = PanelCfg<W, kSpmmCpt>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -509,7 +509,7 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
                 double rel = 0.0;
                 if (sc->bb[c] > 0.0) {
                     rel = s[0] / sc->bb[c];
-                    if (s[0] > sc->rtol2 * sc->bb[c]) atomicOr(&bad, 1);
+                    if (s[0] > rtol2 * sc->bb[c]) atomicOr(&bad, 1);
                 }
                 max_rel[c] = rel;
             }
@@ -541,7 +541,7 @@ template <int W, int GB>
 __global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                        const double* __restrict__ Bv, double* xk, double* xm,
-                       const double* __restrict__ Pinv, int nbr, int K, double alpha, double mu,
+                       const double* __restrict__ Pinv, int nbr, int K, double alpha, double mu, double rtol2,
                        CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
     namespace cg = cooperative_groups;
     using C = PanelCfg<W, kSpmmCpt>;
@@ -672,7 +672,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
             double rel = 0.0;
             if (s[1] > 0.0) {
                 rel = s[0] / s[1];
-                if (s[0] > sc->rtol2 * s[1]) atomicOr(&bad, 1);
+                if (s[0] > rtol2 * s[1]) atomicOr(&bad, 1);
             }
             max_rel[c] = rel;
         }
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 bsr3_cheb_iter1_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                        const double* __restrict__ Xold, double* __restrict__ Xnew, const double* __restrict__ Bv,
                        const double* __restrict__ Pinv, int nbr, int max_bpr,
-                       double omega, double alpha, int iters_done,
+                       double omega, double alpha, int iters_done, double rtol2,
                        CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
     using C = LaneCfg<W>;
     extern __shared__ double2 sblk[];
@@ -811,7 +811,7 @@ bsr3_cheb_iter1_kernel(const int* __restrict__ browptr, const double* __restrict
                 double rel = 0.0;
                 if (sc->bb[c] > 0.0) {
                     rel = s[0] / sc->bb[c];
-                    if (s[0] > sc->rtol2 * sc->bb[c]) atomicOr(&bad, 1);
+                    if (s[0] > rtol2 * sc->bb[c]) atomicOr(&bad, 1);
                 }
                 max_rel[c] = rel;
             }

@@ -53,7 +53,8 @@ def test_ref5_against_cpu_port(setup5):
         e, h, l2 = norms.calculate_norm(sw, Y[k], ref[i])   # eta L2, u H(div), u L2 (calculate_norm.py:94-96)
         assert max(e, h, l2) < 1e-10, (k, e, h, l2)
     st = op.stats()
-    assert st["last_max_rel_residual"] <= 1e-12
+    # the last solve belongs to the last Chebyshev term, whose tolerance is relaxed by up to 1e6
+    assert st["last_max_rel_residual"] <= 1e-12 * 1e6
 
 
 def test_ref5_forward_backward_roundtrip(setup5):
