@@ -95,3 +95,30 @@ def test_krylov_matches_oracle_and_cheby(sw3):
     assert abs(_relM(M, y, yc) - _relM(M, yo, yc)) < 1e-7
     assert _relM(M, y, yc) < 5e-3
     op.close()
+
+
+def test_krylov_ref4_kdim40_matches_oracle():
+    """M4-sized Krylov space (kdim 40, test_krylov.py:89-90) at ref 4: the GPU Arnoldi follows the oracle.  The
+    SAI-Krylov result itself agrees with Chebyshev only to ~1e-3 here -- with exact solves in the oracle too --
+    so that gap is a property of the reference algorithm (gamma = t/10, MGS, inv(H)), not of this port."""
+    import krylov_exp_b200 as kx
+    from oracle import krylov_ref
+    from oracle.assemble_sw import test_pulse
+    from conftest import get_sw
+    sw = get_sw(4)
+    t, kdim = 7200.0, 40
+    gamma = t / 10.0
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13, max_it=80)
+    sh = kx.ShiftedOperator(op, sw.K, sw.Mu, sw.Meta_blocks, gamma, rtol=1e-13)
+    ke = kx.krylov_exp(sh, None, None, gamma, kdim, op, None, None)
+    x = test_pulse(sw)
+    y = np.empty(sw.n)
+    ke.apply(x, y, t, residuals=False)
+    M = sw.M()
+    lu_s = splu((M + gamma * sw.K).tocsc())
+    lu_m = splu(M.tocsc())
+    yo, Ho, uo, _ = krylov_ref.krylov_apply(lambda v: lu_s.solve(M @ v), lambda v: lu_m.solve(sw.K @ v),
+                                            lambda a, b: a @ (M @ b), x, t, gamma, kdim, residuals=False)
+    assert np.abs(ke.H - Ho).max() <= 1e-6 * np.abs(Ho).max()
+    assert _relM(M, y, yo) < 1e-5
+    op.close()
