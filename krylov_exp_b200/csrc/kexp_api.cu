@@ -342,8 +342,8 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
         {   // one cooperative kernel for the whole solve when every CTA's row range fits its shared-memory stage
             const DevCsr& A = ctx->As;
             auto k = cheb_solve_coop_kernel<W, kSpmmGB>;
-            constexpr int per_cta0 = PanelCfg<W, kSpmmCpt>::BPC;
-            const int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta0 - 1) / per_cta0));
+            // as many CTAs as can be co-resident (narrow panels would otherwise get few, long row ranges)
+            const int grid = std::max(1, std::min(max_grid(ctx, k, kSpmmSmemBytes), A.nbr));
             const int rows_cta = (A.nbr + grid - 1) / grid;
             if (ctx->use_coop && K >= 2 && rows_cta <= kSpmmSmemRows && (int64_t)rows_cta * A.max_bpr <= kSpmmSmemBlocks && !ctx->timing_split) {
                 TimedLaunch tl(ctx, KC_SPMM_CG);
