@@ -91,6 +91,7 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
     blocks.reserve((size_t)(rp[nrows] / 9 + nbr) * 10);
     std::vector<int> cols;
     int max_bpr = 1;
+    bool all_diag = true;
     for (int b = 0; b < nbr; ++b) {
         cols.clear();
         for (int k = rp[3 * b]; k < rp[3 * b + 3]; ++k) cols.push_back(ci[k] / 3);
@@ -107,6 +108,16 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
                 const size_t j = std::lower_bound(cols.begin(), cols.end(), ci[k] / 3) - cols.begin();
                 blocks[base + j * 10 + 3 * i + (ci[k] % 3)] += v[k];
             }
+        if (force && nrows == ncols) {
+            // diagonal block first: the solve kernels take the row's own x from the gathered diagonal block
+            const size_t jd = std::lower_bound(cols.begin(), cols.end(), b) - cols.begin();
+            if (jd < cols.size() && cols[jd] == b) {
+                if (jd != 0)
+                    for (int e = 0; e < 10; ++e) std::swap(blocks[base + jd * 10 + e], blocks[base + e]);
+            } else {
+                all_diag = false;
+            }
+        }
         browptr[b + 1] = browptr[b] + (int)cols.size();
         max_bpr = std::max(max_bpr, (int)cols.size());
     }
@@ -117,6 +128,7 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
     KEXP_CUDA(cudaMemcpy(d.browptr, browptr.data(), sizeof(int) * (size_t)(nbr + 1), cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.blocks, blocks.data(), sizeof(double) * 10 * (size_t)nblocks, cudaMemcpyHostToDevice));
     d.nbr = nbr; d.nblocks = nblocks; d.max_bpr = max_bpr;
+    d.diag_first = force && nrows == ncols && all_diag;
     if (force && nrows == ncols) build_tma_chunks(ctx, d, browptr, blocks);
     if (max_bpr > kSpmmSmemBlocks) { cudaFree(d.browptr); cudaFree(d.blocks); d.browptr = nullptr; d.blocks = nullptr; }
     return 0;
@@ -355,7 +367,7 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
                 attr[0].val.cooperative = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
                 cudaLaunchKernelEx(&cfg, k, (const int*)A.browptr, (const double*)A.blocks, (const double*)ctx->T, xk, xm,
-                                   (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                                   (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, rtol2, A.diag_first ? 1 : 0, ctx->d_sc, ctx->d_partials, ctx->d_counter);
                 ctx->st_op_apps++;
                 return;
             }

@@ -24,6 +24,7 @@ struct DevCsr {
     double* blocks = nullptr;
     int nbr = 0;
     int max_bpr = 1;               // most blocks in any block row
+    bool diag_first = false;       // every block row starts with its diagonal block
     int64_t nblocks = 0;
     // chunked copy for the TMA-staged CG product (kexp_spmm_tma.cuh)
     int* ccolptr = nullptr;

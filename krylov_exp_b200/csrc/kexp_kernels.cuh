@@ -541,7 +541,7 @@ template <int W, int GB>
 __global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                        const double* __restrict__ Bv, double* xk, double* xm,
-                       const double* __restrict__ Pinv, int nbr, int K, double alpha, double mu, double rtol2,
+                       const double* __restrict__ Pinv, int nbr, int K, double alpha, double mu, double rtol2, int diag_first,
                        CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
     namespace cg = cooperative_groups;
     using C = PanelCfg<W, kSpmmCpt>;
@@ -603,7 +603,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                 double2 xo[3], bv[3], xmv[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
-                    xo[i] = ld2(xk + o + (size_t)i * W);
+                    if (!diag_first) xo[i] = ld2(xk + o + (size_t)i * W);
                     bv[i] = ld2(Bv + o + (size_t)i * W);
                     xmv[i] = ld2(xm + o + (size_t)i * W);
                 }
@@ -617,6 +617,10 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
 #pragma unroll
                             for (int r = 0; r < 3; ++r) x[j][r] = ld2(xr + (size_t)r * W);
                         }
+                    }
+                    if (diag_first && kg == k0) {          // the row's own x_k: the diagonal block is gathered first
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) xo[i] = x[0][i];
                     }
 #pragma unroll
                     for (int j = 0; j < GB; ++j) {
