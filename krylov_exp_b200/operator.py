@@ -113,7 +113,7 @@ class CondensedPlan:
 def block_jacobi_spectrum(As, safety=1.015):
     """Enclosure [lmin, lmax] of the spectrum of P^-1 S, P the 3x3 block-Jacobi of the SPD matrix S
     (host, once; SciPy Lanczos on the symmetrised L^-1 S L^-T, D = L L^T)."""
-    from scipy.sparse.linalg import eigsh, splu
+    from scipy.sparse.linalg import eigsh
     As = _csr(As)
     n = As.shape[0]
     nb = n // 3
@@ -123,8 +123,9 @@ def block_jacobi_spectrum(As, safety=1.015):
     Li = np.linalg.inv(np.linalg.cholesky(D))
     LiM = sp.bsr_matrix((Li, np.arange(nb), np.arange(nb + 1)), shape=(n, n)).tocsr()
     Sym = (LiM @ As @ LiM.T).tocsc()
-    lmax = float(eigsh(Sym, k=1, which="LA", return_eigenvectors=False, tol=1e-5)[0])
-    lmin = float(eigsh(Sym, k=1, sigma=0.0, which="LM", return_eigenvectors=False, tol=1e-5)[0])
+    # plain Lanczos (no factorisation): Ritz values lie inside the spectrum, hence the safety factor
+    lmax = float(eigsh(Sym, k=1, which="LA", return_eigenvectors=False, tol=1e-4, ncv=40)[0])
+    lmin = float(eigsh(Sym, k=1, which="SA", return_eigenvectors=False, tol=1e-4, ncv=40)[0])
     return lmin / safety, lmax * safety
 
 
