@@ -119,7 +119,7 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-def cpu_reference_run(sw, L, t, x, ncols, steps, warmup, rtol=1e-5, literal=True):
+def cpu_reference_run(sw, L, t, x, ncols, steps, warmup, rtol=1e-5, literal=True, nthreads=0):
     """The reference's CPU algorithm (literal recurrence cheby_exp.py:110-165, CG at PETSc's default
     rtol 1e-5, one sample time per core) through the oracle's C/OpenMP port.  Returns per-step seconds."""
     from oracle import coeffs
@@ -132,9 +132,9 @@ def cpu_reference_run(sw, L, t, x, ncols, steps, warmup, rtol=1e-5, literal=True
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        cpu.apply_batch(coef, n, L, X, tk, literal=literal)
+        cpu.apply_batch(coef, n, L, X, tk, literal=literal, nthreads=nthreads)   # explicit: torchrun exports OMP_NUM_THREADS=1
         times.append(time.perf_counter() - t0)
-    return times[warmup:], cpu.num_threads(), n
+    return times[warmup:], (nthreads if nthreads > 0 else cpu.num_threads()), n
 
 
 def main():
@@ -169,7 +169,7 @@ def main():
             return
         sw, L, t, w, x = workload(args.ref_level, args.samples)
         ncols = cores
-        times, nthreads, ncheb = cpu_reference_run(sw, L, t, x, ncols, args.steps, max(args.warmup, 1))
+        times, nthreads, ncheb = cpu_reference_run(sw, L, t, x, ncols, args.steps, max(args.warmup, 1), nthreads=cores)
         per = float(np.mean(times))
         val = ncols / per
         sample = (f"{ncols} of the {args.samples} backward applications per step (one per host thread), literal "
@@ -376,7 +376,7 @@ def main():
     # ------------------------------------------------------------ CPU baseline (rank 0, N = 1)
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
-        times, nthreads, ncheb = cpu_reference_run(sw, L, t, x, cores, 1, 1)
+        times, nthreads, ncheb = cpu_reference_run(sw, L, t, x, cores, 1, 1, nthreads=cores)
         cpu = {"value": cores / float(np.mean(times)), "unit": "applications/s", "cores": nthreads, "kind": "port",
                "sample": f"{cores} backward applications (one per host thread), literal 2*ncheb-1={2 * ncheb - 1} solves, "
                          f"block-Jacobi CG rtol 1e-5; oracle/cpu_cheby.c"}

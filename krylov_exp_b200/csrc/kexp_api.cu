@@ -1103,8 +1103,11 @@ static int cheby_apply_shared(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch*
     }
     if (swap_lane(ctx, 0)) return 1;
     cudaStreamSynchronize(ctx->stream);              // d_D reuse
-    cudaFree(ctx->d_D); ctx->d_D = nullptr;
-    KEXP_CUDA(cudaMalloc(&ctx->d_D, sizeof(double) * D.size()));
+    if (ctx->d_D_cap < D.size()) {
+        cudaFree(ctx->d_D); ctx->d_D = nullptr; ctx->d_D_cap = 0;
+        KEXP_CUDA(cudaMalloc(&ctx->d_D, sizeof(double) * D.size()));
+        ctx->d_D_cap = D.size();
+    }
     KEXP_CUDA(cudaMemcpy(ctx->d_D, D.data(), sizeof(double) * D.size(), cudaMemcpyHostToDevice));
     if (ensure_panels(ctx, 2)) return 1;
     warm_occupancy<2>(ctx);

@@ -130,6 +130,7 @@ struct kexp_ctx {
     double* d_basis = nullptr;     // n x basis_ld: U_m of the shared-input path
     int basis_ld = 0;
     double* d_D = nullptr;         // (ncheb+1) x 64 combination coefficients
+    size_t d_D_cap = 0;
     bool use_shared_basis = true;  // KEXP_SHARED_BASIS=0: treat shared-input batches as 64 independent columns
     bool capture_basis = false;    // enqueue_cheby stores every S_m (column 0) into d_basis
 
