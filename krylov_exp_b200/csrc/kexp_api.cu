@@ -788,6 +788,8 @@ int kexp_destroy(kexp_ctx* ctx) {
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ev_prev) cudaEventDestroy(ctx->ev_prev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->nccl_comm && ctx->nccl_lib) {
@@ -1002,32 +1004,83 @@ int kexp_batch_destroy(kexp_batch* b) {
     if (!b) return 0;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
+    if (b->pending && b->ctx->copy_stream) cudaStreamSynchronize(b->ctx->copy_stream);
     for (double* p : b->panel) cudaFree(p);
+    for (cudaEvent_t e : b->ready) cudaEventDestroy(e);
     cudaFree(b->shared_vec);
     delete b;
     return 0;
 }
 
-int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared) {
+// Upload of a host batch.  Distinct-input batches are copied and packed panel by panel on a separate copy
+// stream, each panel signalling an event; with wait == false the caller (the host-pointer entry points) starts
+// computing on panel 0 while panel 1 is still crossing PCIe.
+static int finish_upload(kexp_batch* b) {
+    kexp_ctx* ctx = b->ctx;
+    if (b->pending) {
+        KEXP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        b->pending = false;
+    }
+    return 0;
+}
+
+static int batch_upload_impl(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared, bool wait) {
     if (!b || !X) return 1;
     kexp_ctx* ctx = b->ctx;
     cudaSetDevice(ctx->device);
+    if (swap_lane(ctx, 0)) return 1;
     const int nvec = x_is_shared ? 1 : b->B;
     if (!x_is_shared && ldx < ctx->n) return kexp::fail(ctx, "ldx < n");
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * nvec)) return 1;
-    KEXP_CUDA(cudaMemcpy2DAsync(ctx->d_stage, sizeof(double) * ctx->n, X, sizeof(double) * (x_is_shared ? ctx->n : ldx),
-                                sizeof(double) * ctx->n, nvec, cudaMemcpyHostToDevice, ctx->stream));
     b->is_shared = x_is_shared != 0;
-    if (b->is_shared && ctx->use_shared_basis) {
-        // one vector only: the forward pass runs the recurrence for a single column (see basis_combine_kernel)
-        if (!b->shared_vec) KEXP_CUDA(cudaMalloc(&b->shared_vec, sizeof(double) * 2 * (size_t)ctx->n));
-        if (pack_panel(ctx, ctx->d_stage, ctx->n, 1, 1, 0, 2, b->shared_vec)) return 1;
-    } else {
-        for (size_t p = 0; p < b->panel.size(); ++p)
-            if (pack_panel(ctx, ctx->d_stage, ctx->n, x_is_shared, b->B, (int)p * b->stride, b->panelW[p], b->panel[p])) return 1;
+    if (finish_upload(b)) return 1;
+    if (b->is_shared) {
+        KEXP_CUDA(cudaMemcpy2DAsync(ctx->d_stage, sizeof(double) * ctx->n, X, sizeof(double) * ctx->n, sizeof(double) * ctx->n, 1,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->use_shared_basis) {
+            // one vector only: the forward pass runs the recurrence for a single column (see basis_combine_kernel)
+            if (!b->shared_vec) KEXP_CUDA(cudaMalloc(&b->shared_vec, sizeof(double) * 2 * (size_t)ctx->n));
+            if (pack_panel(ctx, ctx->d_stage, ctx->n, 1, 1, 0, 2, b->shared_vec)) return 1;
+        } else {
+            for (size_t p = 0; p < b->panel.size(); ++p)
+                if (pack_panel(ctx, ctx->d_stage, ctx->n, 1, b->B, (int)p * b->stride, b->panelW[p], b->panel[p])) return 1;
+        }
+        KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
     }
-    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->copy_stream) {
+        KEXP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        KEXP_CUDA(cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming));
+    }
+    while (b->ready.size() < b->panel.size()) {
+        cudaEvent_t e;
+        KEXP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->ready.push_back(e);
+    }
+    // the copy stream starts after whatever the compute stream still does with the staging buffer / the panels
+    KEXP_CUDA(cudaEventRecord(ctx->ev_prev, ctx->stream));
+    KEXP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prev, 0));
+    cudaStream_t compute = ctx->stream;
+    ctx->stream = ctx->copy_stream;                  // pack kernels of this upload run behind their copy
+    int rc = 0;
+    for (size_t p = 0; p < b->panel.size() && !rc; ++p) {
+        const int col0 = (int)p * b->stride;
+        const int ncols = std::min(b->panelW[p], b->B - col0);
+        cudaError_t e = cudaMemcpy2DAsync(ctx->d_stage + (size_t)col0 * ctx->n, sizeof(double) * ctx->n, X + (size_t)col0 * ldx,
+                                          sizeof(double) * ldx, sizeof(double) * ctx->n, ncols, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e != cudaSuccess) { rc = kexp::fail(ctx, cudaGetErrorString(e)); break; }
+        rc = pack_panel(ctx, ctx->d_stage, ctx->n, 0, b->B, col0, b->panelW[p], b->panel[p]);
+        if (!rc && cudaEventRecord(b->ready[p], ctx->copy_stream) != cudaSuccess) rc = kexp::fail(ctx, "event record failed");
+    }
+    ctx->stream = compute;
+    if (rc) return rc;
+    b->pending = true;
+    if (wait) return finish_upload(b);
     return 0;
+}
+
+int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared) {
+    return batch_upload_impl(b, X, ldx, x_is_shared, true);
 }
 
 int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
@@ -1036,6 +1089,7 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
     cudaSetDevice(ctx->device);
     if (ldy < ctx->n) return kexp::fail(ctx, "ldy < n");
     if (b->is_shared && ctx->use_shared_basis) return kexp::fail(ctx, "a shared-input batch holds one vector; nothing to download");
+    if (finish_upload(b)) return 1;
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
     for (size_t p = 0; p < b->panel.size(); ++p)
         if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * b->stride, b->panelW[p])) return 1;
@@ -1159,6 +1213,7 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
         }
         const int W = in->panelW[p];
         if (ensure_panels(ctx, W)) return 1;
+        if (in->pending) KEXP_CUDA(cudaStreamWaitEvent(ctx->stream, in->ready[p], 0));     // panel still being uploaded
         const size_t bytes = sizeof(double) * (size_t)ctx->n * W;
         if (set_tscale(ctx, id, t, p * in->stride, in->B, W)) return 1;
         KEXP_CUDA(cudaMemcpyAsync(ctx->S0, in->panel[p], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1258,6 +1313,7 @@ int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev) {
     if (!b || !w || !v_dev) return 1;
     kexp_ctx* ctx = b->ctx;
     cudaSetDevice(ctx->device);
+    if (finish_upload(b)) return 1;
     for (size_t p = 0; p < b->panel.size(); ++p)
         if (colsum_panel(ctx, b->panel[p], w, (int)p * b->stride, b->B, b->panelW[p], v_dev, p > 0)) return 1;
     return 0;
@@ -1285,7 +1341,7 @@ int kexp_cheby_apply_batch(kexp_ctx* ctx, int id, const double* X, int64_t ldx, 
     if (X == Y) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
     kexp_batch *bi = nullptr, *bo = nullptr;
     int rc = scratch_batches(ctx, B, &bi, &bo);
-    if (!rc) rc = kexp_batch_upload(bi, X, ldx, x_is_shared);
+    if (!rc) rc = batch_upload_impl(bi, X, ldx, x_is_shared, false);
     if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
     if (!rc) rc = kexp_batch_download(bo, Y, ldy);
     return rc;
@@ -1304,7 +1360,7 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
     if (!X || !t || !w || !v_out || B < 1) return kexp::fail(ctx, "bad arguments");
     kexp_batch *bi = nullptr, *bo = nullptr;
     int rc = scratch_batches(ctx, B, &bi, &bo);
-    if (!rc) rc = kexp_batch_upload(bi, X, ldx, x_is_shared);
+    if (!rc) rc = batch_upload_impl(bi, X, ldx, x_is_shared, false);
     if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
     if (!rc) rc = kexp_batch_average_dev(bo, w, ctx->d_v);
     if (!rc && do_allreduce) rc = kexp_allreduce_sum_dev(ctx, ctx->d_v, ctx->n);
@@ -1321,6 +1377,7 @@ int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     if (!ctx->have_op) return kexp::fail(ctx, "operator not set");
     if (!in || !out || in->B != out->B) return kexp::fail(ctx, "bad batches");
     cudaSetDevice(ctx->device);
+    if (finish_upload(in)) return 1;
     int maxW = 0;
     for (int W : in->panelW) maxW = std::max(maxW, W);
     if (ensure_panels(ctx, maxW)) return 1;
@@ -1351,6 +1408,7 @@ int kexp_spmm_K_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     if (!ctx->have_op) return kexp::fail(ctx, "operator not set");
     if (!in || !out || in->B != out->B || in == out) return kexp::fail(ctx, "bad batches");
     cudaSetDevice(ctx->device);
+    if (finish_upload(in)) return 1;
     KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
     for (size_t p = 0; p < in->panel.size(); ++p) {
         const int W = in->panelW[p];

@@ -161,7 +161,8 @@ struct kexp_ctx {
     int cur_lane = 0;
     int nlanes = 1;
     int panel_cap = 64;            // widest panel a new batch gets (32 with two lanes)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prev = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host->device uploads overlap the compute of the previous panel
 
     // krylov
     kexp::KrylovState* kry = nullptr;
@@ -180,6 +181,8 @@ struct kexp_batch {
     int stride = 64;               // first column of panel p is p*stride
     double* shared_vec = nullptr;  // [n][2] panel holding the one input of a shared-input batch (column 1 = 0)
     bool is_shared = false;
+    std::vector<cudaEvent_t> ready;   // per panel: upload + pack finished (copy stream)
+    bool pending = false;          // an asynchronous upload may still be in flight
 };
 
 namespace kexp {
