@@ -155,8 +155,6 @@ int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp
 // ------------------------------------------------------------------ launch plumbing
 namespace {
 
-struct CaptureStats { int64_t launches = 0; };
-
 template <typename K>
 int max_grid(kexp_ctx* ctx, K kernel, int dyn_smem = 0) {
     const void* key = (const void*)kernel;
@@ -357,7 +355,7 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
             // as many CTAs as can be co-resident (narrow panels would otherwise get few, long row ranges)
             const int grid = std::max(1, std::min(max_grid(ctx, k, kSpmmSmemBytes), A.nbr));
             const int rows_cta = (A.nbr + grid - 1) / grid;
-            if (ctx->use_coop && K >= 2 && rows_cta <= kSpmmSmemRows && (int64_t)rows_cta * A.max_bpr <= kSpmmSmemBlocks && !ctx->timing_split) {
+            if (ctx->use_coop && K >= 2 && rows_cta <= kSpmmSmemRows && (int64_t)rows_cta * A.max_bpr <= kSpmmSmemBlocks) {
                 TimedLaunch tl(ctx, KC_SPMM_CG);
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads);

@@ -107,7 +107,6 @@ struct kexp_ctx {
     int spmm_blocks_per_sm = 0;    // 0: from occupancy
     bool use_relax = true;         // relax the mass-solve tolerance of late Chebyshev terms (KEXP_RELAX=0: uniform rtol)
     bool use_coop = true;          // whole Chebyshev mass solve as one cooperative kernel (KEXP_COOP=0: one kernel per iteration)
-    bool timing_split = false;     // reserved
     bool cheb_scalar_lanes = false; // one column per lane in the Chebyshev iteration kernel (64 registers, 32 warps/SM)
     int red_blocks_per_sm = 4;     // grid of the reduction kernels
 
