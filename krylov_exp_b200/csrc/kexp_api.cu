@@ -25,7 +25,7 @@ int pick_W(int B) {
 
 void free_csr(DevCsr& d) {
     cudaFree(d.rowptr); cudaFree(d.col); cudaFree(d.val);
-    cudaFree(d.browptr); cudaFree(d.blocks);
+    cudaFree(d.browptr); cudaFree(d.blocks); cudaFree(d.rowmap);
     cudaFree(d.ccolptr); cudaFree(d.ccols); cudaFree(d.lblocks);
     d = DevCsr();
 }
@@ -123,10 +123,39 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
     }
     const int64_t nblocks = browptr[nbr];
     if (!force && (double)nblocks * 9.0 > 1.4 * (double)rp[nrows]) return 0;
+    // Rectangular-coupled matrices (K~: edge / interior / depth rows of one cell gather the same column blocks but
+    // live far apart): store the block rows sorted by their smallest block column, so that a CTA's contiguous range
+    // re-uses gathered rows out of L1; rowmap gives the output block row of each stored row.
+    std::vector<int> rowmap;
+    const char* ro = getenv("KEXP_NO_ROW_ORDER");
+    if (!force && !(ro && ro[0] == '1')) {
+        std::vector<int> key((size_t)nbr), order((size_t)nbr);
+        for (int b = 0; b < nbr; ++b) {
+            int mn = ncols;
+            for (int k = browptr[b]; k < browptr[b + 1]; ++k) { int64_t bits; memcpy(&bits, &blocks[(size_t)k * 10 + 9], 8); mn = std::min(mn, (int)bits); }
+            key[b] = mn; order[b] = b;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return key[a] < key[b2]; });
+        std::vector<int> bp2((size_t)nbr + 1, 0);
+        std::vector<double> bl2(blocks.size());
+        size_t w = 0;
+        for (int i = 0; i < nbr; ++i) {
+            const int b = order[i];
+            const size_t cnt = (size_t)(browptr[b + 1] - browptr[b]);
+            memcpy(&bl2[w * 10], &blocks[(size_t)browptr[b] * 10], cnt * 10 * sizeof(double));
+            w += cnt;
+            bp2[i + 1] = (int)w;
+        }
+        browptr.swap(bp2); blocks.swap(bl2); rowmap.swap(order);
+    }
     KEXP_CUDA(cudaMalloc(&d.browptr, sizeof(int) * (size_t)(nbr + 1)));
     KEXP_CUDA(cudaMalloc(&d.blocks, sizeof(double) * 10 * (size_t)std::max<int64_t>(nblocks, 1)));
     KEXP_CUDA(cudaMemcpy(d.browptr, browptr.data(), sizeof(int) * (size_t)(nbr + 1), cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.blocks, blocks.data(), sizeof(double) * 10 * (size_t)nblocks, cudaMemcpyHostToDevice));
+    if (!rowmap.empty()) {
+        KEXP_CUDA(cudaMalloc(&d.rowmap, sizeof(int) * (size_t)nbr));
+        KEXP_CUDA(cudaMemcpy(d.rowmap, rowmap.data(), sizeof(int) * (size_t)nbr, cudaMemcpyHostToDevice));
+    }
     d.nbr = nbr; d.nblocks = nblocks; d.max_bpr = max_bpr;
     d.diag_first = force && nrows == ncols && all_diag;
     if (force && nrows == ncols) build_tma_chunks(ctx, d, browptr, blocks);
@@ -316,7 +345,7 @@ void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
         constexpr int per_cta = PanelCfg<W, kSpmmCpt>::BPC;
         int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
         launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, X, Y, A.nbr, A.max_bpr, ctx->T, ctx->d_Pinv,
-                 ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                 (const int*)A.rowmap, ctx->d_sc, ctx->d_partials, ctx->d_counter);
     } else {
         // MODE 1 (the CG product) always has a BSR copy: n_s is a multiple of 3 by contract
         auto k = csr_spmm_kernel<W>;

@@ -22,6 +22,7 @@ struct DevCsr {
     // the 3-dofs-per-entity structure with little fill
     int* browptr = nullptr;
     double* blocks = nullptr;
+    int* rowmap = nullptr;         // stored block row -> output block row (locality ordering), or null
     int nbr = 0;
     int max_bpr = 1;               // most blocks in any block row
     bool diag_first = false;       // every block row starts with its diagonal block

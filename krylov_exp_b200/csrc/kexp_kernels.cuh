@@ -274,7 +274,7 @@ template <int W, int MODE, int GB>
 __global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                  const double* __restrict__ X, double* __restrict__ Y, int nbr, int max_bpr,
-                 const double* __restrict__ R, const double* __restrict__ Pinv,
+                 const double* __restrict__ R, const double* __restrict__ Pinv, const int* __restrict__ rowmap,
                  CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
     using C = PanelCfg<W, kSpmmCpt>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -309,7 +309,8 @@ bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blo
             const int br = base + warp * BRW + g;
             if (br < sub_end) {
                 const int k0 = sptr[br - sub], k1 = sptr[br - sub + 1];
-                const size_t o = (size_t)(3 * br) * W + 2 * l;
+                const int orow = (MODE == 0 && rowmap) ? __ldg(rowmap + br) : br;      // MODE 1 matrices keep their row order
+                const size_t o = (size_t)(3 * orow) * W + 2 * l;
                 double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
                 double2 pv[3], rv[3];
                 if (MODE == 1) {
