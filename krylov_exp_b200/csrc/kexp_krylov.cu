@@ -6,8 +6,11 @@
 //                 Hinv, H1 = (Hinv - I)/gamma, expm(-H1 s t) e1       :87-99  (one CTA)
 //   y = beta sum_j u_j V_j                                            :102-109
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <string>
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 #include "kexp_internal.h"
 #include "kexp_krylov_kernels.cuh"
@@ -39,6 +42,19 @@ struct KrylovState {
     double* d_svals = nullptr;
     int grid = 148;
     int coop_grid = 148;
+    // one-kernel BiCGStab (default); KEXP_BICG_HOST=1 keeps the host-driven loop for comparison
+    bool bicg_coop = true;
+    int bicg_grid = 148;
+    double* d_bicg_partials = nullptr;
+    int* d_info = nullptr;             // [0] iterations (accumulated), [1] sticky status, [2] last solve
+    int* h_info = nullptr;             // pinned copy
+    bool info_pending = false;
+    // matrix-in-shared-memory variant (bicgstab_smem_kernel): sliced-ELL chunks, one per SM
+    bool bicg_smem = false;
+    double* sm_vals = nullptr;
+    int *sm_cols = nullptr, *sm_chunk_slice = nullptr, *sm_slice_slot = nullptr, *sm_chunk_row = nullptr, *sm_rowmap = nullptr;
+    size_t sm_bytes = 0;               // dynamic shared memory per CTA
+    int sm_grid = 0;
 };
 
 static void free_state(KrylovState* k) {
@@ -48,7 +64,12 @@ static void free_state(KrylovState* k) {
                       k->d_dots, k->d_partials, k->d_H, k->d_small, k->d_u, k->d_fac, k->d_svals};
     for (double* b : bufs) cudaFree(b);
     cudaFree(k->d_counter);
+    cudaFree(k->d_bicg_partials);
+    cudaFree(k->d_info);
+    cudaFree(k->sm_vals); cudaFree(k->sm_cols); cudaFree(k->sm_chunk_slice); cudaFree(k->sm_slice_slot);
+    cudaFree(k->sm_chunk_row); cudaFree(k->sm_rowmap);
     if (k->h_dots) cudaFreeHost(k->h_dots);
+    if (k->h_info) cudaFreeHost(k->h_info);
     delete k;
 }
 
@@ -107,6 +128,39 @@ int shifted_solve(kexp_ctx* ctx, const double* vin, double* wout) {
         ctx->st_launches++;
     };
     spmv(ctx, k->Brhs, vin, k->b);                                   // b = M_u v_u - gamma K_ue v_eta
+    if (k->bicg_smem) {
+        BicgSmemArgs a;
+        a.vals = k->sm_vals; a.cols = k->sm_cols; a.chunk_slice = k->sm_chunk_slice; a.slice_slot = k->sm_slice_slot;
+        a.chunk_row = k->sm_chunk_row; a.rowmap = k->sm_rowmap; a.Pinv = k->d_Pinv; a.b = k->b;
+        a.x = k->x; a.y = k->y; a.z = k->z; a.max_it = k->max_it; a.rtol = k->rtol;
+        a.partials = k->d_bicg_partials; a.info = k->d_info;
+        void* args[] = {&a};
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)bicgstab_smem_kernel, dim3(k->sm_grid), dim3(kBicgSmemThreads), args, k->sm_bytes, ctx->stream);
+        if (e != cudaSuccess) return kexp::fail(ctx, std::string("cooperative BiCGStab (shared-memory matrix) launch: ") + cudaGetErrorString(e));
+        ctx->st_launches++;
+        KEXP_CUDA(cudaMemcpyAsync(k->h_info, k->d_info, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        k->info_pending = true;
+        KEXP_CUDA(cudaMemcpyAsync(wout, k->x, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+        spmv(ctx, k->Eback, k->x, k->tmp);
+        lincomb(ctx, wout + nu, 1.0, vin + nu, 1.0, k->tmp, 0.0, nullptr, n - nu);
+        return 0;
+    }
+    if (k->bicg_coop) {
+        BicgArgs a;
+        a.rowptr = k->Ash.rowptr; a.col = k->Ash.col; a.val = k->Ash.val; a.Pinv = k->d_Pinv; a.b = k->b;
+        a.x = k->x; a.r = k->r; a.r0 = k->r0; a.p = k->p; a.v = k->v; a.s = k->s; a.t = k->t; a.y = k->y; a.z = k->z;
+        a.nu = nu; a.max_it = k->max_it; a.rtol = k->rtol; a.partials = k->d_bicg_partials; a.info = k->d_info;
+        void* args[] = {&a};
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)bicgstab_coop_kernel, dim3(k->bicg_grid), dim3(kKryThreads), args, 0, ctx->stream);
+        if (e != cudaSuccess) return kexp::fail(ctx, std::string("cooperative BiCGStab launch: ") + cudaGetErrorString(e));
+        ctx->st_launches++;
+        KEXP_CUDA(cudaMemcpyAsync(k->h_info, k->d_info, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        k->info_pending = true;
+        KEXP_CUDA(cudaMemcpyAsync(wout, k->x, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
+        spmv(ctx, k->Eback, k->x, k->tmp);
+        lincomb(ctx, wout + nu, 1.0, vin + nu, 1.0, k->tmp, 0.0, nullptr, n - nu);
+        return 0;
+    }
     KEXP_CUDA(cudaMemsetAsync(k->x, 0, sizeof(double) * nu, ctx->stream));
     KEXP_CUDA(cudaMemcpyAsync(k->r, k->b, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
     KEXP_CUDA(cudaMemcpyAsync(k->r0, k->b, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -159,6 +213,114 @@ int shifted_solve(kexp_ctx* ctx, const double* vin, double* wout) {
     spmv(ctx, k->Eback, k->x, k->tmp);
     lincomb(ctx, wout + nu, 1.0, vin + nu, 1.0, k->tmp, 0.0, nullptr, n - nu);
     return 0;
+}
+
+// after a stream synchronisation: outcome of the cooperative solves enqueued since the last check
+int check_solves(kexp_ctx* ctx) {
+    KrylovState* k = ctx->kry;
+    if (!k->info_pending) return 0;
+    k->info_pending = false;
+    ctx->st_bicg += k->h_info[0];
+    const int status = k->h_info[1];
+    KEXP_CUDA(cudaMemsetAsync(k->d_info, 0, sizeof(int) * 4, ctx->stream));
+    if (status == 2) return kexp::fail(ctx, "BiCGStab breakdown in the shifted solve");
+    if (status == 1) return kexp::fail(ctx, "shifted solve did not converge (raise solve_max_it)");
+    return 0;
+}
+
+// Sliced-ELL chunks of the shifted operator for bicgstab_smem_kernel: block rows split into `G`
+// contiguous ranges of about equal block count; inside a range rows are sorted by block count and
+// cut into slices of 32.  Returns false (and leaves the state untouched) when a chunk does not fit.
+bool build_smem_chunks(kexp_ctx* ctx, KrylovState* k, const int32_t* rowptr, const int32_t* col, const double* val,
+                       int64_t nu, int G, size_t smem_limit) {
+    const int nbr = (int)(nu / 3);
+    // 3x3 block structure
+    std::vector<int> bptr(nbr + 1, 0);
+    std::vector<int> bcol;
+    std::vector<double> bval;
+    {
+        std::vector<int> seen(nbr, -1);
+        for (int br = 0; br < nbr; ++br) {
+            const size_t first = bcol.size();
+            for (int i = 0; i < 3; ++i)
+                for (int q = rowptr[3 * br + i]; q < rowptr[3 * br + i + 1]; ++q) {
+                    const int bc = col[q] / 3;
+                    if (seen[bc] < (int)first) {                  // not yet in this block row
+                        seen[bc] = (int)bcol.size();
+                        bcol.push_back(bc);
+                        bval.insert(bval.end(), 9, 0.0);
+                    }
+                    bval[(size_t)seen[bc] * 9 + 3 * i + (col[q] % 3)] += val[q];
+                }
+            bptr[br + 1] = (int)bcol.size();
+        }
+    }
+    const int64_t nblocks = bptr[nbr];
+    std::vector<int> chunk_row(G + 1, 0), chunk_slice(G + 1, 0), slice_slot(1, 0), rowmap(nbr);
+    {
+        int br = 0;
+        for (int c = 0; c < G; ++c) {
+            const int64_t target = nblocks * (c + 1) / G;
+            chunk_row[c] = br;
+            while (br < nbr && bptr[br + 1] <= target) ++br;
+            if (c == G - 1) br = nbr;
+        }
+        chunk_row[G] = nbr;
+    }
+    std::vector<double> vals;
+    std::vector<int> cols;
+    size_t worst = 0;
+    for (int c = 0; c < G; ++c) {
+        const int r0 = chunk_row[c], r1 = chunk_row[c + 1];
+        if (r1 - r0 > kBicgSmemThreads) return false;
+        std::vector<int> order(r1 - r0);
+        for (int i = 0; i < r1 - r0; ++i) order[i] = r0 + i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bptr[a + 1] - bptr[a] > bptr[b + 1] - bptr[b]; });
+        for (int i = 0; i < r1 - r0; ++i) rowmap[r0 + i] = order[i];
+        chunk_slice[c] = (int)slice_slot.size() - 1;
+        const int slot_first = slice_slot.back();
+        for (int s0 = 0; s0 < r1 - r0; s0 += 32) {
+            const int lanes = std::min(32, r1 - r0 - s0);
+            int width = 0;
+            for (int l = 0; l < lanes; ++l) width = std::max(width, bptr[order[s0 + l] + 1] - bptr[order[s0 + l]]);
+            const size_t slot0 = (size_t)slice_slot.back();
+            vals.resize((slot0 + width) * 9 * 32, 0.0);
+            cols.resize((slot0 + width) * 32, 0);
+            for (int l = 0; l < 32; ++l) {
+                const int br = (l < lanes) ? order[s0 + l] : order[s0];
+                const int cnt = (l < lanes) ? bptr[br + 1] - bptr[br] : 0;
+                for (int q = 0; q < width; ++q) {
+                    cols[(slot0 + q) * 32 + l] = (q < cnt) ? bcol[bptr[br] + q] : br;      // padding: own column, zero values
+                    if (q < cnt)
+                        for (int e = 0; e < 9; ++e) vals[((slot0 + q) * 9 + e) * 32 + l] = bval[(size_t)(bptr[br] + q) * 9 + e];
+                }
+            }
+            slice_slot.push_back((int)(slot0 + width));
+        }
+        const size_t nslots = (size_t)(slice_slot.back() - slot_first);
+        worst = std::max(worst, nslots * (9 * 32 * sizeof(double) + 32 * sizeof(int)));
+    }
+    chunk_slice[G] = (int)slice_slot.size() - 1;
+    const size_t bytes = worst + (size_t)9 * kBicgSmemThreads * sizeof(double);
+    if (bytes > smem_limit) return false;
+    auto up = [&](auto** dst, const auto& v) -> bool {
+        using T = std::remove_reference_t<decltype(**dst)>;
+        if (cudaMalloc(dst, sizeof(T) * std::max<size_t>(v.size(), 1)) != cudaSuccess) return true;
+        return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess;
+    };
+    if (up(&k->sm_vals, vals) || up(&k->sm_cols, cols) || up(&k->sm_chunk_slice, chunk_slice) || up(&k->sm_slice_slot, slice_slot) ||
+        up(&k->sm_chunk_row, chunk_row) || up(&k->sm_rowmap, rowmap)) return false;
+    if (cudaFuncSetAttribute(bicgstab_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bicgstab_smem_kernel, kBicgSmemThreads, bytes);
+    if (occ < 1) return false;
+    k->sm_bytes = bytes;
+    k->sm_grid = G;
+    (void)ctx;
+    return true;
 }
 
 int alloc_d(kexp_ctx* ctx, double** p, size_t count) {
@@ -231,6 +393,31 @@ int kexp_set_krylov_operator(kexp_ctx* ctx, double gamma,
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mgs_sweep_kernel, kKryThreads, 0);
     k->coop_grid = std::max(1, occ) * ctx->num_sms;
+    {
+        const char* e = getenv("KEXP_BICG_HOST");
+        k->bicg_coop = !(e && atoi(e) != 0);
+        int per_sm = 4;
+        if ((e = getenv("KEXP_BICG_BLOCKS")) && atoi(e) > 0) per_sm = atoi(e);
+        occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bicgstab_coop_kernel, kKryThreads, 0);
+        k->bicg_grid = std::max(1, std::min(per_sm, occ)) * ctx->num_sms;
+        if (alloc_d(ctx, &k->d_bicg_partials, (size_t)k->bicg_grid * 16) ||
+            cudaMalloc(&k->d_info, sizeof(int) * 4) != cudaSuccess || cudaMemset(k->d_info, 0, sizeof(int) * 4) != cudaSuccess ||
+            cudaMallocHost(&k->h_info, sizeof(int) * 4) != cudaSuccess) { krylov_free(ctx); return kexp::fail(ctx, "out of memory in kexp_set_krylov_operator"); }
+        k->h_info[0] = k->h_info[1] = k->h_info[2] = k->h_info[3] = 0;
+        // matrix resident in shared memory when it fits (ref <= 5); KEXP_BICG_SMEM=0 keeps it in L2
+        e = getenv("KEXP_BICG_SMEM");
+        if (k->bicg_coop && !(e && atoi(e) == 0)) {
+            int optin = 0;
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+            const size_t limit = (size_t)std::max(0, optin - 1024);             // static shared memory of the kernel
+            k->bicg_smem = build_smem_chunks(ctx, k, Ash_rowptr, Ash_col, Ash_val, nu, ctx->num_sms, limit);
+            if (k->bicg_smem && k->sm_grid > k->bicg_grid) {                     // partials sized for bicg_grid CTAs
+                cudaFree(k->d_bicg_partials); k->d_bicg_partials = nullptr;
+                if (alloc_d(ctx, &k->d_bicg_partials, (size_t)k->sm_grid * 16)) { krylov_free(ctx); return 1; }
+            }
+        }
+    }
     return 0;
 }
 
@@ -315,6 +502,7 @@ int kexp_krylov_apply(kexp_ctx* ctx, const double* x, double* y, double t, int k
         spmv(ctx, k->M, k->w, k->mw);
         double wmw = 0.0;
         if (dot1(ctx, k->w, k->mw, n, &wmw)) { rc = 1; break; }
+        if (check_solves(ctx)) { rc = 1; break; }
         const double hn = sqrt(std::max(wmw, 0.0));                  // H[j+1,j] = ||w||_M  (krylov_exp.py:78)
         if (cudaMemcpyAsync(k->d_H + (size_t)(j + 1) * ldh + j, &hn, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = 1; break; }
         if (!(hn > 0.0)) { rc = kexp::fail(ctx, "Arnoldi breakdown (invariant subspace reached)"); break; }

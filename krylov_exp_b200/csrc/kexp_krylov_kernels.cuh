@@ -138,11 +138,15 @@ mgs_sweep_kernel(double* __restrict__ w, const double* __restrict__ V, const dou
             partials[(size_t)(it & 1) * gridDim.x + blockIdx.x] = t;
         }
         grid.sync();
-        if (threadIdx.x == 0) {
+        if (warp == 0) {                                   // lanes stride over the blocks, fixed xor tree
             double t = 0.0;
-            for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(partials + (size_t)(it & 1) * gridDim.x + b);
-            s_h = t;
-            if (blockIdx.x == 0) Hcol[it] = t;
+            for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(partials + (size_t)(it & 1) * gridDim.x + b);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0) {
+                s_h = t;
+                if (blockIdx.x == 0) Hcol[it] = t;
+            }
         }
         __syncthreads();
         const double h = s_h;
@@ -157,6 +161,445 @@ mgs_sweep_kernel(double* __restrict__ w, const double* __restrict__ V, const dou
     for (int e = 0; e < kMgsPerThread; ++e) {
         const int i = base + e * kKryThreads + threadIdx.x;
         if (i < n) w[i] = wv[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// The whole shifted solve  (M_u + gamma K_uu + gamma^2 G M_eta^-1 D) x = b  as ONE cooperative
+// kernel: right-preconditioned (3x3 block-Jacobi) BiCGStab, four grid-wide barriers per
+// iteration, every scalar (rho, alpha, omega, the norms) reduced in a fixed order by every block
+// from per-block partial sums, so no host round trip and a deterministic result for a fixed
+// grid.  The matrix (CSR, 8 lanes per row) and the ten work vectors stay in L2.
+//   stage 1   p = r + beta (p - omega v);  y = P^-1 p                      (own 3-blocks)
+//   stage 2   v = A y;  r0.v                         -> alpha
+//   stage 3   s = r - alpha v;  z = P^-1 s;  s.s, r0.s                     (own 3-blocks)
+//   stage 4   t = A z;  t.s, t.t, r0.t               -> omega, rho' = r0.s - omega r0.t
+//   stage 5   x += alpha y + omega z;  r = s - omega t   (fused with stage 1 of the next iteration)
+// ------------------------------------------------------------------------------------
+struct BicgArgs {
+    const int* rowptr; const int* col; const double* val;   // A (n_u x n_u CSR)
+    const double* Pinv;                                     // 9 doubles per 3x3 block
+    const double* b;
+    double *x, *r, *r0, *p, *v, *s, *t, *y, *z;
+    int nu, max_it;
+    double rtol;
+    double* partials;                                       // 4 slots x gridDim.x x 4
+    int* info;                                              // [0] += iterations, [1] sticky status, [2] iterations of this solve
+};
+
+template <int NV>
+__device__ inline void bicg_grid_sums(cg::grid_group& grid, double (&v)[NV], double* slot, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = v[k];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) sh[k * 8 + warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kKryThreads / 32; ++w) s += sh[threadIdx.x * 8 + w];
+        __stcg(slot + (size_t)blockIdx.x * 4 + threadIdx.x, s);
+    }
+    grid.sync();
+    if (warp < NV) {
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(slot + (size_t)b * 4 + warp);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) sh[32 + warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = sh[32 + k];
+    __syncthreads();
+}
+
+// out = A in (8 lanes per row), and up to three dots of the new row values with d0/d1 (and with themselves)
+template <int MODE>   // 0: acc[0] += d0[row]*out[row];  1: acc[0] += out*d1[row], acc[1] += out*out, acc[2] += d0[row]*out
+__device__ inline void bicg_spmv(const BicgArgs& a, const double* in, double* out, const double* d0, const double* d1, double (&acc)[3]) {
+    // kBicgRows rows in flight per 8-lane group and three predicated passes per row (rows of the
+    // shifted operator hold 12 or 21 entries), so the rowptr -> col/val -> gather chains of several
+    // rows overlap; longer rows finish in a tail loop.
+    constexpr int kBicgRows = 4;
+    const int sub = threadIdx.x & 7;
+    const int grp = (blockIdx.x * kKryThreads + threadIdx.x) >> 3, ngrp = (gridDim.x * kKryThreads) >> 3;
+    for (int r0 = grp; r0 < a.nu; r0 += kBicgRows * ngrp) {
+        int k0[kBicgRows], k1[kBicgRows];
+#pragma unroll
+        for (int u = 0; u < kBicgRows; ++u) {
+            const int r = r0 + u * ngrp;
+            k0[u] = (r < a.nu) ? __ldg(a.rowptr + r) : 0;
+            k1[u] = (r < a.nu) ? __ldg(a.rowptr + r + 1) : 0;
+        }
+        int cc[kBicgRows][3];
+        double vv[kBicgRows][3];
+#pragma unroll
+        for (int u = 0; u < kBicgRows; ++u)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int k = k0[u] + sub + 8 * q;
+                const bool ok = k < k1[u];
+                cc[u][q] = ok ? __ldg(a.col + k) : -1;
+                vv[u][q] = ok ? __ldg(a.val + k) : 0.0;
+            }
+        double s[kBicgRows];
+#pragma unroll
+        for (int u = 0; u < kBicgRows; ++u) {
+            double xg[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) xg[q] = (cc[u][q] >= 0) ? __ldcg(in + cc[u][q]) : 0.0;
+            s[u] = fma(vv[u][2], xg[2], fma(vv[u][1], xg[1], vv[u][0] * xg[0]));
+        }
+#pragma unroll
+        for (int u = 0; u < kBicgRows; ++u) {
+            for (int k = k0[u] + sub + 24; k < k1[u]; k += 8) s[u] = fma(__ldg(a.val + k), __ldcg(in + __ldg(a.col + k)), s[u]);
+            s[u] += __shfl_xor_sync(0xffffffffu, s[u], 4);
+            s[u] += __shfl_xor_sync(0xffffffffu, s[u], 2);
+            s[u] += __shfl_xor_sync(0xffffffffu, s[u], 1);
+            const int r = r0 + u * ngrp;
+            if (sub == 0 && r < a.nu) {
+                __stcg(out + r, s[u]);
+                if (MODE == 0) acc[0] = fma(__ldcg(d0 + r), s[u], acc[0]);
+                else { acc[0] = fma(s[u], __ldcg(d1 + r), acc[0]); acc[1] = fma(s[u], s[u], acc[1]); acc[2] = fma(__ldcg(d0 + r), s[u], acc[2]); }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kKryThreads)
+bicgstab_coop_kernel(BicgArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[48];
+    const int nblk = a.nu / 3;
+    const int gt = blockIdx.x * kKryThreads + threadIdx.x, gs = gridDim.x * kKryThreads;
+    double* slot0 = a.partials;
+    double* slot1 = a.partials + (size_t)gridDim.x * 4;
+    double* slot2 = a.partials + (size_t)gridDim.x * 8;
+    double* slot3 = a.partials + (size_t)gridDim.x * 12;
+
+    double red1[1] = {0.0};
+    for (int i = gt; i < a.nu; i += gs) {
+        const double bi = __ldcg(a.b + i);
+        a.x[i] = 0.0; a.r[i] = bi; a.r0[i] = bi; a.p[i] = 0.0; a.v[i] = 0.0;
+        red1[0] = fma(bi, bi, red1[0]);
+    }
+    bicg_grid_sums<1>(grid, red1, slot3, sh);
+    const double bb = red1[0];
+    int status = 0, it = 0;
+    if (bb > 0.0) {
+        const double tol2 = a.rtol * a.rtol * bb;
+        double rho = 1.0, alpha = 1.0, omega = 1.0, rho_new = bb;
+        bool have_update = false;                 // stage 5 of the previous iteration still to be applied
+        status = 1;
+        for (; it < a.max_it; ++it) {
+            if (rho_new == 0.0 || omega == 0.0) { status = 2; break; }
+            const double beta = (rho_new / rho) * (alpha / omega);
+            // stage 5 (previous iteration) + stage 1
+            for (int blk = gt; blk < nblk; blk += gs) {
+                double rr[3], pp[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int i = 3 * blk + c;
+                    if (have_update) {
+                        const double sv = __ldcg(a.s + i);
+                        a.x[i] = fma(omega, __ldcg(a.z + i), fma(alpha, __ldcg(a.y + i), __ldcg(a.x + i)));
+                        rr[c] = fma(-omega, __ldcg(a.t + i), sv);
+                        a.r[i] = rr[c];
+                    } else rr[c] = __ldcg(a.r + i);
+                    pp[c] = fma(beta, fma(-omega, __ldcg(a.v + i), __ldcg(a.p + i)), rr[c]);
+                    a.p[i] = pp[c];
+                }
+                const double* B = a.Pinv + (size_t)9 * blk;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    __stcg(a.y + 3 * blk + c, fma(__ldg(B + 3 * c), pp[0], fma(__ldg(B + 3 * c + 1), pp[1], __ldg(B + 3 * c + 2) * pp[2])));
+            }
+            have_update = false;
+            grid.sync();
+            // stage 2
+            double acc[3] = {0.0, 0.0, 0.0};
+            bicg_spmv<0>(a, a.y, a.v, a.r0, nullptr, acc);
+            double red_a[1] = {acc[0]};
+            bicg_grid_sums<1>(grid, red_a, slot0, sh);
+            if (red_a[0] == 0.0) { status = 2; break; }
+            alpha = rho_new / red_a[0];
+            // stage 3
+            double red_s[2] = {0.0, 0.0};
+            for (int blk = gt; blk < nblk; blk += gs) {
+                double ss[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int i = 3 * blk + c;
+                    ss[c] = fma(-alpha, __ldcg(a.v + i), __ldcg(a.r + i));
+                    __stcg(a.s + i, ss[c]);
+                    red_s[0] = fma(ss[c], ss[c], red_s[0]);
+                    red_s[1] = fma(__ldcg(a.r0 + i), ss[c], red_s[1]);
+                }
+                const double* B = a.Pinv + (size_t)9 * blk;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    __stcg(a.z + 3 * blk + c, fma(__ldg(B + 3 * c), ss[0], fma(__ldg(B + 3 * c + 1), ss[1], __ldg(B + 3 * c + 2) * ss[2])));
+            }
+            bicg_grid_sums<2>(grid, red_s, slot1, sh);
+            if (red_s[0] <= tol2) {                // s already small enough: x += alpha y
+                for (int i = gt; i < a.nu; i += gs) a.x[i] = fma(alpha, __ldcg(a.y + i), __ldcg(a.x + i));
+                status = 0; ++it; break;
+            }
+            // stage 4
+            acc[0] = acc[1] = acc[2] = 0.0;
+            bicg_spmv<1>(a, a.z, a.t, a.r0, a.s, acc);
+            bicg_grid_sums<3>(grid, acc, slot2, sh);
+            omega = (acc[1] > 0.0) ? acc[0] / acc[1] : 0.0;
+            rho = rho_new;
+            rho_new = fma(-omega, acc[2], red_s[1]);                         // r0.r = r0.s - omega r0.t
+            have_update = true;
+            const double rr = fma(omega, fma(omega, acc[1], -2.0 * acc[0]), red_s[0]);   // |s - omega t|^2
+            if (rr <= tol2) { status = 0; ++it; break; }
+        }
+        if (have_update)                           // apply the pending x update of the last iteration
+            for (int i = gt; i < a.nu; i += gs) a.x[i] = fma(omega, __ldcg(a.z + i), fma(alpha, __ldcg(a.y + i), __ldcg(a.x + i)));
+    }
+    if (gt == 0) {
+        a.info[0] += it;
+        a.info[2] = it;
+        if (status) a.info[1] = status;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// The same solve with the MATRIX RESIDENT IN SHARED MEMORY for its whole duration (ref <= 5:
+// 24 MB of 3x3 blocks over 148 x 227 KB).  One persistent CTA per SM owns a contiguous range of
+// block rows, one thread per block row; its slices of x, r, r0, p, v, s, t, y, z never leave
+// registers.  Per iteration only y and z are published (the neighbours gather them), plus one
+// partial sum per CTA and reduction.  Layout per CTA ("sliced ELL", built on the host): rows sorted
+// by block count, slices of 32 rows padded to the slice width, values [slot][9][lane], columns
+// [slot][lane]; padding slots carry zero values and the row's own column.
+// ------------------------------------------------------------------------------------
+constexpr int kBicgSmemThreads = 512;
+
+struct BicgSmemArgs {
+    const double* vals;        // all chunks, doubles
+    const int* cols;           // all chunks
+    const int* chunk_slice;    // [G+1] first slice of chunk c
+    const int* slice_slot;     // [nslices+1] first 32-lane slot of slice s
+    const int* chunk_row;      // [G+1] first local row of chunk c (index into rowmap)
+    const int* rowmap;         // local row -> global block row
+    const double* Pinv;        // 9 doubles per global block row
+    const double* b;
+    double* x;                 // out (n_u)
+    double *y, *z;             // published SpMV inputs (n_u)
+    int max_it;
+    double rtol;
+    double* partials;          // 4 slots x gridDim.x x 4
+    int* info;
+};
+
+template <int NV>
+__device__ inline void bicg_smem_sums(cg::grid_group& grid, double (&v)[NV], double* slot, double* sh) {
+    constexpr int NW = kBicgSmemThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = v[k];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) sh[k * NW + warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += sh[threadIdx.x * NW + w];
+        __stcg(slot + (size_t)blockIdx.x * 4 + threadIdx.x, s);
+    }
+    grid.sync();
+    __threadfence();
+    if (warp < NV) {
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(slot + (size_t)b * 4 + warp);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) sh[4 * NW + warp] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = sh[4 * NW + k];
+    __syncthreads();
+}
+
+// o = (A in)(own block row): values and columns from shared memory, `in` gathered from global
+__device__ inline void bicg_smem_row(const double* sv, const int* sc, int slot0, int width, int lane,
+                                     const double* in, double (&o)[3]) {
+    o[0] = o[1] = o[2] = 0.0;
+    int q = 0;
+    for (; q + 4 <= width; q += 4) {
+        int c[4];
+        double xg[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = sc[(slot0 + q + u) * 32 + lane];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            xg[u][0] = in[3 * c[u]]; xg[u][1] = in[3 * c[u] + 1]; xg[u][2] = in[3 * c[u] + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double* m = sv + (size_t)(slot0 + q + u) * 9 * 32 + lane;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                o[i] = fma(m[(3 * i) * 32], xg[u][0], fma(m[(3 * i + 1) * 32], xg[u][1], fma(m[(3 * i + 2) * 32], xg[u][2], o[i])));
+        }
+    }
+    for (; q < width; ++q) {
+        const int c = sc[(slot0 + q) * 32 + lane];
+        const double x0 = in[3 * c], x1 = in[3 * c + 1], x2 = in[3 * c + 2];
+        const double* m = sv + (size_t)(slot0 + q) * 9 * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            o[i] = fma(m[(3 * i) * 32], x0, fma(m[(3 * i + 1) * 32], x1, fma(m[(3 * i + 2) * 32], x2, o[i])));
+    }
+}
+
+__global__ void __launch_bounds__(kBicgSmemThreads, 1)
+bicgstab_smem_kernel(BicgSmemArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double smem_dyn[];
+    __shared__ double sh[5 * (kBicgSmemThreads / 32)];
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x;
+    const int s_first = a.chunk_slice[c], s_last = a.chunk_slice[c + 1];
+    const int slot_base = a.slice_slot[s_first];
+    const int nslots = a.slice_slot[s_last] - slot_base;
+    const int row_first = a.chunk_row[c];
+    const int rows = a.chunk_row[c + 1] - row_first;
+    // shared layout: values [nslots][9][32] | Pinv [9][T] | columns [nslots][32]
+    double* sv = smem_dyn;
+    double* sP = sv + (size_t)nslots * 9 * 32;
+    int* sc = reinterpret_cast<int*>(sP + 9 * kBicgSmemThreads);
+    {
+        const double* gv = a.vals + (size_t)slot_base * 9 * 32;
+        for (int i = threadIdx.x; i < nslots * 9 * 32; i += kBicgSmemThreads) sv[i] = __ldg(gv + i);
+        const int* gc = a.cols + (size_t)slot_base * 32;
+        for (int i = threadIdx.x; i < nslots * 32; i += kBicgSmemThreads) sc[i] = __ldg(gc + i);
+    }
+    const bool active = (int)threadIdx.x < rows;
+    const int g = active ? __ldg(a.rowmap + row_first + threadIdx.x) : 0;        // global block row
+    {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) sP[e * kBicgSmemThreads + threadIdx.x] = active ? __ldg(a.Pinv + (size_t)9 * g + e) : 0.0;
+    }
+    int my_slot = 0, width = 0;
+    if (active) {
+        const int sl = s_first + (threadIdx.x >> 5);
+        my_slot = __ldg(a.slice_slot + sl) - slot_base;
+        width = __ldg(a.slice_slot + sl + 1) - __ldg(a.slice_slot + sl);
+    }
+    __syncthreads();
+    const double* P = sP + threadIdx.x;
+    auto precond = [&](const double (&in)[3], double (&out)[3]) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            out[i] = fma(P[(3 * i) * kBicgSmemThreads], in[0], fma(P[(3 * i + 1) * kBicgSmemThreads], in[1], P[(3 * i + 2) * kBicgSmemThreads] * in[2]));
+    };
+    double* slot0 = a.partials;
+    double* slot1 = a.partials + (size_t)gridDim.x * 4;
+    double* slot2 = a.partials + (size_t)gridDim.x * 8;
+    double* slot3 = a.partials + (size_t)gridDim.x * 12;
+
+    double x[3] = {0, 0, 0}, r[3] = {0, 0, 0}, r0[3] = {0, 0, 0}, p[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+    double s[3] = {0, 0, 0}, t[3] = {0, 0, 0}, y[3] = {0, 0, 0}, z[3] = {0, 0, 0};
+    double red1[1] = {0.0};
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { r[i] = r0[i] = __ldcg(a.b + 3 * g + i); red1[0] = fma(r[i], r[i], red1[0]); }
+    }
+    bicg_smem_sums<1>(grid, red1, slot3, sh);
+    const double bb = red1[0];
+    int status = 0, it = 0;
+    if (bb > 0.0) {
+        const double tol2 = a.rtol * a.rtol * bb;
+        double rho = 1.0, alpha = 1.0, omega = 1.0, rho_new = bb;
+        bool have_update = false;
+        status = 1;
+        for (; it < a.max_it; ++it) {
+            if (rho_new == 0.0 || omega == 0.0) { status = 2; break; }
+            const double beta = (rho_new / rho) * (alpha / omega);
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (have_update) {
+                        x[i] = fma(omega, z[i], fma(alpha, y[i], x[i]));
+                        r[i] = fma(-omega, t[i], s[i]);
+                    }
+                    p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+                }
+                precond(p, y);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) __stcg(a.y + 3 * g + i, y[i]);
+            }
+            have_update = false;
+            grid.sync();
+            __threadfence();
+            double red_a[1] = {0.0};
+            if (active) {
+                bicg_smem_row(sv, sc, my_slot, width, lane, a.y, v);
+                red_a[0] = fma(r0[0], v[0], fma(r0[1], v[1], r0[2] * v[2]));
+            }
+            bicg_smem_sums<1>(grid, red_a, slot0, sh);
+            if (red_a[0] == 0.0) { status = 2; break; }
+            alpha = rho_new / red_a[0];
+            double red_s[2] = {0.0, 0.0};
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    s[i] = fma(-alpha, v[i], r[i]);
+                    red_s[0] = fma(s[i], s[i], red_s[0]);
+                    red_s[1] = fma(r0[i], s[i], red_s[1]);
+                }
+                precond(s, z);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) __stcg(a.z + 3 * g + i, z[i]);
+            }
+            bicg_smem_sums<2>(grid, red_s, slot1, sh);
+            if (red_s[0] <= tol2) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) x[i] = fma(alpha, y[i], x[i]);
+                status = 0; ++it; break;
+            }
+            double acc[3] = {0.0, 0.0, 0.0};
+            if (active) {
+                bicg_smem_row(sv, sc, my_slot, width, lane, a.z, t);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    acc[0] = fma(t[i], s[i], acc[0]);
+                    acc[1] = fma(t[i], t[i], acc[1]);
+                    acc[2] = fma(r0[i], t[i], acc[2]);
+                }
+            }
+            bicg_smem_sums<3>(grid, acc, slot2, sh);
+            omega = (acc[1] > 0.0) ? acc[0] / acc[1] : 0.0;
+            rho = rho_new;
+            rho_new = fma(-omega, acc[2], red_s[1]);
+            have_update = true;
+            const double rr = fma(omega, fma(omega, acc[1], -2.0 * acc[0]), red_s[0]);
+            if (rr <= tol2) { status = 0; ++it; break; }
+        }
+        if (have_update) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) x[i] = fma(omega, z[i], fma(alpha, y[i], x[i]));
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a.x[3 * g + i] = x[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.info[0] += it;
+        a.info[2] = it;
+        if (status) a.info[1] = status;
     }
 }
 

@@ -15,6 +15,7 @@ M = sw.M()
 rel = lambda a, b: float(np.sqrt(((a - b) @ (M @ (a - b))) / (b @ (M @ b))))
 ce = kx.cheby_exp(op, None, None, 10000, 1e-8, kx.EIGS[2] * t)
 yc = np.empty(sw.n)
+ce.apply(x, yc, -t)                                                     # warm-up
 t0 = time.perf_counter(); ce.apply(x, yc, -t); tc = time.perf_counter() - t0
 print(f"cheby_exp: ncheb {ce.ncheb}, {tc * 1e3:.1f} ms")
 nu = sw.n_u
@@ -22,6 +23,7 @@ E = lambda z: sw.H * (z[:nu] @ (sw.Mu @ z[:nu])) + sw.g * (z[nu:] @ (sw.Meta() @
 for kdim in (40, 50):
     ke = kx.krylov_exp(sh, None, None, gamma, kdim, op, None, None)
     y = np.empty(sw.n)
+    ke.apply(x, y, t, residuals=False)                                  # warm-up (allocations, first launches)
     op.stats_reset()
     t0 = time.perf_counter(); ke.apply(x, y, t, residuals=False); tk = time.perf_counter() - t0
     st = op.stats()

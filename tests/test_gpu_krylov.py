@@ -122,3 +122,34 @@ def test_krylov_ref4_kdim40_matches_oracle():
     assert np.abs(ke.H - Ho).max() <= 1e-6 * np.abs(Ho).max()
     assert _relM(M, y, yo) < 1e-5
     op.close()
+
+
+def test_one_kernel_bicgstab_matches_host_driven_loop(sw3, monkeypatch):
+    """The cooperative one-kernel BiCGStab -- matrix resident in shared memory (default) or read from L2
+    (KEXP_BICG_SMEM=0) -- and the host-driven loop (KEXP_BICG_HOST=1) solve the same shifted systems to the
+    same tolerance: H and y agree far below the Arnoldi sensitivity."""
+    import krylov_exp_b200 as kx
+    from oracle.assemble_sw import test_pulse
+    sw = sw3
+    t, kdim = 3600.0, 12
+    gamma = t / 10.0
+    x = test_pulse(sw)
+    out = {}
+    for mode, env in (("smem", {}), ("l2", {"KEXP_BICG_SMEM": "0"}), ("host", {"KEXP_BICG_HOST": "1"})):
+        for key in ("KEXP_BICG_SMEM", "KEXP_BICG_HOST"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13, max_it=80)
+        sh = kx.ShiftedOperator(op, sw.K, sw.Mu, sw.Meta_blocks, gamma, rtol=1e-13)
+        ke = kx.krylov_exp(sh, None, None, gamma, kdim, op, None, None)
+        y = np.empty(sw.n)
+        op.stats_reset()
+        ke.apply(x, y, t, residuals=False)
+        out[mode] = (y, ke.H.copy(), op.stats()["bicg_iterations"])
+        op.close()
+    M = sw.M()
+    for mode in ("smem", "l2"):
+        assert _relM(M, out[mode][0], out["host"][0]) < 1e-9, mode
+        assert np.abs(out[mode][1] - out["host"][1]).max() <= 1e-9 * np.abs(out["host"][1]).max(), mode
+        assert out[mode][2] > 0 and abs(out[mode][2] - out["host"][2]) <= 0.2 * out["host"][2], mode
