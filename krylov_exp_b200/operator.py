@@ -263,6 +263,29 @@ class Operator:
         bi.close(); bo.close()
         return Y
 
+    def largest_imag_eig(self, tol=1e-10, ncv=None, v0=None):
+        """Largest |imag| eigenvalue of M^-1 K -- the `eigs` table of averaged_sw_explicit.py:77-82, which the
+        reference hard-codes per refinement level and computes offline with SLEPc (L_eigs.py:36-58,
+        eps_largest_imaginary).  M^-1 K is skew-adjoint in the energy inner product, so (M^-1 K)^2 has the real
+        spectrum -omega^2; ARPACK (host) drives the device operator for the products.  Needed for levels the
+        table lacks (ref >= 6, averaged_sw_williamson6.py:112-117)."""
+        from scipy.sparse.linalg import LinearOperator, eigs
+        bi, bo = self.batch(1), self.batch(1)
+        try:
+            def A2(v):
+                for _ in range(2):
+                    bi.upload(np.ascontiguousarray(v, dtype=np.float64).reshape(1, -1))
+                    self._check(self.lib.kexp_operator_apply_dev(self.ctx, bi.handle, bo.handle), "kexp_operator_apply_dev")
+                    v = bo.download()[0]
+                return v
+            if v0 is None:
+                v0 = np.random.default_rng(0).standard_normal(self.n)
+            vals = eigs(LinearOperator((self.n, self.n), matvec=A2, dtype=np.float64), k=1, which="LM", tol=tol,
+                        ncv=ncv, v0=v0, return_eigenvectors=False)
+        finally:
+            bi.close(); bo.close()
+        return float(np.sqrt(np.max(-vals.real)))
+
     def spmm_K(self, X):
         X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
         bi, bo = self.batch(X.shape[0]), self.batch(X.shape[0])

@@ -86,3 +86,17 @@ def test_M5_degree1_mesh_H8000():
     ref = cheby_ref.apply_batch(coeffs.real_recurrence_coeffs(c, n), L, lambda V: lu.solve(sw.K @ V), X.T, t).T
     assert max(_relM(sw.M(), Y[k], ref[k]) for k in range(7)) < 1e-10
     op.close()
+
+
+def test_spectral_bound_from_the_device_operator():
+    """N4: the `eigs` table (averaged_sw_explicit.py:77-82) recomputed with ARPACK driving the device operator:
+    equals the host eigen-solve of the same pencil and sits within the assembler's 1e-3 of eigs.dat:2."""
+    import krylov_exp_b200 as kx
+    from oracle.assemble_sw import largest_imag_eig
+    sw = get_sw(3)
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13, max_it=80)
+    lam = op.largest_imag_eig()
+    op.close()
+    assert abs(lam / largest_imag_eig(sw) - 1) < 1e-8
+    assert abs(lam / 0.0034641819861161867 - 1) < 1e-3
+    assert lam <= kx.EIGS[0] * 1.0005
