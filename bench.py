@@ -49,6 +49,7 @@ def workload(ref_level, samples, seed=1234):
     L = eig * DT * RHO
     t, w = sample_times_weights(samples, DT, RHO)
     x = test_pulse(sw)
+    workload.eig = eig                     # the bound L is built from (averaged_sw_explicit.py:77-82,168)
     return sw, L, t, w, x
 
 
@@ -151,6 +152,8 @@ def main():
     ap.add_argument("--solver", default="chebyshev", choices=["chebyshev", "cg"],
                     help="mass solve: Chebyshev semi-iteration (one fused kernel per iteration) or batched PCG")
     ap.add_argument("--no-condense", action="store_true")
+    ap.add_argument("--full-series", action="store_true",
+                    help="every column runs all ncheb terms (no per-column economised re-expansion)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -202,7 +205,7 @@ def main():
 
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, device=local_rank, condense=not args.no_condense,
                      rtol=args.cg_rtol, max_it=args.max_it, solver=args.solver)
-    ce = kx.cheby_exp(op, None, None, NCHEB0, TOL, L)
+    ce = kx.cheby_exp(op, None, None, NCHEB0, TOL, L, spectral_radius=None if args.full_series else workload.eig)
     n = op.n
 
     # pinned host buffers (e2e) and device-resident batches (value)
@@ -213,6 +216,7 @@ def main():
     noisy_inputs(sw, x, B, hX, seed=1234 + rank * B)
     b_fwd_in, b_fwd_out, b_bwd_in, b_bwd_out = op.batch(B), op.batch(B), op.batch(B), op.batch(B)
     b_fwd_in.upload(hx, shared=True)
+    b_bwd_in.set_order(np.argsort(np.abs(t), kind="stable"))     # panels of similar |t_k|: similar series length
     b_bwd_in.upload(hX)
     v = torch.zeros(n, dtype=torch.float64, device=f"cuda:{local_rank}")
 
@@ -259,18 +263,22 @@ def main():
     ms_per_step = ms_total / args.steps
     value = apps_per_step / (ms_per_step * 1e-3)
     cg_its_per_solve = st["cg_iterations"] / max(st["cg_solves"], 1)
+    # operator applications per step: (terms of the forward basis run) + sum over backward panels of their terms
+    terms_per_panel = st["op_applications"] / args.steps
 
     # ------------------------------------------------------------ the same step with the forward batch
     # treated as 64 independent columns (no shared-basis shortcut), for transparency
-    value_indep = None
-    if rank == 0 and not args.no_roofline:
-        os.environ["KEXP_SHARED_BASIS"] = "0"
+    def plain_variant(shared_basis, economise):
+        """The same step with one of the exact rewritings switched off (a second context)."""
+        if not shared_basis:
+            os.environ["KEXP_SHARED_BASIS"] = "0"
         op2 = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, device=local_rank, condense=not args.no_condense,
                           rtol=args.cg_rtol, max_it=args.max_it, solver=args.solver, spectrum=op.spectrum)
-        del os.environ["KEXP_SHARED_BASIS"]
-        ce2 = kx.cheby_exp(op2, None, None, NCHEB0, TOL, L)
+        os.environ.pop("KEXP_SHARED_BASIS", None)
+        ce2 = kx.cheby_exp(op2, None, None, NCHEB0, TOL, L, spectral_radius=workload.eig if economise else None)
         f_in, f_out, g_in, g_out = op2.batch(B), op2.batch(B), op2.batch(B), op2.batch(B)
         f_in.upload(hx, shared=True)
+        g_in.set_order(np.argsort(np.abs(t), kind="stable"))
         g_in.upload(hX)
         for _ in range(3):
             ce2.apply_dev(f_in, f_out, t); ce2.apply_dev(g_in, g_out, -t)
@@ -280,10 +288,15 @@ def main():
             ce2.apply_dev(f_in, f_out, t); ce2.apply_dev(g_in, g_out, -t)
             g_out.average_into(w, v.data_ptr())
         ms2 = op2.timer_stop() / 3
-        value_indep = 2 * B / (ms2 * 1e-3)
         for b_ in (f_in, f_out, g_in, g_out):
             b_.close()
         op2.close()
+        return 2 * B / (ms2 * 1e-3)
+
+    value_indep = value_full = None
+    if rank == 0 and not args.no_roofline:
+        value_indep = plain_variant(shared_basis=False, economise=not args.full_series)
+        value_full = plain_variant(shared_basis=False, economise=False)
 
     # ------------------------------------------------------------ e2e through host pointers
     e2e = None
@@ -394,10 +407,15 @@ def main():
                                      f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}",
                        "parallelism": f"samples sharded, {B}/GPU", "panels_per_batch": b_bwd_in.num_panels,
                        "forward_batch": "shared input: recurrence for one column at max|t_k| + dense re-expansion to the 64 "
-                                        "sample times (exact, DESIGN.md); value_independent_columns = same step without it"},
+                                        "sample times (exact, DESIGN.md); value_independent_columns = same step without it",
+                       "series": ("full reference series for every column" if args.full_series else
+                                  "per-column economised re-expansion of the reference series (same polynomial, dropped tail "
+                                  "<= 1e-13; t_valid = L/eig = dt*rho); value_full_series = all 29 terms for all 128 columns, "
+                                  "no shared-input basis"),
+                       "terms_per_panel": terms_per_panel},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "value_independent_columns": value_indep,
+            "value_independent_columns": value_indep, "value_full_series": value_full,
             "timing": {"device_ms": ms_dev, "host_ms": ms_host},
         }
         print(json.dumps(out))

@@ -85,6 +85,13 @@ int kexp_set_mass_solver_chebyshev(kexp_ctx* ctx, double rtol, double lmin, doub
  * and L (cheby_exp.py:51-98).  id selects one of KEXP_MAX_CHEBY tables (cheby, cheby2). */
 #define KEXP_MAX_CHEBY 8
 int kexp_set_cheby(kexp_ctx* ctx, int id, const double* a, int ncheb, double L);
+/* Optional: the largest |t| the table is meant for, t_valid = L / rho(M^-1 K) -- the drivers build L exactly
+ * so, L = eigs[ref]*dt*rho (averaged_sw_explicit.py:77-82,168), i.e. t_valid = dt*rho, while the sample times
+ * only reach |t_k| <= dt*rho/2 (:91-95).  With it every column evaluates the SAME polynomial
+ * sum_n a_n S_n((t_k/L) A) through its exact re-expansion on the part of the Chebyshev interval the spectrum
+ * of (t_k/L) A actually fills, which needs fewer terms (dropped tail <= 1e-13 sum|b_m|).  A call with any
+ * |t_k| * 1.01 > t_valid, t_valid = 0, or KEXP_ECONOMISE=0 runs the full series. */
+int kexp_set_cheby_time_range(kexp_ctx* ctx, int id, double t_valid);
 
 /* cheby_exp.apply(x, y, t)  (cheby_exp.py:110): y = sum_n a_n S_n, x != y, x unchanged. */
 int kexp_cheby_apply(kexp_ctx* ctx, int id, const double* x, double* y, double t);
@@ -104,6 +111,11 @@ typedef struct kexp_batch kexp_batch;
 int kexp_batch_create(kexp_ctx* ctx, int B, kexp_batch** out);
 int kexp_batch_destroy(kexp_batch* b);
 int kexp_batch_num_panels(kexp_batch* b);     /* a batch is stored as panels of <= 64 (or 32) sample columns */
+/* Column order inside the batch: stored column j holds the caller's column order[j] (a permutation of
+ * 0..B-1; NULL = identity).  Upload, download, the sample times t and the weights w of the calls below
+ * always use the CALLER's order.  Sorting by |t_k| puts sample times of similar series length into one
+ * panel; the host-array entry points above do so themselves. */
+int kexp_batch_set_order(kexp_batch* b, const int32_t* order);
 int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared);   /* host -> HBM */
 int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy);                        /* HBM -> host */
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t);

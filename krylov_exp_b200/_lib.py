@@ -36,12 +36,14 @@ PROTOTYPES = {
     "kexp_set_mass_solver": (C.c_int, [_p, C.c_double, C.c_int, C.c_int]),
     "kexp_set_mass_solver_chebyshev": (C.c_int, [_p, C.c_double, C.c_double, C.c_double, C.c_int]),
     "kexp_set_cheby": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_double]),
+    "kexp_set_cheby_time_range": (C.c_int, [_p, C.c_int, C.c_double]),
     "kexp_cheby_apply": (C.c_int, [_p, C.c_int, _p, _p, C.c_double]),
     "kexp_cheby_apply_batch": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, C.c_int]),
     "kexp_cheby_apply_average": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, _p, C.c_int, _p, C.c_int]),
     "kexp_batch_create": (C.c_int, [_p, C.c_int, C.POINTER(_p)]),
     "kexp_batch_destroy": (C.c_int, [_p]),
     "kexp_batch_num_panels": (C.c_int, [_p]),
+    "kexp_batch_set_order": (C.c_int, [_p, _p]),
     "kexp_batch_upload": (C.c_int, [_p, _p, C.c_int64, C.c_int]),
     "kexp_batch_download": (C.c_int, [_p, _p, C.c_int64]),
     "kexp_cheby_apply_dev": (C.c_int, [_p, C.c_int, _p, _p, _p]),

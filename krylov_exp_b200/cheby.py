@@ -66,7 +66,9 @@ def real_table(coeffs, n):
 
 class cheby_exp(object):
     def __init__(self, operator_solver, operator_in, operator_out,
-                 ncheb, tol, L, filter=False, filter_val=0.75, filter_freq=False):
+                 ncheb, tol, L, filter=False, filter_val=0.75, filter_freq=False, *, spectral_radius=None):
+        """Same positional signature as the reference (cheby_exp.py:5-6).  `spectral_radius` (keyword only, an
+        extension) is the bound L was built from; see set_spectral_radius."""
         if isinstance(operator_solver, Operator):
             self.op = operator_solver
         else:
@@ -81,6 +83,17 @@ class cheby_exp(object):
         self.id = self.op.new_cheby_id()
         lib = self.op.lib
         self.op._check(lib.kexp_set_cheby(self.op.ctx, self.id, _lib.ptr(self.a), self.ncheb, float(L)), "kexp_set_cheby")
+        self.t_valid = 0.0
+        if spectral_radius is not None:
+            self.set_spectral_radius(spectral_radius)
+
+    def set_spectral_radius(self, eig):
+        """State the bound `eig` >= rho(M^-1 K) that L was built from (the drivers' `eigs[ref_level-3]`,
+        averaged_sw_explicit.py:77-82: L = eig*dt*rho).  The series is then valid for |t| <= L/eig and sample
+        times below that evaluate the same polynomial through a shorter, exactly re-expanded series
+        (include/kexp.h, kexp_set_cheby_time_range).  None/0 switches it off."""
+        self.t_valid = float(self.L) / float(eig) if eig else 0.0
+        self.op._check(self.op.lib.kexp_set_cheby_time_range(self.op.ctx, self.id, self.t_valid), "kexp_set_cheby_time_range")
 
     # ---- the reference interface -------------------------------------------------
     def apply(self, x, y, t):

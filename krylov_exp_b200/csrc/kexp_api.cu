@@ -522,26 +522,26 @@ void enqueue_op_finish(kexp_ctx* ctx, double* out) {
 
 // The whole cheby_exp.apply for one panel: S0 holds the input, Y receives the result.
 template <int W>
-void enqueue_cheby(kexp_ctx* ctx, int id) {
-    const ChebTable& tb = ctx->cheb[id];
+void enqueue_cheby(kexp_ctx* ctx, const PanelPlan& plan) {
     const size_t nelem2 = (size_t)ctx->n * W / 2;
+    const double* coef = ctx->d_tscale + kMaxW;             // row m: coefficient of S_m per column
     {
         TimedLaunch tl(ctx, KC_CHEB);
         int grid = (int)std::min<size_t>((size_t)8 * ctx->num_sms, (nelem2 + kThreads - 1) / kThreads);
-        launch_k(ctx, cheb_init_kernel<W>, std::max(grid, 1), kThreads, 0, ctx->S0, ctx->Y, nelem2, tb.d_coef);
+        launch_k(ctx, cheb_init_kernel<W>, std::max(grid, 1), kThreads, 0, ctx->S0, ctx->Y, nelem2, coef);
     }
     const int bgrid = std::max(1, std::min(4 * ctx->num_sms, (int)((ctx->n + kThreads - 1) / kThreads)));
     if (ctx->capture_basis) {
         TimedLaunch tl(ctx, KC_MISC);
         launch_k(ctx, basis_store_kernel<W>, bgrid, kThreads, 0, ctx->S0, (int)ctx->n, ctx->d_basis, ctx->basis_ld, 0);
     }
-    for (int n = 1; n <= tb.ncheb; ++n) {
+    for (int n = 1; n <= plan.M; ++n) {
         const double* in = (n & 1) ? ctx->S0 : ctx->S1;     // S_{n-1}
         double* Sn = (n & 1) ? ctx->S1 : ctx->S0;           // holds S_{n-2}, becomes S_n
-        enqueue_operator<W>(ctx, in, (ctx->use_relax && ctx->solver == 1) ? tb.h_relax[n] : 1.0);
+        enqueue_operator<W>(ctx, in, (ctx->use_relax && ctx->solver == 1) ? plan.relax[n] : 1.0);
         ChebStep st;
         st.n = n; st.has_old = (n >= 2) ? 1 : 0; st.cs = (n == 1) ? 1.0 : 2.0; st.check_cg = 1;
-        enqueue_cheb_update<W>(ctx, Sn, tb.d_coef, st);
+        enqueue_cheb_update<W>(ctx, Sn, coef, st);
         if (ctx->capture_basis) {
             TimedLaunch tl(ctx, KC_MISC);
             launch_k(ctx, basis_store_kernel<W>, bgrid, kThreads, 0, Sn, (int)ctx->n, ctx->d_basis, ctx->basis_ld, n);
@@ -560,20 +560,24 @@ void enqueue_cheby(kexp_ctx* ctx, int id) {
         default: return kexp::fail(ctx, "unsupported panel width"); \
     }
 
-int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
+int run_cheby_panel(kexp_ctx* ctx, int id, int W, const PanelPlan& plan) {
     if (ctx->timing || !ctx->use_graph) {
-        DISPATCH_W(W, enqueue_cheby<kW>(ctx, id));
+        DISPATCH_W(W, enqueue_cheby<kW>(ctx, plan));
         KEXP_CUDA(cudaGetLastError());
         return 0;
     }
-    auto key = std::make_pair(id + (ctx->capture_basis ? 1000 : 0), W);
+    const GraphKey key{id + (ctx->capture_basis ? 1000 : 0), W, plan.sig};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
-        // warm the occupancy cache outside capture
+        if (ctx->graphs.size() >= 48) {                  // sample times that change every call: do not hoard graphs
+            cudaStreamSynchronize(ctx->stream);
+            for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
+            ctx->graphs.clear();
+        }
         cudaGraph_t graph;
         int64_t l0 = ctx->st_launches, a0 = ctx->st_op_apps;
         KEXP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        DISPATCH_W(W, enqueue_cheby<kW>(ctx, id));
+        DISPATCH_W(W, enqueue_cheby<kW>(ctx, plan));
         KEXP_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
         ctx->st_launches = l0; ctx->st_op_apps = a0;     // counted per replay below
         cudaGraphExec_t exec;
@@ -582,10 +586,9 @@ int run_cheby_panel(kexp_ctx* ctx, int id, int W) {
         it = ctx->graphs.emplace(key, exec).first;
     }
     KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
-    const ChebTable& tb = ctx->cheb[id];
-    ctx->st_op_apps += tb.ncheb;
-    ctx->st_launches += 1 + (int64_t)tb.ncheb * (2 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0))
-                        + (ctx->capture_basis ? tb.ncheb + 1 : 0);
+    ctx->st_op_apps += plan.M;
+    ctx->st_launches += 1 + (int64_t)plan.M * (2 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0))
+                        + (ctx->capture_basis ? plan.M + 1 : 0);
     return 0;
 }
 
@@ -614,11 +617,12 @@ void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
 }
 
-int set_tscale(kexp_ctx* ctx, int id, const double* t, int col0, int B, int W) {
-    const double L = ctx->cheb[id].L;
+// Upload one panel's operator scales and series coefficients (graphs read them from d_tscale).
+int set_plan(kexp_ctx* ctx, const PanelPlan& plan) {
     cudaStreamSynchronize(ctx->stream);        // h_pin reuse
-    for (int k = 0; k < kMaxW; ++k) ctx->h_pin[k] = (k < W && col0 + k < B) ? t[col0 + k] / L : 0.0;
-    KEXP_CUDA(cudaMemcpyAsync(ctx->d_tscale, ctx->h_pin, sizeof(double) * kMaxW, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(ctx->h_pin, plan.tscale, sizeof(double) * kMaxW);
+    memcpy(ctx->h_pin + kMaxW, plan.coef.data(), sizeof(double) * plan.coef.size());
+    KEXP_CUDA(cudaMemcpyAsync(ctx->d_tscale, ctx->h_pin, sizeof(double) * (kMaxW + plan.coef.size()), cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
 
@@ -674,8 +678,8 @@ int unpack_panel(kexp_ctx* ctx, const double* src, double* d_dst, int64_t ld, in
 
 int colsum_panel(kexp_ctx* ctx, const double* Ypanel, const double* w, int col0, int B, int W, double* v_dev, int accumulate) {
     cudaStreamSynchronize(ctx->stream);
-    for (int k = 0; k < kMaxW; ++k) ctx->h_pin[kMaxW + k] = (k < W && col0 + k < B) ? w[col0 + k] : 0.0;
-    KEXP_CUDA(cudaMemcpyAsync(ctx->d_w, ctx->h_pin + kMaxW, sizeof(double) * kMaxW, cudaMemcpyHostToDevice, ctx->stream));
+    for (int k = 0; k < kMaxW; ++k) ctx->h_pin[kPinWeights + k] = (k < W && col0 + k < B) ? w[col0 + k] : 0.0;
+    KEXP_CUDA(cudaMemcpyAsync(ctx->d_w, ctx->h_pin + kPinWeights, sizeof(double) * kMaxW, cudaMemcpyHostToDevice, ctx->stream));
     TimedLaunch tl(ctx, KC_MISC);
     DISPATCH_W(W, launch_colsum<kW>(ctx, Ypanel, v_dev, accumulate));
     return 0;
@@ -701,8 +705,10 @@ int alloc_lane_scalars(kexp_ctx* ctx) {
     ok = ok && cudaMalloc(&ctx->d_partials, sizeof(double) * 3 * 9 * (size_t)ctx->num_sms * kMaxW + 4096) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_counter, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_counter, 0, sizeof(unsigned) * (size_t)(2 + ctx->num_sms)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_tscale, sizeof(double) * kMaxW) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ctx->h_pin, sizeof(double) * 2 * kMaxW) == cudaSuccess;
+    // [kMaxW operator scales][kMaxTerms rows of kMaxW series coefficients]; the pinned mirror has the
+    // averaging weights behind it
+    ok = ok && cudaMalloc(&ctx->d_tscale, sizeof(double) * kPinWeights) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_pin, sizeof(double) * (kPinWeights + kMaxW)) == cudaSuccess;
     const double r2 = ctx->rtol * ctx->rtol;
     ok = ok && cudaMemcpy(&ctx->d_sc->rtol2, &r2, sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     ctx->curW = 0;
@@ -769,6 +775,8 @@ int kexp_create(kexp_ctx** out, int device) {
     if (rl) ctx->use_relax = (rl[0] == '1');
     const char* co = getenv("KEXP_COOP");
     if (co) ctx->use_coop = (co[0] == '1');
+    if (const char* ec = getenv("KEXP_ECONOMISE")) ctx->use_econ = (ec[0] != '0');
+    if (const char* ee = getenv("KEXP_ECON_EPS")) { const double v = atof(ee); if (v > 0.0 && v < 1e-6) ctx->econ_eps = v; }
     const char* shb = getenv("KEXP_SHARED_BASIS");
     if (shb && shb[0] == '0') ctx->use_shared_basis = false;
     const char* sb = getenv("KEXP_SPMM_BLOCKS");
@@ -972,33 +980,48 @@ int kexp_set_mass_solver_chebyshev(kexp_ctx* ctx, double rtol, double lmin, doub
     return 0;
 }
 
+// Tolerance relaxation per term: an error introduced in the mass solve of term n reaches y only through
+// sum_{m>=n} a_m U_{m-n}(B) e with ||U_k|| <= k+1 on the spectrum, i.e. with weight w_n = sum_{m>=n} |a_m| (m-n+1).
+// The a_m decay super-exponentially beyond m ~ L, so late terms tolerate rtol * w_max / w_n (capped).
+static void relax_factors(const double* a, int M, std::vector<double>& relax) {
+    relax.assign((size_t)M + 1, 1.0);
+    std::vector<double> wgt((size_t)M + 1, 0.0);
+    double wmax = 0.0;
+    for (int n = 1; n <= M; ++n) {
+        double w = 0.0;
+        for (int m = n; m <= M; ++m) w += std::fabs(a[m]) * (double)(m - n + 1);
+        wgt[n] = w; wmax = std::max(wmax, w);
+    }
+    for (int n = 1; n <= M; ++n)
+        relax[n] = (wgt[n] > 0.0) ? std::min(1e6, std::max(1.0, wmax / wgt[n])) : 1e6;
+}
+
+int kexp_set_cheby_time_range(kexp_ctx* ctx, int id, double t_valid) {
+    if (check_ready(ctx, id)) return 1;
+    if (!(t_valid >= 0.0)) return kexp::fail(ctx, "t_valid must be >= 0 (0 disables the economised series)");
+    ctx->cheb[id].t_valid = t_valid;
+    ctx->plan_cache.clear();
+    return 0;
+}
+
 int kexp_set_cheby(kexp_ctx* ctx, int id, const double* a, int ncheb, double L) {
     if (!ctx) return 1;
     cudaSetDevice(ctx->device);
     if (id < 0 || id >= KEXP_MAX_CHEBY) return kexp::fail(ctx, "cheby id out of range");
     if (!a || ncheb < 0 || !(L > 0.0)) return kexp::fail(ctx, "bad Chebyshev table");
+    if (ncheb >= kMaxTerms) return kexp::fail(ctx, "Chebyshev series too long (ncheb must be below 1024)");
     invalidate_graphs(ctx);
     ChebTable& tb = ctx->cheb[id];
     cudaFree(tb.d_coef); tb.d_coef = nullptr;
     KEXP_CUDA(cudaMalloc(&tb.d_coef, sizeof(double) * (size_t)(ncheb + 1)));
     KEXP_CUDA(cudaMemcpy(tb.d_coef, a, sizeof(double) * (size_t)(ncheb + 1), cudaMemcpyHostToDevice));
-    tb.ncheb = ncheb; tb.L = L;
+    tb.ncheb = ncheb; tb.L = L; tb.t_valid = 0.0;
+    ctx->plan_cache.clear();
     tb.h_coef.assign(a, a + ncheb + 1);
     // Tolerance relaxation per term: an error introduced in the mass solve of term n reaches y only through
     // sum_{m>=n} a_m U_{m-n}(B) e with ||U_k|| <= k+1 on the spectrum, i.e. with weight w_n = sum_{m>=n} |a_m| (m-n+1).
     // The a_m decay super-exponentially beyond m ~ L, so late terms tolerate rtol * w_max / w_n (capped).
-    tb.h_relax.assign((size_t)ncheb + 1, 1.0);
-    {
-        std::vector<double> wgt((size_t)ncheb + 1, 0.0);
-        double wmax = 0.0;
-        for (int n = 1; n <= ncheb; ++n) {
-            double w = 0.0;
-            for (int m = n; m <= ncheb; ++m) w += std::fabs(a[m]) * (double)(m - n + 1);
-            wgt[n] = w; wmax = std::max(wmax, w);
-        }
-        for (int n = 1; n <= ncheb; ++n)
-            if (wgt[n] > 0.0) tb.h_relax[n] = std::min(1e6, std::max(1.0, wmax / wgt[n]));
-    }
+    relax_factors(tb.h_coef.data(), ncheb, tb.h_relax);
     return 0;
 }
 
@@ -1093,8 +1116,14 @@ static int batch_upload_impl(kexp_batch* b, const double* X, int64_t ldx, int x_
     for (size_t p = 0; p < b->panel.size() && !rc; ++p) {
         const int col0 = (int)p * b->stride;
         const int ncols = std::min(b->panelW[p], b->B - col0);
-        cudaError_t e = cudaMemcpy2DAsync(ctx->d_stage + (size_t)col0 * ctx->n, sizeof(double) * ctx->n, X + (size_t)col0 * ldx,
-                                          sizeof(double) * ldx, sizeof(double) * ctx->n, ncols, cudaMemcpyHostToDevice, ctx->copy_stream);
+        cudaError_t e = cudaSuccess;
+        if (b->order.empty())
+            e = cudaMemcpy2DAsync(ctx->d_stage + (size_t)col0 * ctx->n, sizeof(double) * ctx->n, X + (size_t)col0 * ldx,
+                                  sizeof(double) * ldx, sizeof(double) * ctx->n, ncols, cudaMemcpyHostToDevice, ctx->copy_stream);
+        else
+            for (int c = 0; c < ncols && e == cudaSuccess; ++c)
+                e = cudaMemcpyAsync(ctx->d_stage + (size_t)(col0 + c) * ctx->n, X + (size_t)b->order[col0 + c] * ldx,
+                                    sizeof(double) * ctx->n, cudaMemcpyHostToDevice, ctx->copy_stream);
         if (e != cudaSuccess) { rc = kexp::fail(ctx, cudaGetErrorString(e)); break; }
         rc = pack_panel(ctx, ctx->d_stage, ctx->n, 0, b->B, col0, b->panelW[p], b->panel[p]);
         if (!rc && cudaEventRecord(b->ready[p], ctx->copy_stream) != cudaSuccess) rc = kexp::fail(ctx, "event record failed");
@@ -1120,10 +1149,37 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
     for (size_t p = 0; p < b->panel.size(); ++p)
         if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * b->stride, b->panelW[p])) return 1;
-    KEXP_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, ctx->d_stage, sizeof(double) * ctx->n, sizeof(double) * ctx->n, b->B,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+    if (b->order.empty()) {
+        KEXP_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, ctx->d_stage, sizeof(double) * ctx->n, sizeof(double) * ctx->n, b->B,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        for (int j = 0; j < b->B; ++j)
+            KEXP_CUDA(cudaMemcpyAsync(Y + (size_t)b->order[j] * ldy, ctx->d_stage + (size_t)j * ctx->n, sizeof(double) * ctx->n,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    }
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int kexp_batch_set_order(kexp_batch* b, const int32_t* order) {
+    if (!b) return 1;
+    kexp_ctx* ctx = b->ctx;
+    if (finish_upload(b)) return 1;
+    if (!order) { b->order.clear(); return 0; }
+    std::vector<char> seen((size_t)b->B, 0);
+    for (int j = 0; j < b->B; ++j) {
+        if (order[j] < 0 || order[j] >= b->B || seen[order[j]]) return kexp::fail(ctx, "order is not a permutation of 0..B-1");
+        seen[order[j]] = 1;
+    }
+    b->order.assign(order, order + b->B);
+    return 0;
+}
+
+// order[j] = caller's column stored at position j, sorted by |t| (stable)
+static void order_by_abs_time(const double* t, int B, std::vector<int>& order) {
+    order.resize((size_t)B);
+    for (int j = 0; j < B; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::fabs(t[a]) < std::fabs(t[b]); });
 }
 
 // Combination coefficients of the shared-input path: D[m][k] = sum_n a_n E_nm(s_k), where
@@ -1151,36 +1207,166 @@ static void expansion_column(const std::vector<double>& a, double s, double* Dco
     }
 }
 
+static unsigned long long fnv1a(const void* data, size_t bytes, unsigned long long h = 1469598103934665603ull) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+static void finish_plan(PanelPlan& P) {
+    P.sig = fnv1a(&P.M, sizeof(P.M));
+    P.sig = fnv1a(P.relax.data(), sizeof(double) * P.relax.size(), P.sig);
+}
+
+// Number of leading coefficients to keep so that the dropped tail is below eps * sum |b_m|
+static int truncated_length(const double* b, int nb, int stride, double eps) {
+    double total = 0.0;
+    for (int m = 0; m < nb; ++m) total += std::fabs(b[(size_t)m * stride]);
+    double tail = 0.0;
+    int keep = nb;
+    while (keep > 1 && tail + std::fabs(b[(size_t)(keep - 1) * stride]) <= eps * total) { tail += std::fabs(b[(size_t)(keep - 1) * stride]); --keep; }
+    return keep;
+}
+
+// Can the per-column economised expansions be used for these sample times?
+static bool economise(const kexp_ctx* ctx, const ChebTable& tb, const double* t, int B) {
+    if (!ctx->use_econ || !(tb.t_valid > 0.0) || tb.ncheb < 2) return false;
+    for (int k = 0; k < B; ++k)
+        if (std::fabs(t[k]) * (1.0 + ctx->econ_margin) > tb.t_valid) return false;    // outside the stated validity range
+    return true;
+}
+
+// Plans of all panels of a batch of independent columns.
+//   reference series:   y_k = sum_n a_n S_n((t_k/L) A) x_k                                  (cheby_exp.py:110-165)
+//   economised:         the spectrum of (t_k/L) A only fills the fraction s_k = |t_k|/t_valid of the Chebyshev
+//                       interval, so with C = sign(t_k) (t_valid/L) A / (1+margin) (the same operator for every
+//                       column, spectrum in i[-1,1]) the SAME polynomial is  sum_m b_m^(k) S_m(C) x_k,
+//                       b^(k) = E(s_k)^T a  (exact re-expansion, expansion_column), whose coefficients fall below
+//                       round-off long before m = ncheb when s_k < 1.  Dropped tail <= econ_eps * sum|b|.
+static const std::vector<PanelPlan>& batch_plans(kexp_ctx* ctx, int id, const kexp_batch* bt, const double* t) {
+    const ChebTable& tb = ctx->cheb[id];
+    const int B = bt->B, np = (int)bt->panel.size();
+    unsigned long long key = fnv1a(&id, sizeof(id));
+    key = fnv1a(&B, sizeof(B), key);
+    key = fnv1a(&bt->stride, sizeof(bt->stride), key);
+    key = fnv1a(t, sizeof(double) * B, key);
+    auto it = ctx->plan_cache.find(key);
+    if (it != ctx->plan_cache.end()) return it->second;
+    if (ctx->plan_cache.size() >= 64) ctx->plan_cache.clear();
+    std::vector<PanelPlan> plans((size_t)np);
+    const bool econ = economise(ctx, tb, t, B);
+    const int nb = tb.ncheb + 1;
+    std::vector<double> bcol((size_t)nb);
+    for (int p = 0; p < np; ++p) {
+        PanelPlan& P = plans[p];
+        const int W = bt->panelW[p], col0 = p * bt->stride;
+        for (int c = 0; c < kMaxW; ++c) P.tscale[c] = 0.0;
+        if (!econ) {
+            P.M = tb.ncheb;
+            P.coef.assign((size_t)nb * kMaxW, 0.0);
+            for (int m = 0; m < nb; ++m)
+                for (int c = 0; c < W; ++c) P.coef[(size_t)m * kMaxW + c] = tb.h_coef[m];
+            for (int c = 0; c < W && col0 + c < B; ++c) P.tscale[c] = t[col0 + c] / tb.L;
+            P.relax = tb.h_relax;
+        } else {
+            std::vector<double> full((size_t)nb * kMaxW, 0.0);
+            std::vector<int> len((size_t)W, 1);
+            int keep = 1;
+            const double cscale = tb.t_valid / ((1.0 + ctx->econ_margin) * tb.L);
+            for (int c = 0; c < W && col0 + c < B; ++c) {
+                const double tk = t[col0 + c];
+                expansion_column(tb.h_coef, std::fabs(tk) * (1.0 + ctx->econ_margin) / tb.t_valid, &full[c], kMaxW);
+                len[c] = truncated_length(&full[c], nb, kMaxW, ctx->econ_eps);
+                keep = std::max(keep, len[c]);
+                P.tscale[c] = (tk < 0.0) ? -cscale : cscale;
+            }
+            P.M = keep - 1;
+            P.coef.assign(full.begin(), full.begin() + (size_t)keep * kMaxW);
+            // relaxation: the tightest requirement of any column of the panel
+            P.relax.assign((size_t)keep, 1e6);
+            std::vector<double> rc;
+            for (int c = 0; c < W && col0 + c < B; ++c) {
+                for (int m = 0; m < keep; ++m) bcol[m] = full[(size_t)m * kMaxW + c];
+                relax_factors(bcol.data(), P.M, rc);
+                for (int n = 1; n <= P.M; ++n) P.relax[n] = std::min(P.relax[n], rc[n]);
+            }
+            P.relax[0] = 1.0;
+        }
+        finish_plan(P);
+    }
+    return ctx->plan_cache.emplace(key, std::move(plans)).first->second;
+}
+
 // Forward half of an averaged evaluation: one input for all sample times.
 static int cheby_apply_shared(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
     const ChebTable& tb = ctx->cheb[id];
-    const int nb = tb.ncheb + 1;
     const int B = in->B;
+    const bool econ = economise(ctx, tb, t, B);
+    // basis U_m = S_m(c A) x for ONE column: c = t*/L with t* = max|t_k| (reference series, 29 terms at M1), or
+    // c = t_valid / ((1+margin) L) with the series truncated where every column's re-expansion has died out
     double tstar = 0.0;
     for (int k = 0; k < B; ++k) tstar = std::max(tstar, std::fabs(t[k]));
     if (tstar == 0.0) tstar = 1.0;
-    const int ld = (nb + 3) & ~3;
+    const double tbasis = econ ? tb.t_valid / (1.0 + ctx->econ_margin) : tstar;
+    int nb = tb.ncheb + 1;
+    // coefficients for every output panel, panel p at offset nb * (sum of earlier widths)
+    size_t totW = 0;
+    for (int W : out->panelW) totW += (size_t)W;
+    std::vector<double> D((size_t)nb * totW, 0.0);
+    PanelPlan plan;
+    {
+        size_t off = 0;
+        int keep = 1;
+        for (size_t p = 0; p < out->panel.size(); ++p) {
+            const int W = out->panelW[p];
+            for (int c = 0; c < W; ++c) {
+                const int k = (int)p * out->stride + c;
+                if (k < B) {
+                    expansion_column(tb.h_coef, t[k] / tbasis, &D[off + c], W);
+                    keep = std::max(keep, econ ? truncated_length(&D[off + c], nb, W, ctx->econ_eps) : nb);
+                }
+            }
+            off += (size_t)nb * W;
+        }
+        if (keep < nb) {                                   // repack with the shorter row count
+            std::vector<double> D2((size_t)keep * totW, 0.0);
+            size_t o1 = 0, o2 = 0;
+            for (size_t p = 0; p < out->panel.size(); ++p) {
+                const int W = out->panelW[p];
+                std::copy(D.begin() + o1, D.begin() + o1 + (size_t)keep * W, D2.begin() + o2);
+                o1 += (size_t)nb * W; o2 += (size_t)keep * W;
+            }
+            D.swap(D2);
+            nb = keep;
+        }
+        plan.M = nb - 1;
+        for (int c = 0; c < kMaxW; ++c) plan.tscale[c] = 0.0;
+        plan.tscale[0] = tbasis / tb.L;
+        plan.coef.assign((size_t)nb * kMaxW, 0.0);         // the 2-wide panel's own Y is not used
+        // relaxation of the basis run: the tightest requirement of any output column
+        plan.relax.assign((size_t)nb, 1e6);
+        std::vector<double> bcol((size_t)nb), rc;
+        off = 0;
+        for (size_t p = 0; p < out->panel.size(); ++p) {
+            const int W = out->panelW[p];
+            for (int c = 0; c < W; ++c) {
+                if ((int)p * out->stride + c >= B) continue;
+                for (int m = 0; m < nb; ++m) bcol[m] = D[off + (size_t)m * W + c];
+                relax_factors(bcol.data(), plan.M, rc);
+                for (int n = 1; n <= plan.M; ++n) plan.relax[n] = std::min(plan.relax[n], rc[n]);
+            }
+            off += (size_t)nb * W;
+        }
+        plan.relax[0] = 1.0;
+        finish_plan(plan);
+    }
+    const int ld = (tb.ncheb + 1 + 3) & ~3;
     if (ctx->basis_ld < ld) {
         cudaStreamSynchronize(ctx->stream);
         cudaFree(ctx->d_basis); ctx->d_basis = nullptr; ctx->basis_ld = 0;
         KEXP_CUDA(cudaMalloc(&ctx->d_basis, sizeof(double) * (size_t)ctx->n * ld));
         ctx->basis_ld = ld;
         invalidate_graphs(ctx);
-    }
-    // coefficients for every output panel, panel p at offset nb * (sum of earlier widths)
-    size_t totW = 0;
-    for (int W : out->panelW) totW += (size_t)W;
-    std::vector<double> D((size_t)nb * totW, 0.0);
-    {
-        size_t off = 0;
-        for (size_t p = 0; p < out->panel.size(); ++p) {
-            const int W = out->panelW[p];
-            for (int c = 0; c < W; ++c) {
-                const int k = (int)p * out->stride + c;
-                if (k < B) expansion_column(tb.h_coef, t[k] / tstar, &D[off + c], W);
-            }
-            off += (size_t)nb * W;
-        }
     }
     if (swap_lane(ctx, 0)) return 1;
     cudaStreamSynchronize(ctx->stream);              // d_D reuse
@@ -1194,10 +1380,10 @@ static int cheby_apply_shared(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch*
     warm_occupancy<2>(ctx);
     max_grid(ctx, basis_store_kernel<2>);
     if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-    if (set_tscale(ctx, id, &tstar, 0, 1, 2)) return 1;
+    if (set_plan(ctx, plan)) return 1;
     KEXP_CUDA(cudaMemcpyAsync(ctx->S0, in->shared_vec, sizeof(double) * 2 * (size_t)ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->capture_basis = true;
-    const int rc = run_cheby_panel(ctx, id, 2);
+    const int rc = run_cheby_panel(ctx, id, 2, plan);
     ctx->capture_basis = false;
     if (rc) return 1;
     size_t off = 0;
@@ -1226,6 +1412,7 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
     for (int W : in->panelW) maxW = std::max(maxW, W);
     for (int W : in->panelW) DISPATCH_W(W, warm_occupancy<kW>(ctx));
     const int np = (int)in->panel.size();
+    const std::vector<PanelPlan>& plans = batch_plans(ctx, id, in, t);
     const bool two = ctx->nlanes == 2 && !ctx->timing && np >= 2;
     if (swap_lane(ctx, 0)) return 1;
     if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
@@ -1242,9 +1429,9 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
         if (ensure_panels(ctx, W)) return 1;
         if (in->pending) KEXP_CUDA(cudaStreamWaitEvent(ctx->stream, in->ready[p], 0));     // panel still being uploaded
         const size_t bytes = sizeof(double) * (size_t)ctx->n * W;
-        if (set_tscale(ctx, id, t, p * in->stride, in->B, W)) return 1;
+        if (set_plan(ctx, plans[p])) return 1;
         KEXP_CUDA(cudaMemcpyAsync(ctx->S0, in->panel[p], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (run_cheby_panel(ctx, id, W)) return 1;
+        if (run_cheby_panel(ctx, id, W, plans[p])) return 1;
         KEXP_CUDA(cudaMemcpyAsync(out->panel[p], ctx->Y, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (lane1_used) {
@@ -1276,6 +1463,16 @@ static int read_cg_counters(kexp_ctx* ctx, int* max_iters, int* unconverged) {
 
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t) {
     if (!ctx) return 1;
+    std::vector<double> ts;
+    if (in && out && t && in->B == out->B) {
+        // t is given in the caller's column order; the output takes the stored order of a per-column input
+        if (!(in->is_shared && ctx->use_shared_basis) && in != out) out->order = in->order;
+        if (!out->order.empty()) {
+            ts.resize((size_t)out->B);
+            for (int j = 0; j < out->B; ++j) ts[j] = t[out->order[j]];
+            t = ts.data();
+        }
+    }
     if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
     if (ctx->timing) drain_events(ctx);
     if (!ctx->adaptive_its) return 0;
@@ -1341,6 +1538,12 @@ int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev) {
     kexp_ctx* ctx = b->ctx;
     cudaSetDevice(ctx->device);
     if (finish_upload(b)) return 1;
+    std::vector<double> ws;
+    if (!b->order.empty()) {
+        ws.resize((size_t)b->B);
+        for (int j = 0; j < b->B; ++j) ws[j] = w[b->order[j]];
+        w = ws.data();
+    }
     for (size_t p = 0; p < b->panel.size(); ++p)
         if (colsum_panel(ctx, b->panel[p], w, (int)p * b->stride, b->B, b->panelW[p], v_dev, p > 0)) return 1;
     return 0;
@@ -1361,6 +1564,18 @@ static int scratch_batches(kexp_ctx* ctx, int B, kexp_batch** bi, kexp_batch** b
     return 0;
 }
 
+// Host-array entry points own their batches, so they are free to store the columns sorted by |t_k| when the
+// economised series are in use (more than one panel: otherwise the order makes no difference).
+static int set_scratch_order(kexp_ctx* ctx, int id, kexp_batch* bi, kexp_batch* bo, const double* t, int B) {
+    if (finish_upload(bi) || finish_upload(bo)) return 1;
+    bi->order.clear(); bo->order.clear();
+    if (bo->panel.size() > 1 && economise(ctx, ctx->cheb[id], t, B)) {
+        order_by_abs_time(t, B, bi->order);
+        bo->order = bi->order;
+    }
+    return 0;
+}
+
 int kexp_cheby_apply_batch(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
                            double* Y, int64_t ldy, const double* t, int B) {
     if (check_ready(ctx, id)) return 1;
@@ -1368,6 +1583,7 @@ int kexp_cheby_apply_batch(kexp_ctx* ctx, int id, const double* X, int64_t ldx, 
     if (X == Y) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
     kexp_batch *bi = nullptr, *bo = nullptr;
     int rc = scratch_batches(ctx, B, &bi, &bo);
+    if (!rc) rc = set_scratch_order(ctx, id, bi, bo, t, B);
     if (!rc) rc = batch_upload_impl(bi, X, ldx, x_is_shared, false);
     if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
     if (!rc) rc = kexp_batch_download(bo, Y, ldy);
@@ -1387,6 +1603,7 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
     if (!X || !t || !w || !v_out || B < 1) return kexp::fail(ctx, "bad arguments");
     kexp_batch *bi = nullptr, *bo = nullptr;
     int rc = scratch_batches(ctx, B, &bi, &bo);
+    if (!rc) rc = set_scratch_order(ctx, id, bi, bo, t, B);
     if (!rc) rc = batch_upload_impl(bi, X, ldx, x_is_shared, false);
     if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
     if (!rc) rc = kexp_batch_average_dev(bo, w, ctx->d_v);
@@ -1405,6 +1622,7 @@ int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     if (!in || !out || in->B != out->B) return kexp::fail(ctx, "bad batches");
     cudaSetDevice(ctx->device);
     if (finish_upload(in)) return 1;
+    if (in != out) out->order = in->order;
     int maxW = 0;
     for (int W : in->panelW) maxW = std::max(maxW, W);
     if (ensure_panels(ctx, maxW)) return 1;
@@ -1436,6 +1654,7 @@ int kexp_spmm_K_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     if (!in || !out || in->B != out->B || in == out) return kexp::fail(ctx, "bad batches");
     cudaSetDevice(ctx->device);
     if (finish_upload(in)) return 1;
+    out->order = in->order;
     KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
     for (size_t p = 0; p < in->panel.size(); ++p) {
         const int W = in->panelW[p];

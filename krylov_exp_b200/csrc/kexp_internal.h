@@ -55,6 +55,27 @@ struct ChebTable {
     double* d_coef = nullptr;      // ncheb+1 doubles
     std::vector<double> h_coef;    // host copy (shared-input expansion coefficients)
     std::vector<double> h_relax;   // per-term tolerance relaxation factor of the mass solve (>= 1)
+    double t_valid = 0.0;          // largest |t| the series is valid for (L / spectral radius); 0 = unknown
+};
+
+// What one panel of columns runs: number of terms, per-column operator scale and series coefficients
+// (reference series, or its per-column economised re-expansion), per-term tolerance relaxation.
+struct PanelPlan {
+    int M = 0;                          // highest term index = number of operator applications
+    double tscale[64];                  // per column: B_k = tscale_k * M^-1 K
+    std::vector<double> coef;           // (M+1) x kMaxW, row m = coefficient of S_m per column
+    std::vector<double> relax;          // M+1
+    unsigned long long sig = 0;         // identifies (M, relax) -- what a captured graph depends on
+};
+
+struct GraphKey {
+    int id, W;
+    unsigned long long sig;
+    bool operator<(const GraphKey& o) const {
+        if (id != o.id) return id < o.id;
+        if (W != o.W) return W < o.W;
+        return sig < o.sig;
+    }
 };
 
 struct KrylovState;               // kexp_krylov.cu
@@ -72,7 +93,7 @@ struct LaneState {
     unsigned* d_counter = nullptr;
     double* d_tscale = nullptr;
     double* h_pin = nullptr;
-    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
     unsigned long long base_iters = 0, base_solves = 0;
 };
 
@@ -132,10 +153,14 @@ struct kexp_ctx {
     double* d_D = nullptr;         // (ncheb+1) x 64 combination coefficients
     size_t d_D_cap = 0;
     bool use_shared_basis = true;  // KEXP_SHARED_BASIS=0: treat shared-input batches as 64 independent columns
+    std::map<unsigned long long, std::vector<kexp::PanelPlan>> plan_cache;   // per (table, layout, sample times)
+    bool use_econ = true;          // KEXP_ECONOMISE=0: always run the full reference series (no per-column re-expansion)
+    double econ_eps = 1e-13;       // dropped tail of a re-expanded series, relative to sum |b_m|   (KEXP_ECON_EPS)
+    double econ_margin = 0.01;     // safety on the spectral interval: s_k = |t_k| (1 + margin) / t_valid
     bool capture_basis = false;    // enqueue_cheby stores every S_m (column 0) into d_basis
 
     // graphs keyed by (cheby id, W)
-    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    std::map<kexp::GraphKey, cudaGraphExec_t> graphs;
     bool use_graph = true;
     bool use_pdl = true;           // programmatic dependent launch between the kernels of the graph (KEXP_PDL=0 disables): +3 %
     bool use_tma = false;          // shared-memory-staged CG product for 64-column panels (KEXP_STAGED_SPMM=1): slower, see profiles/
@@ -183,6 +208,10 @@ struct kexp_batch {
     bool is_shared = false;
     std::vector<cudaEvent_t> ready;   // per panel: upload + pack finished (copy stream)
     bool pending = false;          // an asynchronous upload may still be in flight
+    // stored column j holds the caller's column order[j] (empty = identity).  Sorting the columns by |t_k|
+    // groups sample times of similar economised series length into the same panel.
+    std::vector<int> order;
+    int user_col(int j) const { return order.empty() ? j : order[j]; }
 };
 
 namespace kexp {

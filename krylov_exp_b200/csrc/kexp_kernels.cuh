@@ -20,6 +20,8 @@ namespace kexp {
 
 constexpr int kThreads = 256;
 constexpr int kMaxW = 64;
+constexpr int kMaxTerms = 1024;                       // rows of the per-panel coefficient table (terms 0..1023)
+constexpr int kPinWeights = kMaxW * (1 + kMaxTerms);  // offset of the averaging weights in the pinned staging buffer
 
 // Per-panel CG scalars, one slot per sample column (device memory).
 struct CgScalars {
@@ -1069,8 +1071,9 @@ cg_update_kernel(double* __restrict__ x, double* __restrict__ r, double* __restr
 //   SRC 0: a panel (the CG solution x, or T for rows that need no solve)
 //   SRC 1: T + Rt * x   (back-substitution rows of the condensed plan, CSR Rt)
 //   SRC 2: Dblk * T     (3x3 block rows: DG1 mass inverse of the plain plan)
-// The coefficient table and t_k/L live in device memory; each block stages them in shared
-// memory once.
+// The coefficient table (one row of kMaxW per term: every column may carry its own series, see
+// the economised per-column expansions in kexp_api.cu) and the per-column operator scale live in
+// device memory; each block stages its row in shared memory once.
 // ------------------------------------------------------------------------------------
 struct ChebStep {
     int n;            // term index (coefficient a[n])
@@ -1089,18 +1092,20 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
                    CgScalars* __restrict__ sc) {
     constexpr int LPR = W / 2;
     __shared__ double s_ts[kMaxW];
-    __shared__ double s_a;
+    __shared__ double s_a[kMaxW];
     pdl_wait();
     pdl_trigger();
-    if (threadIdx.x < W) s_ts[threadIdx.x] = st.cs * tscale[threadIdx.x];
+    if (threadIdx.x < W) {
+        s_ts[threadIdx.x] = st.cs * tscale[threadIdx.x];
+        s_a[threadIdx.x] = coef[(size_t)st.n * kMaxW + threadIdx.x];      // per-column series coefficient of term n
+    }
     if (threadIdx.x == 0) {
-        s_a = coef[st.n];
         if (st.check_cg && blockIdx.x == 0 && !sc->done) sc->unconverged += 1;
     }
     __syncthreads();
     const int l = threadIdx.x % LPR;
     const double2 ts = make_double2(s_ts[2 * l], s_ts[2 * l + 1]);
-    const double an = s_a;
+    const double2 an = make_double2(s_a[2 * l], s_a[2 * l + 1]);
     const int g0 = (blockIdx.x * kThreads + threadIdx.x) / LPR;
     const int ng = gridDim.x * kThreads / LPR;
     if (SRC == 2) {
@@ -1117,7 +1122,7 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
                 double2 s = st.has_old ? ld2_stream(S + oi) : make_double2(0.0, 0.0);
                 s.x = fma(ts.x, wv[i][0].x, s.x); s.y = fma(ts.y, wv[i][0].y, s.y);
                 double2 y = ld2_stream(Y + oi);
-                y.x = fma(an, s.x, y.x); y.y = fma(an, s.y, y.y);
+                y.x = fma(an.x, s.x, y.x); y.y = fma(an.y, s.y, y.y);
                 st2(S + oi, s); st2(Y + oi, y);
             }
         }
@@ -1136,7 +1141,7 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
             double2 s = st.has_old ? ld2_stream(S + o) : make_double2(0.0, 0.0);
             s.x = fma(ts.x, wv.x, s.x); s.y = fma(ts.y, wv.y, s.y);
             double2 y = ld2_stream(Y + o);
-            y.x = fma(an, s.x, y.x); y.y = fma(an, s.y, y.y);
+            y.x = fma(an.x, s.x, y.x); y.y = fma(an.y, s.y, y.y);
             st2(S + o, s); st2(Y + o, y);
         }
     }
@@ -1148,10 +1153,13 @@ __global__ void __launch_bounds__(kThreads)
 cheb_init_kernel(const double* __restrict__ S0, double* __restrict__ Y, size_t nelem2, const double* __restrict__ coef) {
     pdl_wait();
     pdl_trigger();
-    const double a0 = coef[0];
+    constexpr int LPR = W / 2;
+    // kThreads and the grid stride are multiples of LPR: a thread keeps its column pair
+    const int l = threadIdx.x % LPR;
+    const double2 a0 = make_double2(coef[2 * l], coef[2 * l + 1]);
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < nelem2; i += (size_t)gridDim.x * kThreads) {
         double2 v = ld2_stream(S0 + 2 * i);
-        v.x *= a0; v.y *= a0;
+        v.x *= a0.x; v.y *= a0.y;
         st2(Y + 2 * i, v);
     }
 }

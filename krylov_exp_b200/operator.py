@@ -308,6 +308,16 @@ class DeviceBatch:
     def num_panels(self):
         return int(self.op.lib.kexp_batch_num_panels(self.handle))
 
+    def set_order(self, order=None):
+        """Stored column j holds the caller's column order[j]; uploads, downloads, sample times and weights keep the
+        caller's order.  `np.argsort(np.abs(t), kind="stable")` groups sample times of similar series length."""
+        if order is None:
+            self.op._check(self.op.lib.kexp_batch_set_order(self.handle, None), "kexp_batch_set_order")
+            return
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        assert order.shape == (self.B,)
+        self.op._check(self.op.lib.kexp_batch_set_order(self.handle, _lib.ptr(order)), "kexp_batch_set_order")
+
     def upload(self, X, shared=False):
         X = np.asarray(X, dtype=np.float64)
         if shared:

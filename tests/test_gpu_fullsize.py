@@ -18,7 +18,7 @@ def setup5():
     sw = get_sw(5)
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-12, max_it=50, solver="chebyshev")
     L = kx.EIGS[2] * DT * RHO
-    ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L)
+    ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L, spectral_radius=kx.EIGS[2])   # L = eigs[2]*dt*rho, :77-82,168
     assert ce.ncheb == 29                                   # qjrms setup
     t, w = kx.sample_times_weights(64, DT, RHO)
     x = test_pulse(sw)
