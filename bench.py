@@ -293,6 +293,32 @@ def main():
         op2.close()
         return 2 * B / (ms2 * 1e-3)
 
+    # ------------------------------------------------------------ the averaged evaluation with the fused
+    # backward half: forward batch as above, then sum_k w_k exp(-t_k L) N_k by ONE Clenshaw recurrence
+    # (kexp_cheby_average_fused_dev) -- what timestepping_methods.py:7-11 needs; the 64 backward results
+    # are never formed, so this is reported beside `value`, not as it
+    fused = None
+    if rank == 0 and not args.no_roofline:
+        def step_fused():
+            ce.apply_dev(b_fwd_in, b_fwd_out, t)
+            ce.average_dev(b_bwd_in, -t, w, v.data_ptr())
+        for _ in range(3):
+            step_fused()
+        op.synchronize()
+        v_sep = torch.empty_like(v)
+        ce.apply_dev(b_bwd_in, b_bwd_out, -t)
+        b_bwd_out.average_into(w, v_sep.data_ptr())
+        op.synchronize()
+        dv = float(torch.linalg.norm(v - v_sep) / torch.linalg.norm(v_sep))
+        op.timer_start()
+        for _ in range(max(args.steps, 5)):
+            step_fused()
+        ms_f = op.timer_stop() / max(args.steps, 5)
+        fused = {"ms_per_averaged_evaluation": ms_f, "equivalent_applications_per_s": 2 * B / (ms_f * 1e-3),
+                 "rel_l2_vs_separate_applications": dv,
+                 "what": "forward shared-input batch (64 results delivered) + fused Clenshaw weighted average of the 64 backward "
+                         "applications (only their sum is formed)"}
+
     value_indep = value_full = None
     if rank == 0 and not args.no_roofline:
         value_indep = plain_variant(shared_basis=False, economise=not args.full_series)
@@ -416,6 +442,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "value_independent_columns": value_indep, "value_full_series": value_full,
+            "averaged_evaluation_fused": fused,
             "timing": {"device_ms": ms_dev, "host_ms": ms_host},
         }
         print(json.dumps(out))

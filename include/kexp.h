@@ -106,6 +106,13 @@ int kexp_cheby_apply_batch(kexp_ctx* ctx, int id, const double* X, int64_t ldx, 
 int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
                              const double* t, const double* w, int B, double* v_out, int do_allreduce);
 
+/* The same weighted sum WITHOUT forming the B individual results: every column is a polynomial in the
+ * same operator, so  sum_k w_k exp(t_k L) X_k = sum_m S_m(C) z_m  with  z_m = sum_k w_k b_m^(k) X_k,  one
+ * dense combination of the inputs followed by ONE Clenshaw recurrence on a single column
+ * (timestepping_methods.py:9-11 only ever uses the sum).  Same result to round-off. */
+int kexp_cheby_apply_average_fused(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
+                                   const double* t, const double* w, int B, double* v_out, int do_allreduce);
+
 /* ---- device-resident batches (the hot loop without host<->device copies) ---------- */
 typedef struct kexp_batch kexp_batch;
 int kexp_batch_create(kexp_ctx* ctx, int B, kexp_batch** out);
@@ -119,6 +126,8 @@ int kexp_batch_set_order(kexp_batch* b, const int32_t* order);
 int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared);   /* host -> HBM */
 int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy);                        /* HBM -> host */
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t);
+/* device-resident form of kexp_cheby_apply_average_fused; v_dev as in kexp_batch_average_dev */
+int kexp_cheby_average_fused_dev(kexp_ctx* ctx, int id, kexp_batch* in, const double* t, const double* w, double* v_dev);
 /* v_dev: device pointer to n doubles (e.g. a torch tensor's data_ptr), user dof order */
 int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev);
 int kexp_synchronize(kexp_ctx* ctx);

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "kexp_cheby_apply": (C.c_int, [_p, C.c_int, _p, _p, C.c_double]),
     "kexp_cheby_apply_batch": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, C.c_int]),
     "kexp_cheby_apply_average": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, _p, C.c_int, _p, C.c_int]),
+    "kexp_cheby_apply_average_fused": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, _p, C.c_int, _p, C.c_int]),
     "kexp_batch_create": (C.c_int, [_p, C.c_int, C.POINTER(_p)]),
     "kexp_batch_destroy": (C.c_int, [_p]),
     "kexp_batch_num_panels": (C.c_int, [_p]),
@@ -48,6 +49,7 @@ PROTOTYPES = {
     "kexp_batch_download": (C.c_int, [_p, _p, C.c_int64]),
     "kexp_cheby_apply_dev": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "kexp_batch_average_dev": (C.c_int, [_p, _p, _p]),
+    "kexp_cheby_average_fused_dev": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "kexp_synchronize": (C.c_int, [_p]),
     "kexp_timer_start": (C.c_int, [_p]),
     "kexp_timer_stop": (C.c_int, [_p, C.POINTER(C.c_double)]),

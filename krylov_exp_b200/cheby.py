@@ -126,17 +126,28 @@ class cheby_exp(object):
                                                   _lib.ptr(out), out.strides[0] // 8, _lib.ptr(t), B), "kexp_cheby_apply_batch")
         return out
 
-    def apply_average(self, X, t, w, shared=False, allreduce=False):
-        """sum_k w_k exp(t_k L) X_k: `DU *= wt; ensemble.allreduce(DU, V)` (timestepping_methods.py:9-11)."""
+    def apply_average(self, X, t, w, shared=False, allreduce=False, fused=False):
+        """sum_k w_k exp(t_k L) X_k: `DU *= wt; ensemble.allreduce(DU, V)` (timestepping_methods.py:9-11).
+        fused=True never forms the B individual results: the inputs are combined into the vector coefficients of
+        one polynomial in M^-1 K, evaluated by a single Clenshaw recurrence (same sum to round-off)."""
         t = np.ascontiguousarray(t, dtype=np.float64)
         w = np.ascontiguousarray(w, dtype=np.float64)
         B = t.shape[0]
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1) if shared else np.atleast_2d(X), dtype=np.float64)
         v = np.empty(self.op.n)
         lib = self.op.lib
-        self.op._check(lib.kexp_cheby_apply_average(self.op.ctx, self.id, _lib.ptr(X), self.op.n, int(shared), _lib.ptr(t),
-                                                    _lib.ptr(w), B, _lib.ptr(v), int(allreduce)), "kexp_cheby_apply_average")
+        fn = lib.kexp_cheby_apply_average_fused if fused else lib.kexp_cheby_apply_average
+        self.op._check(fn(self.op.ctx, self.id, _lib.ptr(X), self.op.n, int(shared), _lib.ptr(t),
+                          _lib.ptr(w), B, _lib.ptr(v), int(allreduce)), "kexp_cheby_apply_average")
         return v
+
+    def average_dev(self, bin_: DeviceBatch, t, w, v_dev_ptr):
+        """Fused weighted average of a device-resident batch into the device vector at `v_dev_ptr` (n doubles)."""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        assert t.shape == (bin_.B,) and w.shape == (bin_.B,)
+        self.op._check(self.op.lib.kexp_cheby_average_fused_dev(self.op.ctx, self.id, bin_.handle, _lib.ptr(t), _lib.ptr(w),
+                                                                C.c_void_p(int(v_dev_ptr))), "kexp_cheby_average_fused_dev")
 
     def apply_dev(self, bin_: DeviceBatch, bout: DeviceBatch, t):
         """Device-resident batch in, device-resident batch out (no host copies)."""

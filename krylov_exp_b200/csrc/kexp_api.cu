@@ -697,6 +697,41 @@ void launch_combine(kexp_ctx* ctx, int nb, const double* D, double* Y) {
     k<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_basis, ctx->basis_ld, nb, D, Y, (int)ctx->n);
 }
 
+template <int W>
+void enqueue_clenshaw(kexp_ctx* ctx, const PanelPlan& plan) {
+    const int n = (int)ctx->n;
+    const size_t bytes = sizeof(double) * (size_t)n * W;
+    const int bgrid = std::max(1, std::min(4 * ctx->num_sms, (n + kThreads - 1) / kThreads));
+    const double* coef = ctx->d_tscale + kMaxW;             // one row of zeros: the Y accumulation is not used
+    cudaMemsetAsync(ctx->S0, 0, bytes, ctx->stream);
+    cudaMemsetAsync(ctx->S1, 0, bytes, ctx->stream);
+    cudaMemsetAsync(ctx->Y, 0, bytes, ctx->stream);
+    auto add_z = [&](double* S, int m) {
+        TimedLaunch tl(ctx, KC_MISC);
+        basis_axpy_kernel<W><<<bgrid, kThreads, 0, ctx->stream>>>(S, n, ctx->d_basis, ctx->basis_ld, m);
+    };
+    double* A = ctx->S0;                                    // u_{m+1}
+    double* Bf = ctx->S1;                                   // u_{m+2}
+    add_z(A, plan.M);                                       // u_M = z_M
+    for (int m = plan.M - 1; m >= 0; --m) {
+        add_z(Bf, m);                                       // u_{m+2} + z_m
+        enqueue_operator<W>(ctx, A, (ctx->use_relax && ctx->solver == 1) ? plan.relax[m] : 1.0);
+        ChebStep st;
+        st.n = 0; st.has_old = 1; st.cs = (m == 0) ? 1.0 : 2.0; st.check_cg = 1;
+        enqueue_cheb_update<W>(ctx, Bf, coef, st);          // + cs * c * M^-1 K u_{m+1}
+        std::swap(A, Bf);
+    }
+}
+
+template <int W>
+void launch_clenshaw_combine(kexp_ctx* ctx, const double* X, const double* G, int nb, int accumulate) {
+    auto k = clenshaw_combine_kernel<W>;
+    const size_t smem = sizeof(double) * (size_t)nb * W;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = std::max(1, std::min(8 * ctx->num_sms, (int)((ctx->n + kThreads - 1) / kThreads)));
+    k<<<grid, kThreads, smem, ctx->stream>>>(X, (int)ctx->n, G, nb, ctx->d_basis, ctx->basis_ld, accumulate);
+}
+
 int alloc_lane_scalars(kexp_ctx* ctx) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_sc, sizeof(CgScalars)) == cudaSuccess;
@@ -1398,6 +1433,145 @@ static int cheby_apply_shared(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch*
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused weighted average  v = sum_k w_k exp(t_k L) X_k  as ONE Clenshaw recurrence (see
+// clenshaw_combine_kernel).  t and w are in the stored column order of `in`.
+// ---------------------------------------------------------------------------------------------
+static int run_clenshaw(kexp_ctx* ctx, int id, const PanelPlan& plan) {
+    constexpr int W = 2;
+    if (ctx->timing || !ctx->use_graph) {
+        enqueue_clenshaw<W>(ctx, plan);
+        KEXP_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const GraphKey key{id + 2000, W, plan.sig};
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+        if (ctx->graphs.size() >= 48) {
+            cudaStreamSynchronize(ctx->stream);
+            for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.second);
+            ctx->graphs.clear();
+        }
+        cudaGraph_t graph;
+        int64_t l0 = ctx->st_launches, a0 = ctx->st_op_apps;
+        KEXP_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_clenshaw<W>(ctx, plan);
+        KEXP_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+        ctx->st_launches = l0; ctx->st_op_apps = a0;
+        cudaGraphExec_t exec;
+        KEXP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = ctx->graphs.emplace(key, exec).first;
+    }
+    KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
+    ctx->st_op_apps += plan.M;
+    ctx->st_launches += 1 + (int64_t)plan.M * (3 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
+    return 0;
+}
+
+static int cheby_average_fused_impl(kexp_ctx* ctx, int id, kexp_batch* in, const double* t, const double* w, double* v_dev) {
+    if (check_ready(ctx, id)) return 1;
+    if (!in || !t || !w || !v_dev) return kexp::fail(ctx, "null argument");
+    cudaSetDevice(ctx->device);
+    const ChebTable& tb = ctx->cheb[id];
+    const int B = in->B;
+    const bool shared = in->is_shared && in->shared_vec && ctx->use_shared_basis;
+    if ((size_t)(tb.ncheb + 1) * 64 * sizeof(double) > 160 * 1024) return kexp::fail(ctx, "series too long for the fused average");
+    if (swap_lane(ctx, 0)) return 1;
+    if (finish_upload(in)) return 1;
+    const bool econ = economise(ctx, tb, t, B);
+    double tstar = 0.0;
+    for (int k = 0; k < B; ++k) tstar = std::max(tstar, std::fabs(t[k]));
+    if (tstar == 0.0) tstar = 1.0;
+    const double tbasis = econ ? tb.t_valid / (1.0 + ctx->econ_margin) : tstar;
+    const int nbf = tb.ncheb + 1;
+    // b^(k) for every column, the common truncation, and the per-step tolerance relaxation
+    std::vector<double> D((size_t)nbf * B);
+    int keep = 1;
+    for (int k = 0; k < B; ++k) {
+        expansion_column(tb.h_coef, t[k] / tbasis, &D[k], B);
+        if (w[k] != 0.0) keep = std::max(keep, truncated_length(&D[k], nbf, B, ctx->econ_eps));
+    }
+    PanelPlan plan;
+    plan.M = keep - 1;
+    for (int c = 0; c < kMaxW; ++c) plan.tscale[c] = 0.0;
+    plan.tscale[0] = tbasis / tb.L;
+    plan.coef.assign((size_t)kMaxW, 0.0);
+    // step m applies the operator to u_{m+1}; an error there reaches v through a polynomial of degree m
+    // (norm <= m+1), and u_{m+1} only holds the share sum_{j>m} (j-m) |b_j| of a column's series
+    plan.relax.assign((size_t)keep, 1e6);
+    for (int k = 0; k < B; ++k) {
+        if (w[k] == 0.0) continue;
+        std::vector<double> om((size_t)keep, 0.0);
+        double omax = 0.0;
+        for (int m = 0; m < plan.M; ++m) {
+            double g = 0.0;
+            for (int j = m + 1; j <= plan.M; ++j) g += (double)(j - m) * std::fabs(D[(size_t)j * B + k]);
+            om[m] = (double)(m + 1) * g;
+            omax = std::max(omax, om[m]);
+        }
+        for (int m = 0; m < plan.M; ++m)
+            if (om[m] > 0.0) plan.relax[m] = std::min(plan.relax[m], std::max(1.0, omax / om[m]));
+    }
+    finish_plan(plan);
+    // Z = inputs x (w_k b_m^(k)):   [n][ld]
+    const int ld = (tb.ncheb + 1 + 3) & ~3;
+    if (ctx->basis_ld < ld) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_basis); ctx->d_basis = nullptr; ctx->basis_ld = 0;
+        KEXP_CUDA(cudaMalloc(&ctx->d_basis, sizeof(double) * (size_t)ctx->n * ld));
+        ctx->basis_ld = ld;
+        invalidate_graphs(ctx);
+    }
+    std::vector<double> G;
+    std::vector<size_t> goff;
+    if (shared) {
+        G.assign((size_t)keep * 2, 0.0);
+        for (int m = 0; m < keep; ++m)
+            for (int k = 0; k < B; ++k) G[(size_t)m * 2] += w[k] * D[(size_t)m * B + k];
+        goff.push_back(0);
+    } else {
+        for (size_t p = 0; p < in->panel.size(); ++p) {
+            const int W = in->panelW[p], col0 = (int)p * in->stride;
+            goff.push_back(G.size());
+            G.resize(G.size() + (size_t)keep * W, 0.0);
+            double* g = &G[goff.back()];
+            for (int m = 0; m < keep; ++m)
+                for (int c = 0; c < W && col0 + c < B; ++c) g[(size_t)m * W + c] = w[col0 + c] * D[(size_t)m * B + col0 + c];
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);              // d_D reuse
+    if (ctx->d_D_cap < G.size()) {
+        cudaFree(ctx->d_D); ctx->d_D = nullptr; ctx->d_D_cap = 0;
+        KEXP_CUDA(cudaMalloc(&ctx->d_D, sizeof(double) * G.size()));
+        ctx->d_D_cap = G.size();
+    }
+    KEXP_CUDA(cudaMemcpy(ctx->d_D, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice));
+    if (ensure_panels(ctx, 2)) return 1;
+    warm_occupancy<2>(ctx);
+    KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    if (shared) {
+        TimedLaunch tl(ctx, KC_MISC);
+        launch_clenshaw_combine<2>(ctx, in->shared_vec, ctx->d_D, keep, 0);
+    } else {
+        for (size_t p = 0; p < in->panel.size(); ++p) {
+            const int W = in->panelW[p];
+            TimedLaunch tl(ctx, KC_MISC);
+            DISPATCH_W(W, launch_clenshaw_combine<kW>(ctx, in->panel[p], ctx->d_D + goff[p], keep, p > 0));
+        }
+    }
+    KEXP_CUDA(cudaGetLastError());
+    if (set_plan(ctx, plan)) return 1;
+    if (run_clenshaw(ctx, id, plan)) return 1;
+    // the result is column 0 of the buffer written last (M swaps after starting in S0)
+    const double* res = (plan.M % 2 == 0) ? ctx->S0 : ctx->S1;
+    const double one[2] = {1.0, 0.0};
+    if (colsum_panel(ctx, res, one, 0, 2, 2, v_dev, 0)) return 1;
+    KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+    KEXP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
     if (check_ready(ctx, id)) return 1;
     if (in && out && t && in != out && in->B == out->B && in->is_shared && in->shared_vec && ctx->use_shared_basis &&
@@ -1607,6 +1781,51 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
     if (!rc) rc = batch_upload_impl(bi, X, ldx, x_is_shared, false);
     if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
     if (!rc) rc = kexp_batch_average_dev(bo, w, ctx->d_v);
+    if (!rc && do_allreduce) rc = kexp_allreduce_sum_dev(ctx, ctx->d_v, ctx->n);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(v_out, ctx->d_v, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = kexp::fail(ctx, cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+int kexp_cheby_average_fused_dev(kexp_ctx* ctx, int id, kexp_batch* in, const double* t, const double* w, double* v_dev) {
+    if (!ctx) return 1;
+    if (!in || !t || !w || !v_dev) return kexp::fail(ctx, "null argument");
+    std::vector<double> ts, ws;
+    if (!in->order.empty()) {
+        ts.resize((size_t)in->B); ws.resize((size_t)in->B);
+        for (int j = 0; j < in->B; ++j) { ts[j] = t[in->order[j]]; ws[j] = w[in->order[j]]; }
+        t = ts.data(); w = ws.data();
+    }
+    if (cheby_average_fused_impl(ctx, id, in, t, w, v_dev)) return 1;
+    if (ctx->timing) drain_events(ctx);
+    if (!ctx->adaptive_its) return 0;
+    int mx = 0, unc = 0;
+    if (read_cg_counters(ctx, &mx, &unc)) return 1;
+    if (unc > ctx->unconverged_seen && ctx->graph_its < ctx->max_it) {     // same policy as kexp_cheby_apply_dev
+        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 2) : ctx->max_it;
+        ctx->its_tuned = true;
+        ctx->unconverged_seen = unc;
+        invalidate_graphs(ctx);
+        if (cheby_average_fused_impl(ctx, id, in, t, w, v_dev)) return 1;
+        if (ctx->timing) drain_events(ctx);
+        if (read_cg_counters(ctx, &mx, &unc)) return 1;
+    }
+    ctx->unconverged_seen = unc;
+    return 0;
+}
+
+int kexp_cheby_apply_average_fused(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
+                                   const double* t, const double* w, int B, double* v_out, int do_allreduce) {
+    if (check_ready(ctx, id)) return 1;
+    if (!X || !t || !w || !v_out || B < 1) return kexp::fail(ctx, "bad arguments");
+    kexp_batch *bi = nullptr, *bo = nullptr;
+    int rc = scratch_batches(ctx, B, &bi, &bo);
+    if (!rc) rc = finish_upload(bi);
+    if (!rc) { bi->order.clear(); rc = batch_upload_impl(bi, X, ldx, x_is_shared, false); }
+    if (!rc) rc = kexp_cheby_average_fused_dev(ctx, id, bi, t, w, ctx->d_v);
     if (!rc && do_allreduce) rc = kexp_allreduce_sum_dev(ctx, ctx->d_v, ctx->n);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(v_out, ctx->d_v, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);

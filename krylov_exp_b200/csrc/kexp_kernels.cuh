@@ -1266,6 +1266,58 @@ __global__ void pack_kernel(const double* __restrict__ src, int64_t ld, int shar
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Fused weighted average (the adjoint of the shared-input trick above):
+//     v = sum_k w_k exp(t_k L) X_k = sum_k w_k sum_m b_m^(k) S_m(C) X_k = sum_m S_m(C) z_m,
+//     z_m = sum_k w_k b_m^(k) X_k,
+// because after the re-expansion every column is a polynomial in the SAME operator C.  The B input
+// columns are first combined into the M+1 coefficient vectors z_m (clenshaw_combine: a small dense
+// product, one pass over the inputs), then ONE Clenshaw recurrence
+//     u_m = z_m + 2 C u_{m+1} + u_{m+2},      v = z_0 + C u_1 + u_2
+// runs on a single column (basis_axpy adds z_m, the usual operator + update kernels do the rest).
+// The B individual results exp(t_k L) X_k are never formed (timestepping_methods.py:9-11 only uses
+// their weighted sum).
+// ------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+clenshaw_combine_kernel(const double* __restrict__ X, int n, const double* __restrict__ G, int nb,
+                        double* __restrict__ Z, int ld, int accumulate) {
+    extern __shared__ double s_G[];                 // nb x W:  G[m][c] = w_c b_m^(c)
+    pdl_wait();
+    pdl_trigger();
+    for (int i = threadIdx.x; i < nb * W; i += kThreads) s_G[i] = G[i];
+    __syncthreads();
+    constexpr int CH = (W < 16) ? W : 16;           // columns held in registers at a time
+    for (int r = blockIdx.x * kThreads + threadIdx.x; r < n; r += gridDim.x * kThreads) {
+        double* z = Z + (size_t)r * ld;
+#pragma unroll
+        for (int c0 = 0; c0 < W; c0 += CH) {
+            double x[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c += 2) {
+                const double2 v = ld2_stream(X + (size_t)r * W + c0 + c);
+                x[c] = v.x; x[c + 1] = v.y;
+            }
+            for (int m = 0; m < nb; ++m) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) acc = fma(x[c], s_G[m * W + c0 + c], acc);
+                z[m] = (accumulate || c0 > 0) ? z[m] + acc : acc;
+            }
+        }
+    }
+}
+
+// S[:, 0] += Z[:, m]   (column 0 of a panel of width W)
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+basis_axpy_kernel(double* __restrict__ S, int n, const double* __restrict__ Z, int ld, int m) {
+    pdl_wait();
+    pdl_trigger();
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+        S[(size_t)i * W] += Z[(size_t)i * ld + m];
+}
+
 template <int W>
 __global__ void unpack_kernel(const double* __restrict__ src, const int* __restrict__ perm, int n,
                               double* __restrict__ dst, int64_t ld, int B, int col0) {

@@ -114,3 +114,47 @@ def test_device_batch_order(setup):
     with pytest.raises(kx.KexpError):
         bi.set_order(np.zeros(B, dtype=np.int32))
     bi.close(); bo.close()
+
+
+@pytest.mark.parametrize("B", [1, 9, 64, 70])
+@pytest.mark.parametrize("which", ["full", "econ"])
+def test_fused_average_matches_oracle(setup, B, which):
+    """sum_k w_k exp(t_k L) X_k by one Clenshaw recurrence (kexp_cheby_apply_average_fused) = the weighted sum of
+    the oracle's B separate applications (timestepping_methods.py:9-11)."""
+    import krylov_exp_b200 as kx
+    from oracle import cheby_ref
+    sw, op, full, econ, a, L, A, x = setup
+    ce = full if which == "full" else econ
+    t, w = kx.sample_times_weights(B, DT, RHO)
+    X = _inputs(sw, x, B)
+    ref = w @ cheby_ref.apply_batch(a, L, A, X.T, -t).T
+    M = sw.M()
+    v = ce.apply_average(X, -t, w, fused=True)
+    assert _relM(M, v, ref) < 1e-10
+    assert _relM(M, v, ce.apply_average(X, -t, w)) < 1e-11
+    # shared input: (sum_k w_k p_k)(A) x
+    vs = ce.apply_average(x, t, w, shared=True, fused=True)
+    refs = w @ cheby_ref.apply_batch(a, L, A, np.tile(x, (B, 1)).T, t).T
+    assert _relM(M, vs, refs) < 1e-10
+
+
+def test_fused_average_device_batch_with_order(setup):
+    import torch
+    import krylov_exp_b200 as kx
+    sw, op, full, econ, a, L, A, x = setup
+    B = 70
+    t, w = kx.sample_times_weights(B, DT, RHO)
+    X = _inputs(sw, x, B)
+    ref = econ.apply_average(X, -t, w)
+    bi = op.batch(B)
+    bi.set_order(np.argsort(np.abs(t), kind="stable"))
+    bi.upload(X)
+    v = torch.zeros(sw.n, dtype=torch.float64, device="cuda:0")
+    econ.average_dev(bi, -t, w, v.data_ptr())
+    op.synchronize()
+    assert _relM(sw.M(), v.cpu().numpy(), ref) < 1e-11
+    # zero weights / zero times
+    econ.average_dev(bi, np.zeros(B), w, v.data_ptr())
+    op.synchronize()
+    assert _relM(sw.M(), v.cpu().numpy(), w @ X) < 1e-13
+    bi.close()
