@@ -81,10 +81,10 @@ class SampleEnsemble:
         op._check(op.lib.kexp_comm_init(op.ctx, uid.ctypes.data_as(C.c_void_p), self.rank, self.world), "kexp_comm_init")
         self._lib_comm = op
 
-    def averaged_apply(self, cheby, X_local, t_local, w_local, shared=False):
+    def averaged_apply(self, cheby, X_local, t_local, w_local, shared=False, fused=False):
         """sum over ALL ranks and samples of w_k exp(t_k L) X_k  (timestepping_methods.py:9-11)."""
         use_lib = self._lib_comm is cheby.op and self.world > 1
-        v = cheby.apply_average(X_local, t_local, w_local, shared=shared, allreduce=use_lib)
+        v = cheby.apply_average(X_local, t_local, w_local, shared=shared, allreduce=use_lib, fused=fused)
         if not use_lib:
             self.allreduce(v)
         return v

@@ -15,9 +15,12 @@ import numpy as np
 
 
 class AveragedStepper:
-    def __init__(self, cheby, cheby2, slow, expt, wt, dt, ensemble=None):
-        """expt, wt: the LOCAL sample times / weights (all of them on one GPU)."""
+    def __init__(self, cheby, cheby2, slow, expt, wt, dt, ensemble=None, fused=True):
+        """expt, wt: the LOCAL sample times / weights (all of them on one GPU).  fused: the backward half of an
+        averaged evaluation only needs the weighted sum, so it runs as one Clenshaw recurrence
+        (cheby_exp.apply_average(fused=True)); False forms the Mbar backward results first, as the reference does."""
         self.cheby, self.cheby2, self.slow = cheby, cheby2, slow
+        self.fused = bool(fused)
         self.expt = np.ascontiguousarray(expt, dtype=np.float64)
         self.wt = np.ascontiguousarray(wt, dtype=np.float64)
         self.dt = float(dt)
@@ -29,8 +32,8 @@ class AveragedStepper:
         F = self.cheby.apply_batch(U, self.expt, shared=True)
         N = np.ascontiguousarray(self.slow(F))
         if self.ensemble is not None and self.ensemble.world > 1:
-            return self.ensemble.averaged_apply(self.cheby, N, -self.expt, self.wt)
-        return self.cheby.apply_average(N, -self.expt, self.wt)
+            return self.ensemble.averaged_apply(self.cheby, N, -self.expt, self.wt, fused=self.fused)
+        return self.cheby.apply_average(N, -self.expt, self.wt, fused=self.fused)
 
     def exp2(self, X, t):
         """cheby2.apply(X, Y, t): one un-batched exponential."""

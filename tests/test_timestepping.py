@@ -43,7 +43,7 @@ class OracleCheby:
         X = np.repeat(np.asarray(X)[None, :], len(t), axis=0) if shared else np.asarray(X)
         return cheby_ref.apply_batch(self.a, self.L, lambda V: self.A @ V, X.T, np.asarray(t)).T
 
-    def apply_average(self, X, t, w, shared=False):
+    def apply_average(self, X, t, w, shared=False, fused=False):
         return np.asarray(w) @ self.apply_batch(X, t, shared)
 
 
@@ -75,8 +75,10 @@ def test_batched_formulation_matches_reference_ensemble(scheme):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("scheme", SCHEMES)
-def test_gpu_time_step_matches_reference_ensemble(scheme):
+def test_gpu_time_step_matches_reference_ensemble(scheme, fused):
+    """fused=True: backward half of every averaged evaluation as one Clenshaw recurrence; False: Mbar applications."""
     import krylov_exp_b200 as kx
     from krylov_exp_b200.timestepping import AveragedStepper
     g, ts, K, M, nu, ne = _load()
@@ -87,7 +89,7 @@ def test_gpu_time_step_matches_reference_ensemble(scheme):
     cheby = kx.cheby_exp(op, None, None, 10000, 1e-8, Lc)
     cheby2 = kx.cheby_exp(op, None, None, 10000, 1e-8, Lc)
     t, w = kx.sample_times_weights(int(Mbar), dt, rho)
-    st = AveragedStepper(cheby, cheby2, _slow(np.abs(ts["U0"]).max()), t, w, dt)
+    st = AveragedStepper(cheby, cheby2, _slow(np.abs(ts["U0"]).max()), t, w, dt, fused=fused)
     U, U_old = _run(st, ts, scheme)
     ref = ts[f"{scheme}_U"]
     d = U - ref
