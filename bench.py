@@ -200,8 +200,9 @@ def main():
     B = args.samples
     # weak scaling: every rank owns `samples` columns of a window with world*samples samples
     t_all, w_all = kx.sample_times_weights(B * world, DT, RHO)
-    t = np.ascontiguousarray(t_all[rank * B:(rank + 1) * B])
-    w = np.ascontiguousarray(w_all[rank * B:(rank + 1) * B])
+    # cyclic assignment (sample k on rank k mod world): every rank gets the same mix of |t_k|, i.e. of series lengths
+    t = np.ascontiguousarray(t_all[rank::world])
+    w = np.ascontiguousarray(w_all[rank::world])
 
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, device=local_rank, condense=not args.no_condense,
                      rtol=args.cg_rtol, max_it=args.max_it, solver=args.solver)
@@ -431,7 +432,7 @@ def main():
                              "figure is effective (algorithmic) bandwidth",
                        "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi {'Chebyshev iteration' if args.solver == 'chebyshev' else 'PCG'} rtol {args.cg_rtol:g}, "
                                      f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}",
-                       "parallelism": f"samples sharded, {B}/GPU", "panels_per_batch": b_bwd_in.num_panels,
+                       "parallelism": f"samples sharded cyclically (sample k on rank k mod N), {B}/GPU", "panels_per_batch": b_bwd_in.num_panels,
                        "forward_batch": "shared input: recurrence for one column at max|t_k| + dense re-expansion to the 64 "
                                         "sample times (exact, DESIGN.md); value_independent_columns = same step without it",
                        "series": ("full reference series for every column" if args.full_series else

@@ -21,7 +21,10 @@ def block_partition(Mbar, world):
 
 
 class SampleEnsemble:
-    def __init__(self, Mbar, rank=None, world=None):
+    def __init__(self, Mbar, rank=None, world=None, partition="block"):
+        """partition: "block" (contiguous sample blocks per rank) or "cyclic" (sample k on rank k mod world).
+        With the economised series the cost of a sample grows with |t_k|, and the sample times are ordered, so
+        "cyclic" gives every rank the same mix of short and long series (balanced max-over-ranks time)."""
         try:
             import torch.distributed as dist
             self._dist = dist if dist.is_available() and dist.is_initialized() else None
@@ -32,16 +35,21 @@ class SampleEnsemble:
         if world is None:
             world = self._dist.get_world_size() if self._dist else 1
         self.Mbar, self.rank, self.world = int(Mbar), int(rank), int(world)
+        if partition not in ("block", "cyclic"):
+            raise ValueError("partition must be 'block' or 'cyclic'")
+        self.partition = partition
         self.offsets = block_partition(self.Mbar, self.world)
         self._lib_comm = None
 
     @property
     def local_slice(self):
+        if self.partition == "cyclic":
+            return slice(self.rank, self.Mbar, self.world)
         return slice(int(self.offsets[self.rank]), int(self.offsets[self.rank + 1]))
 
     @property
     def n_local(self):
-        return int(self.offsets[self.rank + 1] - self.offsets[self.rank])
+        return len(range(*self.local_slice.indices(self.Mbar)))
 
     def local_times_weights(self, dt, rho):
         t, w = sample_times_weights(self.Mbar, dt, rho)

@@ -54,6 +54,14 @@ def test_block_partition():
     t, w = e.local_times_weights(900.0, 1.0)
     tt, ww = kx.sample_times_weights(9, 900.0, 1.0)
     assert np.array_equal(t, tt[e.local_slice]) and np.array_equal(w, ww[e.local_slice])
+    # cyclic partition: every sample exactly once, |t| mix balanced across ranks
+    seen = np.zeros(9, dtype=int)
+    for r in range(4):
+        c = kx.SampleEnsemble(9, rank=r, world=4, partition="cyclic")
+        seen[c.local_slice] += 1
+        assert c.n_local == len(tt[c.local_slice])
+        assert np.array_equal(c.local_times_weights(900.0, 1.0)[0], tt[r::4])
+    assert np.all(seen == 1)
 
 
 def test_static_condensation_is_exact(sw2):
