@@ -19,6 +19,13 @@
 namespace kexp {
 
 constexpr int kThreads = 256;
+// A/B switches of the cooperative mass solve (defaults = measured best, profiles/r01e_summary.md)
+#ifndef KEXP_GRID_FENCE
+#define KEXP_GRID_FENCE 0      // 1: every thread fences again after grid.sync() (redundant: the barrier's own fence invalidates L1)
+#endif
+#ifndef KEXP_COOP_PREFETCH
+#define KEXP_COOP_PREFETCH 1   // 1: prefetch b / x_{k-1} rows into L1 and load them after the gather (no spills); 0: load them first
+#endif
 constexpr int kMaxW = 64;
 constexpr int kMaxTerms = 1024;                       // rows of the per-panel coefficient table (terms 0..1023)
 constexpr int kPinWeights = kMaxW * (1 + kMaxTerms);  // offset of the averaging weights in the pinned staging buffer
@@ -52,6 +59,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+__device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // streaming variant: vectors that are touched once per kernel should not displace the
 // gathered rows / matrix blocks in L1
 __device__ __forceinline__ double2 ld2_stream(const double* p) {
@@ -592,7 +600,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
         }
     }
     grid.sync();
-    __threadfence();
+    if (KEXP_GRID_FENCE) __threadfence();
     double omega = 1.0;
     for (int it = 1; it < K; ++it) {
         omega = (it == 1) ? 1.0 / (1.0 - 0.5 * mu * mu) : 1.0 / (1.0 - 0.25 * mu * mu * omega);
@@ -607,8 +615,13 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     if (!diag_first) xo[i] = ld2(xk + o + (size_t)i * W);
-                    bv[i] = ld2(Bv + o + (size_t)i * W);
-                    xmv[i] = ld2(xm + o + (size_t)i * W);
+                    if (KEXP_COOP_PREFETCH) {              // needed only after the gather: keep the registers free
+                        prefetch_l1(Bv + o + (size_t)i * W);
+                        prefetch_l1(xm + o + (size_t)i * W);
+                    } else {
+                        bv[i] = ld2(Bv + o + (size_t)i * W);
+                        xmv[i] = ld2(xm + o + (size_t)i * W);
+                    }
                 }
                 for (int kg = k0; kg < k1; kg += GB) {
                     double2 x[GB][3];
@@ -641,6 +654,13 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                         }
                     }
                 }
+                if (KEXP_COOP_PREFETCH) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        bv[i] = ld2(Bv + o + (size_t)i * W);
+                        xmv[i] = ld2(xm + o + (size_t)i * W);
+                    }
+                }
                 double2 rv[3];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -661,7 +681,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
         }
         if (!last) {
             grid.sync();
-            __threadfence();
+            if (KEXP_GRID_FENCE) __threadfence();
         }
         double* tsw = xk; xk = xm; xm = tsw;
     }
