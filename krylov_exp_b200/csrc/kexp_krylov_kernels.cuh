@@ -416,8 +416,7 @@ __device__ inline void bicg_smem_sums(cg::grid_group& grid, double (&v)[NV], dou
         for (int w = 0; w < NW; ++w) s += sh[threadIdx.x * NW + w];
         __stcg(slot + (size_t)blockIdx.x * 4 + threadIdx.x, s);
     }
-    grid.sync();
-    __threadfence();
+    grid.sync();                                   // its fence invalidates L1: later plain loads see the other CTAs' stores
     if (warp < NV) {
         double s = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(slot + (size_t)b * 4 + warp);
@@ -542,7 +541,6 @@ bicgstab_smem_kernel(BicgSmemArgs a) {
             }
             have_update = false;
             grid.sync();
-            __threadfence();
             double red_a[1] = {0.0};
             if (active) {
                 bicg_smem_row(sv, sc, my_slot, width, lane, a.y, v);
