@@ -41,6 +41,16 @@ def main():
     e1, e2 = rel(v1, ref), rel(v2, ref)
     print(f"rank {rank}/{world}: local samples {ens.n_local}, torch-nccl {e1:.2e}, lib-nccl {e2:.2e}", flush=True)
     assert e1 < 1e-12 and e2 < 1e-12
+    # (3) cyclic partition, economised series, fused Clenshaw average with the library's all-reduce
+    ce.set_spectral_radius(kx.EIGS[0])
+    cyc = kx.SampleEnsemble(Mbar, partition="cyclic")
+    cyc._lib_comm = ens._lib_comm
+    tc, wc = cyc.local_times_weights(dt, rho)
+    v3 = cyc.averaged_apply(ce, X[cyc.local_slice], -tc, wc, fused=True)
+    v4 = cyc.averaged_apply(ce, X[cyc.local_slice], -tc, wc, fused=False)
+    e3, e4 = rel(v3, ref), rel(v4, ref)
+    print(f"rank {rank}/{world}: cyclic/economised fused {e3:.2e}, separate {e4:.2e}", flush=True)
+    assert e3 < 1e-11 and e4 < 1e-11
     dist.barrier()
     op.close()
     dist.destroy_process_group()

@@ -158,3 +158,28 @@ def test_fused_average_device_batch_with_order(setup):
     op.synchronize()
     assert _relM(sw.M(), v.cpu().numpy(), w @ X) < 1e-13
     bi.close()
+
+
+def test_economised_edge_times(setup):
+    """t = 0 (series of length 1), a mix of zero / tiny / maximal sample times in one panel, and B = 1."""
+    from oracle import cheby_ref
+    sw, op, full, econ, a, L, A, x = setup
+    M = sw.M()
+    y = np.empty(sw.n)
+    econ.apply(x, y, 0.0)
+    assert _relM(M, y, x) < 1e-14
+    tmax = DT * RHO / 1.01 * 0.999                                  # just inside the stated range
+    t = np.array([0.0, 1e-9, -1e-3, 17.0, -tmax, tmax, 0.5 * tmax])
+    X = _inputs(sw, x, len(t))
+    Y = econ.apply_batch(X, t)
+    ref = cheby_ref.apply_batch(a, L, A, X.T, t).T
+    assert max(_relM(M, Y[k], ref[k]) for k in range(len(t))) < 1e-10
+    econ.apply(X[4], y, float(t[4]))
+    assert _relM(M, y, ref[4]) < 1e-10
+    # switching the range off again restores the full series
+    econ.set_spectral_radius(None)
+    op.stats_reset()
+    econ.apply(X[3], y, float(t[3]))
+    assert op.stats()["op_applications"] % econ.ncheb == 0 and _relM(M, y, ref[3]) < 1e-10
+    import krylov_exp_b200 as kx
+    econ.set_spectral_radius(kx.EIGS[0])
