@@ -850,7 +850,6 @@ int kexp_destroy(kexp_ctx* ctx) {
                       ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_v, ctx->d_basis, ctx->d_D};
     for (double* b : bufs) cudaFree(b);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sc); cudaFree(ctx->d_counter);
-    for (int i = 0; i < KEXP_MAX_CHEBY; ++i) cudaFree(ctx->cheb[i].d_coef);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1047,9 +1046,6 @@ int kexp_set_cheby(kexp_ctx* ctx, int id, const double* a, int ncheb, double L) 
     if (ncheb >= kMaxTerms) return kexp::fail(ctx, "Chebyshev series too long (ncheb must be below 1024)");
     invalidate_graphs(ctx);
     ChebTable& tb = ctx->cheb[id];
-    cudaFree(tb.d_coef); tb.d_coef = nullptr;
-    KEXP_CUDA(cudaMalloc(&tb.d_coef, sizeof(double) * (size_t)(ncheb + 1)));
-    KEXP_CUDA(cudaMemcpy(tb.d_coef, a, sizeof(double) * (size_t)(ncheb + 1), cudaMemcpyHostToDevice));
     tb.ncheb = ncheb; tb.L = L; tb.t_valid = 0.0;
     ctx->plan_cache.clear();
     tb.h_coef.assign(a, a + ncheb + 1);

@@ -52,8 +52,7 @@ struct ClassStat {
 struct ChebTable {
     int ncheb = -1;
     double L = 0.0;
-    double* d_coef = nullptr;      // ncheb+1 doubles
-    std::vector<double> h_coef;    // host copy (shared-input expansion coefficients)
+    std::vector<double> h_coef;    // a_n, n = 0..ncheb (panel plans and re-expansions are built from it on the host)
     std::vector<double> h_relax;   // per-term tolerance relaxation factor of the mass solve (>= 1)
     double t_valid = 0.0;          // largest |t| the series is valid for (L / spectral radius); 0 = unknown
 };
