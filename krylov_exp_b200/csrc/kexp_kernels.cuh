@@ -24,7 +24,8 @@ constexpr int kThreads = 256;
 #define KEXP_GRID_FENCE 0      // 1: every thread fences again after grid.sync() (redundant: the barrier's own fence invalidates L1)
 #endif
 #ifndef KEXP_COOP_PREFETCH
-#define KEXP_COOP_PREFETCH 1   // 1: prefetch b / x_{k-1} rows into L1 and load them after the gather (no spills); 0: load them first
+#define KEXP_COOP_PREFETCH 16  // panels at least this wide prefetch b / x_{k-1} rows into L1 and load them after the gather (no
+                               // spills); narrower (latency-bound) panels and 0 load them first
 #endif
 constexpr int kMaxW = 64;
 constexpr int kMaxTerms = 1024;                       // rows of the per-panel coefficient table (terms 0..1023)
@@ -557,6 +558,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
     namespace cg = cooperative_groups;
     using C = PanelCfg<W, kSpmmCpt>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
+    constexpr bool kPrefetch = (KEXP_COOP_PREFETCH > 0) && (W >= KEXP_COOP_PREFETCH);
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double2 sblk[];
     double* sP = reinterpret_cast<double*>(sblk + 5 * kSpmmSmemBlocks);
@@ -615,7 +617,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     if (!diag_first) xo[i] = ld2(xk + o + (size_t)i * W);
-                    if (KEXP_COOP_PREFETCH) {              // needed only after the gather: keep the registers free
+                    if (kPrefetch) {                       // needed only after the gather: keep the registers free
                         prefetch_l1(Bv + o + (size_t)i * W);
                         prefetch_l1(xm + o + (size_t)i * W);
                     } else {
@@ -654,7 +656,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                         }
                     }
                 }
-                if (KEXP_COOP_PREFETCH) {
+                if (kPrefetch) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         bv[i] = ld2(Bv + o + (size_t)i * W);
