@@ -113,6 +113,12 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
 int kexp_cheby_apply_average_fused(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
                                    const double* t, const double* w, int B, double* v_out, int do_allreduce);
 
+/* Host-only (no device needed): b = E(s)^T a with  sum_n a_n S_n(s z) = sum_m b_m S_m(z),  |s| <= 1, S_0 = 1, S_1 = z,
+ * S_n = 2 z S_{n-1} + S_{n-2} (the real form of cheby_exp.py:110-165), and the number of leading b_m to keep for a
+ * dropped tail <= eps * sum|b_m|.  This is the coefficient algebra behind kexp_set_cheby_time_range, the shared-input
+ * batches and kexp_cheby_apply_average_fused.  b_out: ncheb+1 doubles. */
+int kexp_series_reexpand(const double* a, int ncheb, double s, double eps, double* b_out, int* keep_out);
+
 /* ---- device-resident batches (the hot loop without host<->device copies) ---------- */
 typedef struct kexp_batch kexp_batch;
 int kexp_batch_create(kexp_ctx* ctx, int B, kexp_batch** out);
@@ -121,7 +127,7 @@ int kexp_batch_num_panels(kexp_batch* b);     /* a batch is stored as panels of 
 /* Column order inside the batch: stored column j holds the caller's column order[j] (a permutation of
  * 0..B-1; NULL = identity).  Upload, download, the sample times t and the weights w of the calls below
  * always use the CALLER's order.  Sorting by |t_k| puts sample times of similar series length into one
- * panel; the host-array entry points above do so themselves. */
+ * panel; the host-array entry points above do so themselves.  Set the order BEFORE uploading. */
 int kexp_batch_set_order(kexp_batch* b, const int32_t* order);
 int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared);   /* host -> HBM */
 int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy);                        /* HBM -> host */

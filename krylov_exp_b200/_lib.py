@@ -37,6 +37,7 @@ PROTOTYPES = {
     "kexp_set_mass_solver_chebyshev": (C.c_int, [_p, C.c_double, C.c_double, C.c_double, C.c_int]),
     "kexp_set_cheby": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_double]),
     "kexp_set_cheby_time_range": (C.c_int, [_p, C.c_int, C.c_double]),
+    "kexp_series_reexpand": (C.c_int, [_p, C.c_int, C.c_double, C.c_double, _p, C.POINTER(C.c_int)]),
     "kexp_cheby_apply": (C.c_int, [_p, C.c_int, _p, _p, C.c_double]),
     "kexp_cheby_apply_batch": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, C.c_int]),
     "kexp_cheby_apply_average": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, _p, C.c_int, _p, C.c_int]),

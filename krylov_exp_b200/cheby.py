@@ -64,6 +64,18 @@ def real_table(coeffs, n):
     return np.ascontiguousarray(np.real(coeffs[:n + 1] * (-1j) ** k))
 
 
+def reexpand_series(a, s, eps=1e-13):
+    """b with sum_n a_n S_n(s z) = sum_m b_m S_m(z) (|s| <= 1) and the truncated length for a dropped tail
+    <= eps*sum|b|: the library's own host routine (kexp_series_reexpand), no GPU involved."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.empty_like(a)
+    keep = C.c_int(0)
+    rc = _lib.load().kexp_series_reexpand(_lib.ptr(a), a.shape[0] - 1, float(s), float(eps), _lib.ptr(b), C.byref(keep))
+    if rc != 0:
+        raise ValueError("kexp_series_reexpand: need |s| <= 1")
+    return b, int(keep.value)
+
+
 class cheby_exp(object):
     def __init__(self, operator_solver, operator_in, operator_out,
                  ncheb, tol, L, filter=False, filter_val=0.75, filter_freq=False, *, spectral_radius=None):

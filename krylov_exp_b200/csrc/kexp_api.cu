@@ -1786,6 +1786,17 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
     return rc;
 }
 
+// Host-only helper (no device, no context): the re-expansion  sum_n a_n S_n(s z) = sum_m b_m S_m(z)  used by the
+// economised series, the shared-input basis and the fused average, and the number of leading coefficients kept
+// for a dropped tail <= eps * sum|b_m|.  Exposed so that the coefficient algebra can be checked on a CPU.
+int kexp_series_reexpand(const double* a, int ncheb, double s, double eps, double* b_out, int* keep_out) {
+    if (!a || !b_out || ncheb < 0 || !(std::fabs(s) <= 1.0)) return 1;
+    std::vector<double> av(a, a + ncheb + 1);
+    expansion_column(av, s, b_out, 1);
+    if (keep_out) *keep_out = truncated_length(b_out, ncheb + 1, 1, eps > 0.0 ? eps : 0.0);
+    return 0;
+}
+
 int kexp_cheby_average_fused_dev(kexp_ctx* ctx, int id, kexp_batch* in, const double* t, const double* w, double* v_dev) {
     if (!ctx) return 1;
     if (!in || !t || !w || !v_dev) return kexp::fail(ctx, "null argument");

@@ -172,3 +172,31 @@ def test_no_cpu_fallback():
     for fn in os.listdir(os.path.join(ROOT, "krylov_exp_b200")):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(ROOT, "krylov_exp_b200", fn)).read().replace("the oracle re-exports", "").replace("CPU oracle", "") or fn == "assembly.py"
+
+
+def test_series_reexpansion_against_numpy_chebyshev():
+    """The coefficient algebra of the economised series / shared-input basis / fused average (host routine of
+    libkexp.so, no GPU): on the spectrum z = i*mu the real recurrence is S_n(i mu) = i^n T_n(mu), so
+    sum_n a_n S_n(s z) = sum_m b_m S_m(z) means f(mu) = sum_n a_n i^n T_n(s mu) has Chebyshev coefficients b_m i^m."""
+    from numpy.polynomial import chebyshev as Ch
+    from krylov_exp_b200.cheby import reexpand_series
+    from oracle import coeffs
+    L = kx.EIGS[2] * 900.0
+    c, n = coeffs.cheby_coeffs(10000, 1e-8, L)
+    a = coeffs.real_recurrence_coeffs(c, n)
+    fac = 1j ** np.arange(n + 1)
+    mu = np.cos(np.pi * (np.arange(4 * n) + 0.5) / (4 * n))
+    for s in (1.0, 0.505, -0.505, 0.25, -0.01, 0.0):
+        b, keep = reexpand_series(a, s, 1e-13)
+        f = Ch.chebval(s * mu, a * fac)                       # the reference polynomial on the scaled spectrum
+        g = Ch.chebval(mu, b * fac)                           # its re-expansion
+        assert np.abs(f - g).max() < 5e-15 * max(1.0, np.abs(f).max()), s
+        g_cut = Ch.chebval(mu, (b * fac)[:keep])
+        tail = np.abs(b[keep:]).sum()
+        assert tail <= 1e-13 * np.abs(b).sum() and np.abs(f - g_cut).max() <= tail + 5e-15, s
+        if abs(s) < 1:
+            assert keep < n + 1                               # shorter than the reference series
+    assert reexpand_series(a, 1.0, 0.0)[1] == n + 1 and np.allclose(reexpand_series(a, 1.0)[0], a, rtol=0, atol=1e-16)
+    assert reexpand_series(a, 0.0)[1] == 1 and abs(reexpand_series(a, 0.0)[0][0] - 1.0) < 1e-12   # series is 1 at A = 0
+    with pytest.raises(ValueError):
+        reexpand_series(a, 1.5)
