@@ -324,6 +324,10 @@ int ensure_stage(kexp_ctx* ctx, size_t bytes) {
 #define KEXP_GB 5
 #endif
 constexpr int kSpmmGB = KEXP_GB;                 // gathered blocks in flight per block row
+#ifndef KEXP_GB0
+#define KEXP_GB0 3
+#endif
+constexpr int kSpmm0GB = KEXP_GB0;               // the same for the plain product T = K~ S
 constexpr int kCptVec = 2;                  // sample columns per thread in the streaming vector kernels
 
 template <int W, int MODE>
@@ -341,7 +345,7 @@ void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
         return;
     }
     if (A.bsr()) {
-        auto k = bsr3_spmm_kernel<W, MODE, kSpmmGB>;
+        auto k = bsr3_spmm_kernel<W, MODE, (MODE == 0 ? kSpmm0GB : kSpmmGB)>;
         constexpr int per_cta = PanelCfg<W, kSpmmCpt>::BPC;
         int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
         launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, X, Y, A.nbr, A.max_bpr, ctx->T, ctx->d_Pinv,
@@ -608,7 +612,7 @@ void invalidate_graphs(kexp_ctx* ctx) {
 template <int W>
 void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, csr_spmm_kernel<W>);
-    max_grid(ctx, bsr3_spmm_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_spmm_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
+    max_grid(ctx, bsr3_spmm_kernel<W, 0, kSpmm0GB>, kSpmmSmemBytes); max_grid(ctx, bsr3_spmm_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cg_init_kernel<W, kCptVec>); max_grid(ctx, cg_update_kernel<W, kCptVec>);
     max_grid(ctx, cheb_solve_init_kernel<W, kCptVec>);
     max_grid(ctx, cheb_solve_coop_kernel<W, kSpmmGB>, kSpmmSmemBytes);

@@ -278,11 +278,15 @@ constexpr int kSpmmSmemRows = 128;        // block rows per staged sub-chunk (ro
 constexpr int kSpmmSmemBytes = kSpmmSmemBlocks * 80 + kSpmmSmemRows * 72 + (kSpmmSmemRows + 4) * 4;
 constexpr int kSpmmCpt = 2;               // PanelCfg CPTMAX of the SpMM (one double2 per lane)
 
+#ifndef KEXP_SPMM0_MINB
+#define KEXP_SPMM0_MINB 3      // resident CTAs per SM the plain product (MODE 0, T = K~ S) is compiled for: with 3 gathered
+                               // blocks in flight (KEXP_GB0) it fits 80 registers; 59 -> 52 us per 32-column launch at ref 5
+#endif
 #ifndef KEXP_SPMM_MINB
 #define KEXP_SPMM_MINB 2
 #endif
 template <int W, int MODE, int GB>
-__global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
+__global__ void __launch_bounds__(kThreads, (MODE == 0 ? KEXP_SPMM0_MINB : KEXP_SPMM_MINB))
 bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                  const double* __restrict__ X, double* __restrict__ Y, int nbr, int max_bpr,
                  const double* __restrict__ R, const double* __restrict__ Pinv, const int* __restrict__ rowmap,
