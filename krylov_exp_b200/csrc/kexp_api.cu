@@ -320,8 +320,11 @@ int ensure_stage(kexp_ctx* ctx, size_t bytes) {
 
 // Y = A X (MODE 0) or the CG product q = A p with the fused p.q reduction (MODE 1); BSR(3x3)
 // kernel when the matrix has that structure, generic CSR kernel otherwise.
+// Measured on the bench step (profiles/r01e_summary.md): 1 -> 5990, 2 -> 5810, 3 -> 5930, 4 -> 5590, 5 -> 5380 applications/s.
+// Explicit gather-ahead costs registers (spills at 5) and buys nothing: the compiler's own schedule of the
+// five-block row with one block per group is the fastest.
 #ifndef KEXP_GB
-#define KEXP_GB 5
+#define KEXP_GB 1
 #endif
 constexpr int kSpmmGB = KEXP_GB;                 // gathered blocks in flight per block row
 #ifndef KEXP_GB0
