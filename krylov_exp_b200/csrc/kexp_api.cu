@@ -366,7 +366,6 @@ void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
 template <int W>
 void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
     constexpr int LPB = PanelCfg<W, kCptVec>::LPB;
-    cudaStream_t s = ctx->stream;
     const int ns = (int)ctx->n_s;
     const int red_grid = ctx->red_blocks_per_sm * ctx->num_sms;   // reduction kernels: few, fat blocks keep the last-block sum short
     {   // T = Kt * in
@@ -471,7 +470,6 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
 template <int W>
 void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep st) {
     constexpr int LPR = W / 2;
-    cudaStream_t s = ctx->stream;
     const int ns = (int)ctx->n_s, nb = (int)ctx->n_b, nd = (int)ctx->n_d;
     ChebStep st2 = st;
     st2.check_cg = 0;

@@ -676,13 +676,11 @@ __device__ inline void dn_expm(double* A, double* E, double* scratch, int m) {
     const double b[14] = {64764752532480000.0, 32382376266240000.0, 7771770303897600.0, 1187353796428800.0,
                           129060195264000.0, 10559470521600.0, 670442572800.0, 33522128640.0, 1323241920.0,
                           40840800.0, 960960.0, 16380.0, 182.0, 1.0};
-    __shared__ double s_norm;
     __shared__ int s_s;
     double *A2 = scratch, *A4 = A2 + m * m, *A6 = A4 + m * m, *U = A6 + m * m, *V = U + m * m, *T1 = V + m * m, *T2 = T1 + m * m;
     if (threadIdx.x == 0) {
         double nrm = 0.0;
         for (int j = 0; j < m; ++j) { double c = 0.0; for (int i = 0; i < m; ++i) c += fabs(A[i * m + j]); nrm = fmax(nrm, c); }
-        s_norm = nrm;
         int s = 0;
         const double theta13 = 5.371920351148152;
         if (nrm > theta13) s = (int)ceil(log2(nrm / theta13));
