@@ -90,3 +90,39 @@ def test_krylov_restatement(golden):
     y12, _, _, _ = krylov_ref.krylov_apply(lambda v: Sinv @ v, lambda v: A @ v, lambda a, b: a @ (Md @ b),
                                            g["x1"], tk, gamma, kdim, its=12)
     assert np.linalg.norm(y12 - g["krylov_its12_y"]) <= 1e-13 * np.linalg.norm(y12)
+
+
+def test_exact_rewritings_on_the_cpu(sw2):
+    """The three rewritings the GPU path relies on, restated in NumPy and checked against the reference recurrence
+    (apply_batch, itself pinned by the golden vectors above): re-expansion onto a common operator, per-column
+    economised series, and the weighted average as one Clenshaw recurrence."""
+    from oracle import cheby_ref, coeffs, samples
+    from oracle.assemble_sw import test_pulse
+    from scipy.sparse.linalg import splu
+    sw = sw2
+    lu = splu(sw.M().tocsc())
+    A = lambda V: lu.solve(sw.K @ V)
+    eig, dt, rho, B = 0.0018, 3600.0, 6.0, 12                   # ref 2: largest |eig| ~ 1.7e-3
+    L = eig * dt * rho
+    c, n = coeffs.cheby_coeffs(10000, 1e-8, L)
+    a = coeffs.real_recurrence_coeffs(c, n)
+    t, w = samples.sample_times_weights(B, dt, rho)
+    x = test_pulse(sw)
+    rng = np.random.default_rng(3)
+    X = x[:, None] * (1 + 0.1 * np.arange(B))[None, :] + 1e-3 * np.abs(x).max() * rng.standard_normal((sw.n, B))
+    ref = cheby_ref.apply_batch(a, L, A, X, -t)
+    M = sw.M()
+    rel = lambda p, q: np.sqrt(((p - q) @ (M @ (p - q))) / (q @ (M @ q)))
+    Ye, Me = cheby_ref.apply_batch_economised(a, L, A, X, -t, t_valid=dt * rho)
+    assert Me < n and max(rel(Ye[:, k], ref[:, k]) for k in range(B)) < 1e-12
+    v, Mc = cheby_ref.average_clenshaw(a, L, A, X, -t, w)
+    assert rel(v, ref @ w) < 1e-12
+    # shared input: the forward half, all columns from one basis
+    tstar = np.abs(t).max()
+    S = [x, (tstar / L) * A(x)]
+    for m in range(2, n + 1):
+        S.append(2.0 * (tstar / L) * A(S[-1]) + S[-2])
+    S = np.array(S).T                                            # N x (n+1): U_m = S_m((t*/L) A) x
+    F = cheby_ref.apply_batch(a, L, A, np.repeat(x[:, None], B, axis=1), t)
+    for k in range(B):
+        assert rel(S @ cheby_ref.reexpand(a, t[k] / tstar), F[:, k]) < 1e-12
