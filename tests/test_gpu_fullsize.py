@@ -92,3 +92,22 @@ def test_ref5_batch_composition_independence(setup5):
     assert _relM(M, y1, Y[11]) < 1e-11
     Y9 = ce.apply_batch(X[:9], -t[:9])                     # natural Mbar of the qjrms setup
     assert _relM(M, Y9[3], Y[3]) < 1e-11
+
+
+def test_ref5_full_series_equals_economised(setup5):
+    """The reference's full 29-term series for every column (no stated spectral bound) against the per-column
+    economised expansions, all 64 sample times at full size; and the fused Clenshaw average against both."""
+    import krylov_exp_b200 as kx
+    sw, op, ce, L, t, w, x, X = setup5
+    M = sw.M()
+    full = kx.cheby_exp(op, None, None, 10000, 1e-8, L)
+    op.stats_reset()
+    Yf = full.apply_batch(X, -t)
+    apps_full = op.stats()["op_applications"]
+    op.stats_reset()
+    Ye = ce.apply_batch(X, -t)
+    apps_econ = op.stats()["op_applications"]
+    assert apps_econ < apps_full
+    assert max(_relM(M, Ye[k], Yf[k]) for k in range(0, 64, 5)) < 1e-11
+    v = ce.apply_average(X, -t, w, fused=True)
+    assert _relM(M, v, w @ Yf) < 1e-11
