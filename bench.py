@@ -408,7 +408,8 @@ def main():
         if os.path.exists(traffic_file):
             try:
                 roofline["traffic"] = json.load(open(traffic_file)).get(dom)
-                roofline["note"] = ("traffic = ncu dram bytes per launch (profiles/r01d_summary.md): the 32-column panel of the mass "
+                roofline["note"] = ("traffic = ncu dram bytes per launch (profiles/r01e_summary.md, captured at K = 33 iterations: first read of b and last write of x, "
+                                    "it does not grow with K): the 32-column panel of the mass "
                                     "solve is L2 resident, so `achieved` is effective (algorithmic) bandwidth, not HBM traffic")
             except Exception:
                 pass
@@ -433,7 +434,7 @@ def main():
                        "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi {'Chebyshev iteration' if args.solver == 'chebyshev' else 'PCG'} rtol {args.cg_rtol:g}, "
                                      f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}",
                        "parallelism": f"samples sharded cyclically (sample k on rank k mod N), {B}/GPU", "panels_per_batch": b_bwd_in.num_panels,
-                       "forward_batch": "shared input: recurrence for one column at max|t_k| + dense re-expansion to the 64 "
+                       "forward_batch": "shared input: recurrence for ONE column on the common operator + dense re-expansion to the 64 "
                                         "sample times (exact, DESIGN.md); value_independent_columns = same step without it",
                        "series": ("full reference series for every column" if args.full_series else
                                   "per-column economised re-expansion of the reference series (same polynomial, dropped tail "
