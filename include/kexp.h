@@ -40,6 +40,10 @@ typedef struct kexp_stats_t {
     double  model_bytes;       /* algorithmic DRAM bytes of the work since last reset (DESIGN.md model) */
     double  spmm_cg_bytes;     /* of which: bytes of the CG-loop SpMM launches */
     int64_t spmm_cg_launches;  /* number of CG-loop SpMM launches since last reset */
+    int64_t unconverged_solves;    /* mass solves that missed their tolerance since the context was created (each one made
+                                      its apply repeat itself with more iterations, or fail at max_it) */
+    double  worst_rel_residual;    /* largest ||r||/||b|| of any such solve */
+    int64_t mass_iterations_per_solve; /* current fixed length of a Chebyshev mass solve / cap of a PCG solve */
 } kexp_stats_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -74,7 +78,8 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
 
 /* fieldsplit_0 CG of averaged_sw_explicit.py:155-157: relative residual tolerance,
  * iteration cap (the whole apply is one CUDA graph with max_it early-exit iterations),
- * precond: 1 = point Jacobi, 3 = 3x3 block Jacobi. */
+ * precond: 1 = point Jacobi, 3 = 3x3 block Jacobi.  A solve that misses rtol within max_it makes the calling apply
+ * FAIL ("mass solve did not reach rtol"); rtol below 2e-14 is clamped to 2e-14 (attainable accuracy in fp64). */
 int kexp_set_mass_solver(kexp_ctx* ctx, double rtol, int max_it, int precond);
 /* Same solve by Chebyshev semi-iteration on the block-Jacobi preconditioned system: spectrum of
  * P^-1 S enclosed by [lmin, lmax] (host estimate); no inner products, one fused kernel per
@@ -137,6 +142,12 @@ int kexp_cheby_average_fused_dev(kexp_ctx* ctx, int id, kexp_batch* in, const do
 /* v_dev: device pointer to n doubles (e.g. a torch tensor's data_ptr), user dof order */
 int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev);
 int kexp_synchronize(kexp_ctx* ctx);
+/* on != 0: kexp_cheby_apply_dev / kexp_cheby_average_fused_dev return as soon as their work is enqueued (no host
+ * synchronisation once the iteration count is tuned), so applies queue back to back and overlap with uploads.  The
+ * convergence record of the mass solves is then inspected by a later call; a solve that missed rtol is reported as an
+ * error by that call, at the latest by kexp_synchronize / kexp_batch_download / kexp_stats.  Default off: every apply
+ * checks (and if needed repeats) itself before returning. */
+int kexp_set_async(kexp_ctx* ctx, int on);
 /* ms of device time between the start and end of the last *_dev / apply call (CUDA events) */
 int kexp_last_device_ms(kexp_ctx* ctx, double* ms);
 /* CUDA events on the library's stream around an arbitrary sequence of calls */

@@ -18,7 +18,9 @@ class Stats(C.Structure):
                 ("cg_iterations", C.c_int64), ("op_applications", C.c_int64),
                 ("kernel_launches", C.c_int64), ("bicg_iterations", C.c_int64),
                 ("last_max_rel_residual", C.c_double), ("model_bytes", C.c_double),
-                ("spmm_cg_bytes", C.c_double), ("spmm_cg_launches", C.c_int64)]
+                ("spmm_cg_bytes", C.c_double), ("spmm_cg_launches", C.c_int64),
+                ("unconverged_solves", C.c_int64), ("worst_rel_residual", C.c_double),
+                ("mass_iterations_per_solve", C.c_int64)]
 
 
 _p = C.c_void_p
@@ -52,6 +54,7 @@ PROTOTYPES = {
     "kexp_batch_average_dev": (C.c_int, [_p, _p, _p]),
     "kexp_cheby_average_fused_dev": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),
     "kexp_synchronize": (C.c_int, [_p]),
+    "kexp_set_async": (C.c_int, [_p, C.c_int]),
     "kexp_timer_start": (C.c_int, [_p]),
     "kexp_timer_stop": (C.c_int, [_p, C.POINTER(C.c_double)]),
     "kexp_last_device_ms": (C.c_int, [_p, C.POINTER(C.c_double)]),

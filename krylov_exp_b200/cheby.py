@@ -112,7 +112,9 @@ class cheby_exp(object):
         """y <- exp(t M^-1 K) x   (cheby_exp.py:110-165).  x is left unchanged, x is not y."""
         if x is y:
             raise ValueError("x and y must be different (cheby_exp.py:119 zeroes y before reading x)")
-        xin = np.ascontiguousarray(as_array(x), dtype=np.float64)
+        xin = np.ascontiguousarray(as_array(x), dtype=np.float64).reshape(-1)
+        if xin.shape[0] != self.op.n:
+            raise ValueError(f"x must hold n = {self.op.n} values, got {xin.shape[0]}")
         yout = np.empty_like(xin)
         lib = self.op.lib
         self.op._check(lib.kexp_cheby_apply(self.op.ctx, self.id, _lib.ptr(xin), _lib.ptr(yout), float(t)), "kexp_cheby_apply")
@@ -121,18 +123,25 @@ class cheby_exp(object):
     # ---- batched over the averaging samples --------------------------------------
     def apply_batch(self, X, t, shared=False, out=None):
         """Rows of X (B x n) advanced by their own t[k]; shared=True: one x for every t[k]."""
-        t = np.ascontiguousarray(t, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
         B = t.shape[0]
+        n = self.op.n
         X = np.asarray(X, dtype=np.float64)
         if shared:
             X = np.ascontiguousarray(X.reshape(-1))
-            ldx = self.op.n
+            if X.shape[0] != n:
+                raise ValueError(f"shared input must hold n = {n} values, got {X.shape[0]}")
+            ldx = n
         else:
             X = np.ascontiguousarray(np.atleast_2d(X))
-            assert X.shape == (B, self.op.n)
-            ldx = self.op.n
+            if X.shape != (B, n):
+                raise ValueError(f"X must have shape (B, n) = ({B}, {n}), got {X.shape}")
+            ldx = n
         if out is None:
-            out = np.empty((B, self.op.n))
+            out = np.empty((B, n))
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float64 or out.shape != (B, n)
+              or out.strides[1] != 8 or out.strides[0] % 8 or out.strides[0] < 8 * n or not out.flags.writeable):
+            raise ValueError(f"out must be a writeable float64 array of shape ({B}, {n}) with unit inner stride")
         lib = self.op.lib
         self.op._check(lib.kexp_cheby_apply_batch(self.op.ctx, self.id, _lib.ptr(X), ldx, int(shared),
                                                   _lib.ptr(out), out.strides[0] // 8, _lib.ptr(t), B), "kexp_cheby_apply_batch")
@@ -142,10 +151,14 @@ class cheby_exp(object):
         """sum_k w_k exp(t_k L) X_k: `DU *= wt; ensemble.allreduce(DU, V)` (timestepping_methods.py:9-11).
         fused=True never forms the B individual results: the inputs are combined into the vector coefficients of
         one polynomial in M^-1 K, evaluated by a single Clenshaw recurrence (same sum to round-off)."""
-        t = np.ascontiguousarray(t, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
+        w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1)
         B = t.shape[0]
+        if w.shape[0] != B:
+            raise ValueError("t and w must have the same length")
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1) if shared else np.atleast_2d(X), dtype=np.float64)
+        if X.shape != ((self.op.n,) if shared else (B, self.op.n)):
+            raise ValueError(f"X must have shape {'(n,)' if shared else '(B, n)'} with n = {self.op.n}, B = {B}; got {X.shape}")
         v = np.empty(self.op.n)
         lib = self.op.lib
         fn = lib.kexp_cheby_apply_average_fused if fused else lib.kexp_cheby_apply_average

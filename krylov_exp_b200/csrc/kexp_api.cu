@@ -696,10 +696,14 @@ namespace {
 template <int W>
 void launch_combine(kexp_ctx* ctx, int nb, const double* D, double* Y) {
     auto k = basis_combine_kernel<W>;
-    const size_t smem = sizeof(double) * (size_t)nb * W;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_max = sizeof(double) * (size_t)std::min(nb, kCombineChunk) * W;
+    if (smem_max > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     const int grid = std::min(8 * ctx->num_sms, blocks_for(ctx->n, W / 2));
-    k<<<grid, kThreads, smem, ctx->stream>>>(ctx->d_basis, ctx->basis_ld, nb, D, Y, (int)ctx->n);
+    for (int m0 = 0; m0 < nb; m0 += kCombineChunk) {          // long series: one pass per chunk of terms
+        const int cnt = std::min(kCombineChunk, nb - m0);
+        k<<<grid, kThreads, sizeof(double) * (size_t)cnt * W, ctx->stream>>>(ctx->d_basis + m0, ctx->basis_ld, cnt, D + (size_t)m0 * W, Y,
+                                                                             (int)ctx->n, m0 > 0 ? 1 : 0);
+    }
 }
 
 template <int W>
@@ -731,10 +735,14 @@ void enqueue_clenshaw(kexp_ctx* ctx, const PanelPlan& plan) {
 template <int W>
 void launch_clenshaw_combine(kexp_ctx* ctx, const double* X, const double* G, int nb, int accumulate) {
     auto k = clenshaw_combine_kernel<W>;
-    const size_t smem = sizeof(double) * (size_t)nb * W;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_max = sizeof(double) * (size_t)std::min(nb, kCombineChunk) * W;
+    if (smem_max > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     const int grid = std::max(1, std::min(8 * ctx->num_sms, (int)((ctx->n + kThreads - 1) / kThreads)));
-    k<<<grid, kThreads, smem, ctx->stream>>>(X, (int)ctx->n, G, nb, ctx->d_basis, ctx->basis_ld, accumulate);
+    for (int m0 = 0; m0 < nb; m0 += kCombineChunk) {          // long series: one pass over the inputs per chunk of terms
+        const int cnt = std::min(kCombineChunk, nb - m0);
+        k<<<grid, kThreads, sizeof(double) * (size_t)cnt * W, ctx->stream>>>(X, (int)ctx->n, G + (size_t)m0 * W, cnt, ctx->d_basis + m0,
+                                                                             ctx->basis_ld, accumulate);
+    }
 }
 
 int alloc_lane_scalars(kexp_ctx* ctx) {
@@ -771,7 +779,11 @@ int for_each_lane(kexp_ctx* ctx, F f) {     // run f with every allocated lane a
 // ====================================================================== C ABI
 extern "C" {
 
-const char* kexp_version(void) { return "kexp-b200 0.1 (sm_100a)"; }
+static int poll_deferred(kexp_ctx* ctx, bool block);      // deferred convergence check of asynchronous applies (below)
+static int unconverged_error(kexp_ctx* ctx, double worst, bool deferred);
+static void raise_iterations(kexp_ctx* ctx);
+
+const char* kexp_version(void) { return "kexp-b200 0.2 (sm_100a)"; }
 
 const char* kexp_last_error(kexp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -801,6 +813,9 @@ int kexp_create(kexp_ctx** out, int device) {
     ok = ok && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_chk, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_sc, sizeof(CgScalars)) == cudaSuccess;
+    if (ok) memset(ctx->h_sc, 0, sizeof(CgScalars));
     if (!ok) { kexp_destroy(ctx); return 6; }
     const char* g = getenv("KEXP_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
@@ -866,6 +881,8 @@ int kexp_destroy(kexp_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_chk) cudaEventDestroy(ctx->ev_chk);
+    if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->nccl_comm && ctx->nccl_lib) {
         typedef int (*destroy_t)(void*);
         destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
@@ -987,6 +1004,7 @@ int kexp_set_mass_solver(kexp_ctx* ctx, double rtol, int max_it, int precond) {
     if (!ctx) return 1;
     cudaSetDevice(ctx->device);
     if (!(rtol > 0.0) || max_it < 1 || (precond != 1 && precond != 3)) return kexp::fail(ctx, "bad mass solver parameters");
+    rtol = std::max(rtol, 2e-14);          // below the attainable accuracy of the fp64 residual (include/kexp.h)
     invalidate_graphs(ctx);
     const bool rebuild = ctx->have_op && precond != ctx->precond;
     ctx->rtol = rtol; ctx->max_it = max_it; ctx->precond = precond;
@@ -1194,7 +1212,7 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
                                       cudaMemcpyDeviceToHost, ctx->stream));
     }
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return poll_deferred(ctx, true);
 }
 
 int kexp_batch_set_order(kexp_batch* b, const int32_t* order) {
@@ -1332,6 +1350,10 @@ static const std::vector<PanelPlan>& batch_plans(kexp_ctx* ctx, int id, const ke
     }
     return ctx->plan_cache.emplace(key, std::move(plans)).first->second;
 }
+
+// A shared-input batch uploaded with the shared-basis path on holds ONE vector (shared_vec); its panels are
+// uninitialised device memory and must never be read.
+static bool panels_unset(const kexp_batch* b) { return b->is_shared && b->ctx->use_shared_basis; }
 
 // Forward half of an averaged evaluation: one input for all sample times.
 static int cheby_apply_shared(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
@@ -1477,7 +1499,6 @@ static int cheby_average_fused_impl(kexp_ctx* ctx, int id, kexp_batch* in, const
     const ChebTable& tb = ctx->cheb[id];
     const int B = in->B;
     const bool shared = in->is_shared && in->shared_vec && ctx->use_shared_basis;
-    if ((size_t)(tb.ncheb + 1) * 64 * sizeof(double) > 160 * 1024) return kexp::fail(ctx, "series too long for the fused average");
     if (swap_lane(ctx, 0)) return 1;
     if (finish_upload(in)) return 1;
     const bool econ = economise(ctx, tb, t, B);
@@ -1575,12 +1596,11 @@ static int cheby_average_fused_impl(kexp_ctx* ctx, int id, kexp_batch* in, const
 
 static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
     if (check_ready(ctx, id)) return 1;
-    if (in && out && t && in != out && in->B == out->B && in->is_shared && in->shared_vec && ctx->use_shared_basis &&
-        (size_t)(ctx->cheb[id].ncheb + 1) * 64 * sizeof(double) <= 160 * 1024)
-        return cheby_apply_shared(ctx, id, in, out, t, time_it);
     if (!in || !out || !t) return kexp::fail(ctx, "null argument");
     if (in == out) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
     if (in->B != out->B) return kexp::fail(ctx, "batch sizes differ");
+    if (in->is_shared && in->shared_vec && ctx->use_shared_basis) return cheby_apply_shared(ctx, id, in, out, t, time_it);
+    if (panels_unset(in)) return kexp::fail(ctx, "the input batch holds one shared vector, its panels were never filled");
     cudaSetDevice(ctx->device);
     if (in->stride != out->stride || in->panelW != out->panelW) return kexp::fail(ctx, "batches have different panel layouts");
     int maxW = 0;
@@ -1622,19 +1642,90 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
 }
 
 // The CG loop inside the graph has a fixed number of early-exit iterations.  After the
-// first apply it is trimmed to the observed maximum + 2; every apply then checks (one
-// 8-byte read-back) that no solve ran into the trimmed cap and otherwise repeats itself
-// with the full max_it.
-static int read_cg_counters(kexp_ctx* ctx, int* max_iters, int* unconverged) {
-    *max_iters = 0; *unconverged = 0;
+// first apply it is trimmed to the observed maximum + 2; every apply then checks (one small
+// read-back) that no solve missed its tolerance and otherwise repeats itself with more
+// iterations, up to max_it.  A solve that still misses rtol at max_it is an ERROR (the result
+// is not delivered silently).  In asynchronous mode (kexp_set_async) the read-back of a tuned
+// context is deferred: it is copied to pinned memory behind the apply and inspected by a later
+// call, at the latest by kexp_synchronize / kexp_batch_download / kexp_stats.
+static int read_cg_counters(kexp_ctx* ctx, int* max_iters, int* unconverged, double* worst) {
+    *max_iters = 0; *unconverged = 0; *worst = 0.0;
     return for_each_lane(ctx, [&]() -> int {
-        int h[2];
-        KEXP_CUDA(cudaMemcpyAsync(h, &ctx->d_sc->max_iters, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CgScalars* h = ctx->h_sc;
+        const size_t off = offsetof(CgScalars, max_iters);
+        KEXP_CUDA(cudaMemcpyAsync((char*)h + off, (const char*)ctx->d_sc + off, sizeof(CgScalars) - off, cudaMemcpyDeviceToHost, ctx->stream));
         KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
-        *max_iters = std::max(*max_iters, h[0]); *unconverged += h[1];
+        *max_iters = std::max(*max_iters, h->max_iters); *unconverged += h->unconverged;
+        *worst = std::max(*worst, h->worst_rel_res);
         return 0;
     });
 }
+
+static int unconverged_error(kexp_ctx* ctx, double worst, bool deferred) {
+    char buf[320];
+    snprintf(buf, sizeof(buf), "mass solve did not reach rtol %.3g within max_it = %d iterations: max rel residual %.3e%s",
+             ctx->rtol, ctx->max_it, worst,
+             deferred ? " (detected after an asynchronous apply: results computed since the last check are invalid)" : "");
+    return kexp::fail(ctx, buf);
+}
+
+static void raise_iterations(kexp_ctx* ctx) {
+    ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 2) : ctx->max_it;
+    ctx->its_tuned = true;              // do not trim again
+    invalidate_graphs(ctx);
+}
+
+// Look at a deferred read-back.  block = false: only if the copy has already finished.
+static int poll_deferred(kexp_ctx* ctx, bool block) {
+    if (!ctx->chk_pending) return 0;
+    if (block) KEXP_CUDA(cudaEventSynchronize(ctx->ev_chk));
+    else if (cudaEventQuery(ctx->ev_chk) != cudaSuccess) { cudaGetLastError(); return 0; }
+    ctx->chk_pending = false;
+    const int unc = ctx->h_sc->unconverged;
+    if (unc > ctx->unconverged_seen) {
+        ctx->unconverged_seen = unc;
+        const double worst = ctx->h_sc->worst_rel_res;
+        if (ctx->graph_its < ctx->max_it) raise_iterations(ctx);       // later applies get more iterations
+        return unconverged_error(ctx, worst, true);
+    }
+    return 0;
+}
+
+extern "C++" {
+template <typename F>
+static int run_checked(kexp_ctx* ctx, F enqueue) {
+    if (poll_deferred(ctx, false)) return 1;
+    for (;;) {
+        if (enqueue()) return 1;
+        if (ctx->timing) drain_events(ctx);
+        if (!ctx->adaptive_its) return 0;
+        if (ctx->async_checks && ctx->its_tuned && ctx->nlanes == 1 && !ctx->timing) {
+            if (ctx->chk_pending) return 0;                            // the pending copy covers the counters (they only grow)
+            const size_t off = offsetof(CgScalars, max_iters);
+            KEXP_CUDA(cudaMemcpyAsync((char*)ctx->h_sc + off, (const char*)ctx->d_sc + off, sizeof(CgScalars) - off, cudaMemcpyDeviceToHost, ctx->stream));
+            KEXP_CUDA(cudaEventRecord(ctx->ev_chk, ctx->stream));
+            ctx->chk_pending = true;
+            return 0;
+        }
+        int mx = 0, unc = 0;
+        double worst = 0.0;
+        if (read_cg_counters(ctx, &mx, &unc, &worst)) return 1;
+        if (unc > ctx->unconverged_seen) {
+            // a solve hit the trimmed cap (CG) or missed rtol with the fixed length (Chebyshev): raise it and redo
+            ctx->unconverged_seen = unc;
+            if (ctx->graph_its >= ctx->max_it) return unconverged_error(ctx, worst, false);
+            raise_iterations(ctx);
+            continue;
+        }
+        if (!ctx->its_tuned && mx > 0) {
+            const int want = std::min(ctx->max_it, mx + 2);
+            if (want < ctx->graph_its) { ctx->graph_its = want; invalidate_graphs(ctx); }
+            ctx->its_tuned = true;
+        }
+        return 0;
+    }
+}
+}  // extern "C++"
 
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t) {
     if (!ctx) return 1;
@@ -1648,26 +1739,14 @@ int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out,
             t = ts.data();
         }
     }
-    if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
-    if (ctx->timing) drain_events(ctx);
-    if (!ctx->adaptive_its) return 0;
-    int mx = 0, unc = 0;
-    if (read_cg_counters(ctx, &mx, &unc)) return 1;
-    if (unc > ctx->unconverged_seen && ctx->graph_its < ctx->max_it) {
-        // a solve hit the trimmed cap (CG) or missed rtol with the fixed length (Chebyshev): raise it and redo
-        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 2) : ctx->max_it;
-        ctx->its_tuned = true;              // do not trim again
-        ctx->unconverged_seen = unc;
-        invalidate_graphs(ctx);
-        if (cheby_apply_dev_impl(ctx, id, in, out, t, true)) return 1;
-        if (ctx->timing) drain_events(ctx);
-        if (read_cg_counters(ctx, &mx, &unc)) return 1;
-    } else if (!ctx->its_tuned && mx > 0) {
-        const int want = std::min(ctx->max_it, mx + 2);
-        if (want < ctx->graph_its) { ctx->graph_its = want; invalidate_graphs(ctx); }
-        ctx->its_tuned = true;
-    }
-    ctx->unconverged_seen = unc;
+    return run_checked(ctx, [&]() { return cheby_apply_dev_impl(ctx, id, in, out, t, true); });
+}
+
+int kexp_set_async(kexp_ctx* ctx, int on) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (!on && poll_deferred(ctx, true)) return 1;
+    ctx->async_checks = on != 0;
     return 0;
 }
 
@@ -1676,7 +1755,7 @@ int kexp_synchronize(kexp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
     KEXP_CUDA(cudaGetLastError());
-    return 0;
+    return poll_deferred(ctx, true);
 }
 
 int kexp_timer_start(kexp_ctx* ctx) {
@@ -1712,6 +1791,7 @@ int kexp_batch_average_dev(kexp_batch* b, const double* w, double* v_dev) {
     if (!b || !w || !v_dev) return 1;
     kexp_ctx* ctx = b->ctx;
     cudaSetDevice(ctx->device);
+    if (panels_unset(b)) return kexp::fail(ctx, "a shared-input batch holds one vector; there are no columns to average");
     if (finish_upload(b)) return 1;
     std::vector<double> ws;
     if (!b->order.empty()) {
@@ -1811,22 +1891,7 @@ int kexp_cheby_average_fused_dev(kexp_ctx* ctx, int id, kexp_batch* in, const do
         for (int j = 0; j < in->B; ++j) { ts[j] = t[in->order[j]]; ws[j] = w[in->order[j]]; }
         t = ts.data(); w = ws.data();
     }
-    if (cheby_average_fused_impl(ctx, id, in, t, w, v_dev)) return 1;
-    if (ctx->timing) drain_events(ctx);
-    if (!ctx->adaptive_its) return 0;
-    int mx = 0, unc = 0;
-    if (read_cg_counters(ctx, &mx, &unc)) return 1;
-    if (unc > ctx->unconverged_seen && ctx->graph_its < ctx->max_it) {     // same policy as kexp_cheby_apply_dev
-        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 2) : ctx->max_it;
-        ctx->its_tuned = true;
-        ctx->unconverged_seen = unc;
-        invalidate_graphs(ctx);
-        if (cheby_average_fused_impl(ctx, id, in, t, w, v_dev)) return 1;
-        if (ctx->timing) drain_events(ctx);
-        if (read_cg_counters(ctx, &mx, &unc)) return 1;
-    }
-    ctx->unconverged_seen = unc;
-    return 0;
+    return run_checked(ctx, [&]() { return cheby_average_fused_impl(ctx, id, in, t, w, v_dev); });
 }
 
 int kexp_cheby_apply_average_fused(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
@@ -1851,6 +1916,7 @@ int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     if (!ctx) return 1;
     if (!ctx->have_op) return kexp::fail(ctx, "operator not set");
     if (!in || !out || in->B != out->B) return kexp::fail(ctx, "bad batches");
+    if (panels_unset(in)) return kexp::fail(ctx, "shared-input batches are only valid as the input of kexp_cheby_apply_dev / kexp_cheby_average_fused_dev");
     cudaSetDevice(ctx->device);
     if (finish_upload(in)) return 1;
     if (in != out) out->order = in->order;
@@ -1869,10 +1935,13 @@ int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
             ok = ok && done;
         }
         KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
-        if (ok || ctx->graph_its >= ctx->max_it) break;
-        ctx->graph_its = (ctx->solver == 1) ? std::min(ctx->max_it, ctx->graph_its + 2) : ctx->max_it;
-        ctx->its_tuned = true;
-        invalidate_graphs(ctx);
+        if (ok) break;
+        if (ctx->graph_its >= ctx->max_it) {
+            double res = 0.0;
+            KEXP_CUDA(cudaMemcpy(&res, &ctx->d_sc->max_rel_res, sizeof(double), cudaMemcpyDeviceToHost));
+            return unconverged_error(ctx, res, false);
+        }
+        raise_iterations(ctx);
     }
     KEXP_CUDA(cudaGetLastError());
     if (ctx->timing) drain_events(ctx);
@@ -1883,6 +1952,7 @@ int kexp_spmm_K_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     if (!ctx) return 1;
     if (!ctx->have_op) return kexp::fail(ctx, "operator not set");
     if (!in || !out || in->B != out->B || in == out) return kexp::fail(ctx, "bad batches");
+    if (panels_unset(in)) return kexp::fail(ctx, "shared-input batches are only valid as the input of kexp_cheby_apply_dev / kexp_cheby_average_fused_dev");
     cudaSetDevice(ctx->device);
     if (finish_upload(in)) return 1;
     out->order = in->order;
@@ -1966,9 +2036,13 @@ int kexp_stats(kexp_ctx* ctx, kexp_stats_t* out) {
         out->cg_solves += (int64_t)(sc.total_solves - ctx->base_solves);
         out->cg_iterations += (int64_t)(sc.total_iters - ctx->base_iters);
         out->last_max_rel_residual = std::max(out->last_max_rel_residual, sc.max_rel_res);
+        out->unconverged_solves += sc.unconverged;
+        out->worst_rel_residual = std::max(out->worst_rel_residual, sc.worst_rel_res);
         return 0;
     });
     if (rc) return rc;
+    out->mass_iterations_per_solve = ctx->graph_its;
+    if (poll_deferred(ctx, true)) return 1;
     out->op_applications = ctx->st_op_apps;
     out->kernel_launches = ctx->st_launches;
     out->bicg_iterations = ctx->st_bicg;

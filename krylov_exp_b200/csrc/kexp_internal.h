@@ -125,6 +125,12 @@ struct kexp_ctx {
     bool its_tuned = false;
     bool adaptive_its = true;
     int unconverged_seen = 0;
+    // deferred convergence check (kexp_set_async): the counters of an apply are copied to pinned memory behind it
+    // and looked at by the next call that finds the copy finished, at the latest by kexp_synchronize / download
+    bool async_checks = false;
+    kexp::CgScalars* h_sc = nullptr;       // pinned
+    cudaEvent_t ev_chk = nullptr;
+    bool chk_pending = false;
     int spmm_blocks_per_sm = 0;    // 0: from occupancy
     bool use_relax = true;         // relax the mass-solve tolerance of late Chebyshev terms (KEXP_RELAX=0: uniform rtol)
     bool use_coop = true;          // whole Chebyshev mass solve as one cooperative kernel (KEXP_COOP=0: one kernel per iteration)

@@ -48,6 +48,7 @@ struct CgScalars {
     unsigned long long total_solves;
     double max_rel_res;    // of the last solve
     double rtol2;
+    double worst_rel_res;  // largest max_rel_res of any solve that missed its tolerance since reset
 };
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
@@ -1126,7 +1127,10 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
         s_a[threadIdx.x] = coef[(size_t)st.n * kMaxW + threadIdx.x];      // per-column series coefficient of term n
     }
     if (threadIdx.x == 0) {
-        if (st.check_cg && blockIdx.x == 0 && !sc->done) sc->unconverged += 1;
+        if (st.check_cg && blockIdx.x == 0 && !sc->done) {
+            sc->unconverged += 1;
+            sc->worst_rel_res = fmax(sc->worst_rel_res, sc->max_rel_res);
+        }
     }
     __syncthreads();
     const int l = threadIdx.x % LPR;
@@ -1208,10 +1212,13 @@ basis_store_kernel(const double* __restrict__ S, int n, double* __restrict__ bas
         basis[(size_t)i * ld + m] = S[(size_t)i * W];
 }
 
+// Long series are combined in chunks of kCombineChunk terms (the coefficient tile lives in shared memory):
+// `basis` and `D` then point at the chunk's first term and accumulate != 0 adds to Y.
+constexpr int kCombineChunk = 256;
 template <int W>
 __global__ void __launch_bounds__(kThreads)
 basis_combine_kernel(const double* __restrict__ basis, int ld, int nb, const double* __restrict__ D,
-                     double* __restrict__ Y, int n) {
+                     double* __restrict__ Y, int n, int accumulate) {
     constexpr int LPR = W / 2;
     extern __shared__ double sD[];                   // nb x W
     for (int e = threadIdx.x; e < nb * W; e += kThreads) sD[e] = D[e];
@@ -1221,7 +1228,7 @@ basis_combine_kernel(const double* __restrict__ basis, int ld, int nb, const dou
     const int ng = gridDim.x * kThreads / LPR;
     for (int i = g0; i < n; i += ng) {
         const double* bi = basis + (size_t)i * ld;
-        double2 acc = make_double2(0.0, 0.0);
+        double2 acc = accumulate ? ld2(Y + (size_t)i * W + 2 * l) : make_double2(0.0, 0.0);
         for (int m = 0; m < nb; ++m) {
             const double u = __ldg(bi + m);
             acc.x = fma(u, sD[m * W + 2 * l], acc.x);

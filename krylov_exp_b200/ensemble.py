@@ -58,8 +58,11 @@ class SampleEnsemble:
     # ---- the one collective of the path
     def allreduce(self, v):
         """Sum v over the ensemble in place (numpy array or torch tensor)."""
-        if self.world == 1 or self._dist is None:
+        if self.world == 1:
             return v
+        if self._dist is None:
+            raise RuntimeError(f"SampleEnsemble(world={self.world}) has no communicator: torch.distributed is not initialised and "
+                               "no library communicator was set up (init_library_comm); refusing to return this rank's partial sum")
         import torch
         if isinstance(v, np.ndarray):
             tv = torch.from_numpy(v)

@@ -216,6 +216,11 @@ class Operator:
         self._next_cheby_id += 1
         return i
 
+    def set_async(self, on=True):
+        """Applies on device batches return once enqueued; the convergence record of their mass solves is checked by a
+        later call (at the latest synchronize / download / stats), which raises if a solve missed rtol."""
+        self._check(self.lib.kexp_set_async(self.ctx, int(bool(on))), "kexp_set_async")
+
     def synchronize(self):
         self._check(self.lib.kexp_synchronize(self.ctx), "kexp_synchronize")
 
