@@ -26,57 +26,7 @@ int pick_W(int B) {
 void free_csr(DevCsr& d) {
     cudaFree(d.rowptr); cudaFree(d.col); cudaFree(d.val);
     cudaFree(d.browptr); cudaFree(d.blocks); cudaFree(d.rowmap);
-    cudaFree(d.ccolptr); cudaFree(d.ccols); cudaFree(d.lblocks);
     d = DevCsr();
-}
-
-// Chunked copy of a square BSR matrix for bsr3_spmm_tma_kernel: per chunk of kTmaRows block rows the
-// sorted list of distinct block columns; blocks re-indexed by slot, diagonal block first in its row.
-static void build_tma_chunks(kexp_ctx* ctx, DevCsr& d, const std::vector<int>& browptr, const std::vector<double>& blocks) {
-    const char* env = getenv("KEXP_STAGED_SPMM");
-    if (!(env && env[0] == '1')) return;
-    const int nbr = (int)browptr.size() - 1;
-    const int nchunks = (nbr + kTmaRows - 1) / kTmaRows;
-    std::vector<int> ccolptr((size_t)nchunks + 1, 0), ccols;
-    std::vector<double> lb(blocks);
-    int maxcols = 0, maxblk = 0;
-    std::vector<int> cols;
-    for (int c = 0; c < nchunks; ++c) {
-        const int r0 = c * kTmaRows, r1 = std::min(r0 + kTmaRows, nbr);
-        cols.clear();
-        for (int k = browptr[r0]; k < browptr[r1]; ++k) { int64_t bits; memcpy(&bits, &blocks[(size_t)k * 10 + 9], 8); cols.push_back((int)bits); }
-        std::sort(cols.begin(), cols.end());
-        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
-        for (int r = r0; r < r1; ++r) {
-            int diag = -1;
-            for (int k = browptr[r]; k < browptr[r + 1]; ++k) {
-                int64_t bits; memcpy(&bits, &blocks[(size_t)k * 10 + 9], 8);
-                if ((int)bits == r) diag = k;
-                int64_t slot = std::lower_bound(cols.begin(), cols.end(), (int)bits) - cols.begin();
-                memcpy(&lb[(size_t)k * 10 + 9], &slot, 8);
-            }
-            if (diag < 0) return;                       // no diagonal block: keep the generic kernel
-            if (diag != browptr[r])
-                for (int e = 0; e < 10; ++e) std::swap(lb[(size_t)diag * 10 + e], lb[(size_t)browptr[r] * 10 + e]);
-        }
-        ccols.insert(ccols.end(), cols.begin(), cols.end());
-        ccolptr[c + 1] = (int)ccols.size();
-        maxcols = std::max(maxcols, (int)cols.size());
-        maxblk = std::max(maxblk, browptr[r1] - browptr[r0]);
-    }
-    TmaStageLayout lay;
-    lay.x_bytes = maxcols * kTmaTile;
-    lay.blk_bytes = ((maxblk * 80 + 127) / 128) * 128;
-    lay.p_bytes = ((kTmaRows * 72 + 127) / 128) * 128;
-    if ((size_t)kTmaStages * lay.stage_bytes() > 227u * 1024u - 1024u) return;     // does not fit: generic kernel
-    if (cudaMalloc(&d.ccolptr, sizeof(int) * ccolptr.size()) != cudaSuccess) return;
-    if (cudaMalloc(&d.ccols, sizeof(int) * std::max<size_t>(ccols.size(), 1)) != cudaSuccess) return;
-    if (cudaMalloc(&d.lblocks, sizeof(double) * std::max<size_t>(lb.size(), 1)) != cudaSuccess) { d.lblocks = nullptr; return; }
-    cudaMemcpy(d.ccolptr, ccolptr.data(), sizeof(int) * ccolptr.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(d.ccols, ccols.data(), sizeof(int) * ccols.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(d.lblocks, lb.data(), sizeof(double) * lb.size(), cudaMemcpyHostToDevice);
-    d.nchunks = nchunks; d.lay = lay;
-    (void)ctx;
 }
 
 // CSR -> BSR(3x3) with 80-byte blocks {9 values row-major, block column in the low word of
@@ -158,7 +108,6 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
     }
     d.nbr = nbr; d.nblocks = nblocks; d.max_bpr = max_bpr;
     d.diag_first = force && nrows == ncols && all_diag;
-    if (force && nrows == ncols) build_tma_chunks(ctx, d, browptr, blocks);
     if (max_bpr > kSpmmSmemBlocks) { cudaFree(d.browptr); cudaFree(d.blocks); d.browptr = nullptr; d.blocks = nullptr; }
     return 0;
 }
@@ -336,17 +285,6 @@ constexpr int kCptVec = 2;                  // sample columns per thread in the 
 template <int W, int MODE>
 void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
     constexpr int LPR = W / 2, RPW = 32 / LPR;
-    if (MODE == 1 && W == kTmaW && A.tma() && ctx->use_tma) {
-        const int dyn = kTmaStages * A.lay.stage_bytes();
-        if (!ctx->tma_attr_set) {
-            cudaFuncSetAttribute(bsr3_spmm_tma_kernel<kTmaStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-            ctx->tma_attr_set = true;
-        }
-        const int grid = std::min(ctx->num_sms, A.nchunks);
-        bsr3_spmm_tma_kernel<kTmaStages><<<grid, kTmaThreads + 32 * kTmaProducers, dyn, ctx->stream>>>(A.browptr, A.lblocks, A.ccolptr, A.ccols, X, Y, A.nbr, A.nchunks,
-                                                                    ctx->T, ctx->d_Pinv, A.lay, ctx->d_sc, ctx->d_partials, ctx->d_counter);
-        return;
-    }
     if (A.bsr()) {
         auto k = bsr3_spmm_kernel<W, MODE, (MODE == 0 ? kSpmm0GB : kSpmmGB)>;
         constexpr int per_cta = PanelCfg<W, kSpmmCpt>::BPC;
@@ -417,20 +355,7 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
         for (int it = 1; it < K; ++it) {
             omega = (it == 1) ? 1.0 / (1.0 - 0.5 * mu * mu) : 1.0 / (1.0 - 0.25 * mu * mu * omega);
             TimedLaunch tl(ctx, KC_SPMM_CG);
-            if (ctx->cheb_scalar_lanes) {
-                constexpr int per1 = LaneCfg<W>::BPC;
-                if (it == K - 1) {
-                    auto k = bsr3_cheb_iter1_kernel<W, 1, kSpmmGB>;
-                    int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per1 - 1) / per1));
-                    launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                             omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
-                } else {
-                    auto k = bsr3_cheb_iter1_kernel<W, 0, kSpmmGB>;
-                    int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per1 - 1) / per1));
-                    launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                             omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
-                }
-            } else if (it == K - 1) {
+            if (it == K - 1) {
                 auto k = bsr3_cheb_iter_kernel<W, 1, kSpmmGB>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
@@ -618,7 +543,6 @@ void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, cheb_solve_init_kernel<W, kCptVec>);
     max_grid(ctx, cheb_solve_coop_kernel<W, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, bsr3_cheb_iter_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
-    max_grid(ctx, bsr3_cheb_iter1_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter1_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
 }
 
@@ -819,13 +743,9 @@ int kexp_create(kexp_ctx** out, int device) {
     if (!ok) { kexp_destroy(ctx); return 6; }
     const char* g = getenv("KEXP_NO_GRAPH");
     if (g && g[0] == '1') ctx->use_graph = false;
-    const char* tm = getenv("KEXP_STAGED_SPMM");
-    if (tm && tm[0] == '1') ctx->use_tma = true;
     const char* ln = getenv("KEXP_LANES");
     if (ln && ln[0] == '1') { ctx->nlanes = 1; ctx->panel_cap = 64; }
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
-    const char* sl = getenv("KEXP_SCALAR_LANES");
-    if (sl) ctx->cheb_scalar_lanes = (sl[0] == '1');
     const char* rl = getenv("KEXP_RELAX");
     if (rl) ctx->use_relax = (rl[0] == '1');
     const char* co = getenv("KEXP_COOP");

@@ -7,7 +7,6 @@
 #include <vector>
 #include "../../include/kexp.h"
 #include "kexp_kernels.cuh"
-#include "kexp_spmm_tma.cuh"
 
 namespace kexp {
 
@@ -27,13 +26,6 @@ struct DevCsr {
     int max_bpr = 1;               // most blocks in any block row
     bool diag_first = false;       // every block row starts with its diagonal block
     int64_t nblocks = 0;
-    // chunked copy for the TMA-staged CG product (kexp_spmm_tma.cuh)
-    int* ccolptr = nullptr;
-    int* ccols = nullptr;
-    double* lblocks = nullptr;
-    int nchunks = 0;
-    TmaStageLayout lay{0, 0, 0};
-    bool tma() const { return lblocks != nullptr; }
     bool bsr() const { return blocks != nullptr; }
     double bytes() const {
         return bsr() ? 80.0 * (double)nblocks + 4.0 * (double)(nbr + 1) : 12.0 * (double)nnz + 4.0 * (double)(nrows + 1);
@@ -134,7 +126,6 @@ struct kexp_ctx {
     int spmm_blocks_per_sm = 0;    // 0: from occupancy
     bool use_relax = true;         // relax the mass-solve tolerance of late Chebyshev terms (KEXP_RELAX=0: uniform rtol)
     bool use_coop = true;          // whole Chebyshev mass solve as one cooperative kernel (KEXP_COOP=0: one kernel per iteration)
-    bool cheb_scalar_lanes = false; // one column per lane in the Chebyshev iteration kernel (64 registers, 32 warps/SM)
     int red_blocks_per_sm = 4;     // grid of the reduction kernels
 
     kexp::ChebTable cheb[KEXP_MAX_CHEBY];
@@ -168,8 +159,6 @@ struct kexp_ctx {
     std::map<kexp::GraphKey, cudaGraphExec_t> graphs;
     bool use_graph = true;
     bool use_pdl = true;           // programmatic dependent launch between the kernels of the graph (KEXP_PDL=0 disables): +3 %
-    bool use_tma = false;          // shared-memory-staged CG product for 64-column panels (KEXP_STAGED_SPMM=1): slower, see profiles/
-    bool tma_attr_set = false;
 
     // timing / stats
     bool timing = false;

@@ -724,145 +724,6 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
     }
 }
 
-// Same iteration with ONE sample column per lane (64-bit loads): a block row of a 64-column panel is
-// shared by two warps.  The kernel above is bound by latency x occupancy (16 warps/SM at 128
-// registers: one CTA per SM instead of two costs 1.54x); holding 15 gathered doubles instead of 15
-// double2 brings it to 64 registers and 32 warps/SM.
-template <int W>
-struct LaneCfg {                                   // one column per lane
-    static constexpr int WPR = (W >= 32) ? W / 32 : 1;          // warps per block row
-    static constexpr int RPW = (W >= 32) ? 1 : 32 / W;          // block rows per warp
-    static constexpr int BPC = (kThreads / 32) * RPW / WPR;     // block rows per CTA pass
-};
-
-template <int W, int LAST, int GB>
-__global__ void __launch_bounds__(kThreads, 4)
-bsr3_cheb_iter1_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
-                       const double* __restrict__ Xold, double* __restrict__ Xnew, const double* __restrict__ Bv,
-                       const double* __restrict__ Pinv, int nbr, int max_bpr,
-                       double omega, double alpha, int iters_done, double rtol2,
-                       CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
-    using C = LaneCfg<W>;
-    extern __shared__ double2 sblk[];
-    double* sP = reinterpret_cast<double*>(sblk + 5 * kSpmmSmemBlocks);
-    int* sptr = reinterpret_cast<int*>(sP + 9 * kSpmmSmemRows);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row_in_pass = (W >= 32) ? warp / C::WPR : warp * C::RPW + lane / W;
-    const int col = (W >= 32) ? (warp % C::WPR) * 32 + lane : lane % W;
-    const int per = nbr / gridDim.x, rem = nbr % gridDim.x;
-    const int start = blockIdx.x * per + min((int)blockIdx.x, rem);
-    const int end = start + per + ((int)blockIdx.x < rem ? 1 : 0);
-    const int rows_sub = max(1, min(kSpmmSmemRows, kSpmmSmemBlocks / max_bpr));
-    double rr = 0.0;
-    bool first = true;
-
-    for (int sub = start; sub < end; sub += rows_sub) {
-        const int sub_end = min(sub + rows_sub, end);
-        const int kb0 = __ldg(browptr + sub), kb1 = __ldg(browptr + sub_end);
-        const double2* gsrc = reinterpret_cast<const double2*>(blocks) + (size_t)5 * kb0;
-        for (int i = threadIdx.x; i < 5 * (kb1 - kb0); i += kThreads) sblk[i] = __ldg(gsrc + i);
-        for (int i = threadIdx.x; i <= sub_end - sub; i += kThreads) sptr[i] = __ldg(browptr + sub + i) - kb0;
-        for (int i = threadIdx.x; i < 9 * (sub_end - sub); i += kThreads) sP[i] = __ldg(Pinv + (size_t)9 * sub + i);
-        __syncthreads();
-        if (first) { first = false; pdl_wait(); pdl_trigger(); }
-        for (int base = sub; base < sub_end; base += C::BPC) {
-            const int br = base + row_in_pass;
-            if (br < sub_end) {
-                const int k0 = sptr[br - sub], k1 = sptr[br - sub + 1];
-                const size_t o = (size_t)(3 * br) * W + col;
-                double acc[3] = {0.0, 0.0, 0.0};
-                double xo[3], bv[3], xm[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    xo[i] = Xold[o + (size_t)i * W];
-                    bv[i] = __ldcs(Bv + o + (size_t)i * W);
-                    xm[i] = __ldcs(Xnew + o + (size_t)i * W);
-                }
-                for (int kg = k0; kg < k1; kg += GB) {
-                    double x[GB][3];
-#pragma unroll
-                    for (int j = 0; j < GB; ++j) {
-                        if (kg + j < k1) {
-                            const int c = __double2loint(sblk[5 * (kg + j) + 4].y);
-                            const double* xr = Xold + (size_t)(3 * c) * W + col;
-#pragma unroll
-                            for (int r = 0; r < 3; ++r) x[j][r] = xr[(size_t)r * W];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < GB; ++j) {
-                        if (kg + j < k1) {
-                            const double2* bp = sblk + 5 * (kg + j);
-                            const double2 v01 = bp[0], v23 = bp[1], v45 = bp[2], v67 = bp[3], v8c = bp[4];
-                            acc[0] = fma(v01.x, x[j][0], fma(v01.y, x[j][1], fma(v23.x, x[j][2], acc[0])));
-                            acc[1] = fma(v23.y, x[j][0], fma(v45.x, x[j][1], fma(v45.y, x[j][2], acc[1])));
-                            acc[2] = fma(v67.x, x[j][0], fma(v67.y, x[j][1], fma(v8c.x, x[j][2], acc[2])));
-                        }
-                    }
-                }
-                double rv[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    rv[i] = bv[i] - acc[i];
-                    if (LAST) rr = fma(rv[i], rv[i], rr);
-                }
-                const double* Pb = sP + 9 * (br - sub);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const double z = fma(Pb[3 * i], rv[0], fma(Pb[3 * i + 1], rv[1], Pb[3 * i + 2] * rv[2]));
-                    Xnew[o + (size_t)i * W] = fma(omega, fma(alpha, z, xo[i]) - xm[i], xm[i]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (first) { pdl_wait(); pdl_trigger(); }
-    if (LAST) {
-        // block sums per column in fixed order: the column of a thread is fixed, sum over the threads that share it
-        __shared__ double shr[kThreads];
-        shr[threadIdx.x] = rr;
-        __syncthreads();
-        if (threadIdx.x < W) {
-            const int c = threadIdx.x;
-            double s = 0.0;
-            if (W >= 32) {
-                for (int w = c / 32; w < kThreads / 32; w += C::WPR) s += shr[w * 32 + (c & 31)];
-            } else {
-                for (int t = c; t < kThreads; t += W) s += shr[t];
-            }
-            partials[(size_t)blockIdx.x * W + c] = s;
-        }
-        if (partials_tickets<W, 1>(partials, counter)) {
-            double s[1];
-            final_sums<W, 1>(partials, s);
-            __shared__ int bad;
-            __shared__ double max_rel[kMaxW];
-            if (threadIdx.x == 0) bad = 0;
-            __syncthreads();
-            if (threadIdx.x < W) {
-                const int c = threadIdx.x;
-                sc->rr[c] = s[0];
-                double rel = 0.0;
-                if (sc->bb[c] > 0.0) {
-                    rel = s[0] / sc->bb[c];
-                    if (s[0] > rtol2 * sc->bb[c]) atomicOr(&bad, 1);
-                }
-                max_rel[c] = rel;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double m = 0.0;
-                for (int c = 0; c < W; ++c) m = fmax(m, max_rel[c]);
-                sc->max_rel_res = sqrt(m);
-                sc->iters = iters_done;
-                sc->total_iters += (unsigned long long)iters_done;
-                if (iters_done > sc->max_iters) sc->max_iters = iters_done;
-                sc->done = bad ? 0 : 1;
-            }
-        }
-    }
-}
-
 // Chebyshev start:  x_0 = 0,  x_1 = alpha P^-1 b,  bb = ||b||^2
 template <int W, int CPTMAX>
 __global__ void __launch_bounds__(kThreads)
