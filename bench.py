@@ -3,14 +3,17 @@
 
 Workload M1 (BASELINE.json configs[1]): icosahedral sphere ref_level 5,
 degree-3 geometry, BDM2 x DG1 (N = 215 040), dt = 0.25 h, rho = 1, tol = 1e-8
-(L = 13.4595, 29 Chebyshev terms), 64 averaging samples per GPU.
+(L = 13.4595, 29 Chebyshev terms), an averaging window of 64 samples.  With N GPUs the 64 samples
+are sharded over the ranks (strong scaling: sample k on rank k mod N, averaged_sw_explicit.py:37,
+107,233-235 -- one ensemble member per sample); `--weak` gives every GPU 64 samples of a 64 N window
+instead, and a short weak-scaling measurement is always reported beside the strong one.
 
 One "step" = one averaged nonlinear evaluation's worth of exponentials
 (timestepping_methods.py:7-11):
     forward   exp(+t_k L) U         one shared input, 64 sample times
     backward  exp(-t_k L) X_k       64 distinct inputs
     average   V = sum_k w_k (.)     weighted column reduction (+ NCCL all-reduce when N > 1)
-= 128 applications of exp(sL) per GPU per step.
+= 128 applications of exp(sL) per step (whole job).
 
   value  applications/s with inputs resident in HBM (device batches)
   e2e    same through the host-pointer C-ABI calls (pinned host buffers, H2D/D2H inside)
@@ -53,13 +56,15 @@ def workload(ref_level, samples, seed=1234):
     return sw, L, t, w, x
 
 
-def noisy_inputs(sw, x, B, out, seed=1234):
+def noisy_inputs(sw, x, cols, out, seed=1234):
+    """M1 backward inputs: column k of the window = pulse + noise from default_rng(seed + k).
+    `cols`: the GLOBAL sample indices held in the rows of `out` (a rank's share of the window)."""
     amp = 1e-3 * np.abs(x).max()
-    for k in range(B):
-        rng = np.random.default_rng(seed + k)
-        out[k] = x
-        out[k, sw.n_u:] += amp * rng.standard_normal(sw.n_eta)
-        out[k, :sw.n_u] += amp * np.sqrt(sw.g / sw.H) * sw.radius / 2 ** sw.ref_level * rng.standard_normal(sw.n_u)
+    for i, k in enumerate(cols):
+        rng = np.random.default_rng(seed + int(k))
+        out[i] = x
+        out[i, sw.n_u:] += amp * rng.standard_normal(sw.n_eta)
+        out[i, :sw.n_u] += amp * np.sqrt(sw.g / sw.H) * sw.radius / 2 ** sw.ref_level * rng.standard_normal(sw.n_u)
     return out
 
 
@@ -128,7 +133,7 @@ def cpu_reference_run(sw, L, t, x, ncols, steps, warmup, rtol=1e-5, literal=True
     cpu = CpuCheby(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=rtol, max_it=500)
     c, n = coeffs.cheby_coeffs(NCHEB0, TOL, L)
     coef = c if literal else coeffs.real_recurrence_coeffs(c, n)
-    X = noisy_inputs(sw, x, ncols, np.empty((ncols, sw.n)))
+    X = noisy_inputs(sw, x, range(ncols), np.empty((ncols, sw.n)))
     tk = np.resize(-t, ncols)
     times = []
     for s in range(warmup + steps):
@@ -145,18 +150,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kexp", choices=["kexp", "reference"])
     ap.add_argument("--ref-level", type=int, default=5)
-    ap.add_argument("--samples", type=int, default=64, help="averaging samples per GPU")
+    ap.add_argument("--samples", type=int, default=64, help="averaging samples of the window (whole job); per GPU with --weak")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --samples per GPU, window of samples*N")
     ap.add_argument("--cg-rtol", type=float, default=1e-11,
-                    help="relative residual of the batched mass CG; 1e-11 gives 1.7e-12 parity error at ref 5 (profiles/)")
+                    help="relative residual of the batched mass solve; 1e-11 gives <= 3.2e-12 parity error at ref 5 "
+                         "(tests/test_gpu_parity_r2.py::test_M1_exact_bench_settings_all_columns)")
     ap.add_argument("--max-it", type=int, default=40)
     ap.add_argument("--solver", default="chebyshev", choices=["chebyshev", "cg"],
-                    help="mass solve: Chebyshev semi-iteration (one fused kernel per iteration) or batched PCG")
+                    help="mass solve: Chebyshev semi-iteration (no inner products) or batched PCG")
     ap.add_argument("--no-condense", action="store_true")
     ap.add_argument("--full-series", action="store_true",
                     help="every column runs all ncheb terms (no per-column economised re-expansion)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the variant / weak-scaling side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -164,7 +172,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0))
-    workload_name = f"M1: icosahedral ref{args.ref_level} BDM2xDG1, dt=0.25h rho=1 tol=1e-8, {args.samples} samples/GPU"
+    Btot = args.samples * (world if args.weak else 1)          # samples of the averaging window (whole job)
+    workload_name = (f"M1: icosahedral ref{args.ref_level} BDM2xDG1, dt=0.25h rho=1 tol=1e-8, window of {Btot} samples"
+                     + (f" ({args.samples}/GPU, weak)" if args.weak else f" sharded over {world} GPU(s)"))
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -180,7 +190,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": "applications/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name, "ncheb": ncheb, "L": L},
             "cpu_baseline": {"value": val, "unit": "applications/s", "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "applications/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -194,40 +204,27 @@ def main():
     import krylov_exp_b200 as kx
 
     torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sw, L, t, w, x = workload(args.ref_level, args.samples)
-    B = args.samples
-    # weak scaling: every rank owns `samples` columns of a window with world*samples samples
-    t_all, w_all = kx.sample_times_weights(B * world, DT, RHO)
-    # cyclic assignment (sample k on rank k mod world): every rank gets the same mix of |t_k|, i.e. of series lengths
-    t = np.ascontiguousarray(t_all[rank::world])
-    w = np.ascontiguousarray(w_all[rank::world])
+    sw, L, _, _, x = workload(args.ref_level, Btot)
+    n = sw.n
+    t_all, w_all = kx.sample_times_weights(Btot, DT, RHO)
+    if Btot % world:
+        raise SystemExit(f"--samples {Btot} is not a multiple of the {world} GPUs")
 
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, device=local_rank, condense=not args.no_condense,
                      rtol=args.cg_rtol, max_it=args.max_it, solver=args.solver)
     ce = kx.cheby_exp(op, None, None, NCHEB0, TOL, L, spectral_radius=None if args.full_series else workload.eig)
-    n = op.n
-
-    # pinned host buffers (e2e) and device-resident batches (value)
-    hX = torch.empty((B, n), dtype=torch.float64).pin_memory().numpy()
-    hY = torch.empty((B, n), dtype=torch.float64).pin_memory().numpy()
-    hx = torch.empty((n,), dtype=torch.float64).pin_memory().numpy()
-    hx[:] = x
-    noisy_inputs(sw, x, B, hX, seed=1234 + rank * B)
-    b_fwd_in, b_fwd_out, b_bwd_in, b_bwd_out = op.batch(B), op.batch(B), op.batch(B), op.batch(B)
-    b_fwd_in.upload(hx, shared=True)
-    b_bwd_in.set_order(np.argsort(np.abs(t), kind="stable"))     # panels of similar |t_k|: similar series length
-    b_bwd_in.upload(hX)
-    v = torch.zeros(n, dtype=torch.float64, device=f"cuda:{local_rank}")
-
-    def step_dev():
-        ce.apply_dev(b_fwd_in, b_fwd_out, t)
-        ce.apply_dev(b_bwd_in, b_bwd_out, -t)
-        b_bwd_out.average_into(w, v.data_ptr())
-        if world > 1:
-            op.synchronize()
-            dist.all_reduce(v)
+    ens = kx.SampleEnsemble(Btot, rank=rank, world=world, partition="cyclic")
+    lib_comm = False
+    if world > 1:
+        try:                                   # NCCL inside libkexp.so: the all-reduce runs on the library's stream
+            ens.init_library_comm(op)
+            lib_comm = True
+        except Exception as e:                 # torch.distributed's NCCL on torch's stream (needs a host-side join)
+            if rank == 0:
+                print(f"library NCCL unavailable ({e}); using torch.distributed", file=sys.stderr)
 
     def barrier():
         op.synchronize()
@@ -235,42 +232,116 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(val):
+        if world == 1:
+            return float(val)
+        tt = torch.tensor([val], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    class Shard:
+        """One rank's share of a window: cyclic sample partition (every rank holds the same mix of |t_k|, i.e. of
+        economised series lengths), pinned host buffers for the e2e path, device batches for `value`."""
+
+        def __init__(self, Bwin):
+            self.Bwin = Bwin
+            self.cols = np.arange(rank, Bwin, world)
+            self.B = len(self.cols)
+            tw, ww = kx.sample_times_weights(Bwin, DT, RHO)
+            self.t = np.ascontiguousarray(tw[self.cols])
+            self.w = np.ascontiguousarray(ww[self.cols])
+            self.hX = torch.empty((self.B, n), dtype=torch.float64).pin_memory().numpy()
+            self.hY = torch.empty((self.B, n), dtype=torch.float64).pin_memory().numpy()
+            self.hx = torch.empty((n,), dtype=torch.float64).pin_memory().numpy()
+            self.hx[:] = x
+            noisy_inputs(sw, x, self.cols, self.hX)
+            self.f_in, self.f_out, self.b_in, self.b_out = (op.batch(self.B) for _ in range(4))
+            self.f_in.upload(self.hx, shared=True)
+            self.b_in.set_order(np.argsort(np.abs(self.t), kind="stable"))     # panels of similar |t_k|: similar series length
+            self.b_in.upload(self.hX)
+            self.v = torch.zeros(n, dtype=torch.float64, device=dev)
+
+        def step_dev(self):
+            ce.apply_dev(self.f_in, self.f_out, self.t)
+            ce.apply_dev(self.b_in, self.b_out, -self.t)
+            self.b_out.average_into(self.w, self.v.data_ptr())
+            if world > 1:
+                if lib_comm:
+                    op._check(op.lib.kexp_allreduce_sum_dev(op.ctx, self.v.data_ptr(), n), "kexp_allreduce_sum_dev")
+                else:
+                    op.synchronize()
+                    dist.all_reduce(self.v)
+
+        def step_host(self):
+            """The same step through the host-pointer C-ABI calls: H2D of 1 + B vectors, D2H of B + 1 vectors.  The D2H of
+            the forward results stays in flight under the backward half; the all-reduce runs on the device."""
+            ce.apply_batch(self.hx, self.t, shared=True, out=self.hY, wait=False)
+            vh = ce.apply_average(self.hX, -self.t, self.w, allreduce=lib_comm)
+            op.wait_transfers()
+            if world > 1 and not lib_comm:
+                ens.allreduce(vh)
+            return vh
+
+        def timed(self, fn, steps):
+            """K steps bracketed by barrier + synchronize on both sides; device time on the library's stream (CUDA events),
+            host time around it; max over ranks."""
+            barrier()
+            h0 = time.perf_counter()
+            op.timer_start()
+            for _ in range(steps):
+                fn()
+            ms_dev = op.timer_stop()
+            barrier()
+            ms_host = (time.perf_counter() - h0) * 1e3
+            return max_over_ranks(ms_dev), max_over_ranks(ms_host)
+
+        def close(self):
+            for b_ in (self.f_in, self.f_out, self.b_in, self.b_out):
+                b_.close()
+
+    sh = Shard(Btot)
+    B = sh.B
     for _ in range(max(args.warmup, 3)):
-        step_dev()
+        sh.step_dev()
+    barrier()
+    op.set_async(True)               # tuned now: applies queue back to back, convergence checked at the closing synchronize
+    sh.step_dev()
     barrier()
     op.stats_reset()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_host0 = time.perf_counter()
-    op.timer_start()
-    for _ in range(args.steps):
-        step_dev()
-    ms_dev = op.timer_stop()
-    barrier()
-    ms_host = (time.perf_counter() - t_host0) * 1e3
+    ms_dev, ms_host = sh.timed(sh.step_dev, args.steps)
     clocks = sampler.stop()
     st = op.stats()
-    # device time on the library stream; with N > 1 the torch all-reduce runs on torch's stream, so the
-    # host-bracketed time (barrier + synchronize on both sides) is the one that contains everything
-    ms_total = ms_dev if world == 1 else ms_host
-    if world > 1:
-        tt = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
-    apps_per_step = 2 * B * world
+    # with the library communicator everything (all-reduce included) is on the library's stream: CUDA-event time;
+    # with torch's all-reduce (other stream, host join per step) the host-bracketed time is the one that contains it
+    ms_total = ms_dev if (world == 1 or lib_comm) else ms_host
+    apps_per_step = 2 * Btot
     ms_per_step = ms_total / args.steps
     value = apps_per_step / (ms_per_step * 1e-3)
     cg_its_per_solve = st["cg_iterations"] / max(st["cg_solves"], 1)
-    # operator applications per step: (terms of the forward basis run) + sum over backward panels of their terms
-    terms_per_panel = st["op_applications"] / args.steps
+    terms_per_step = st["op_applications"] / args.steps
+    solve_path = {0: "batched PCG", 1: "Chebyshev, one kernel per iteration", 2: "Chebyshev, one cooperative kernel per solve",
+                  3: "persistent narrow-panel apply kernel"}.get(int(st["solve_path"]), "?")
 
-    # ------------------------------------------------------------ the same step with the forward batch
-    # treated as 64 independent columns (no shared-basis shortcut), for transparency
+    # ------------------------------------------------------------ multi-GPU numerics: the all-reduced average against
+    # a single-GPU recomputation of the whole window on rank 0
+    parity = None
+    if world > 1:
+        v_multi = sh.v.cpu().numpy().copy()
+        if rank == 0:
+            Xall = noisy_inputs(sw, x, range(Btot), np.empty((Btot, n)))
+            v_single = ce.apply_average(Xall, -t_all, w_all)
+            M = sw.M()
+            d = v_multi - v_single
+            parity = float(np.sqrt((d @ (M @ d)) / (v_single @ (M @ v_single))))
+            del Xall
+        barrier()
+
+    # ------------------------------------------------------------ the same step with one of the exact rewritings
+    # switched off (a second context), for transparency; N = 1 only
     def plain_variant(shared_basis, economise):
-        """The same step with one of the exact rewritings switched off (a second context)."""
         if not shared_basis:
             os.environ["KEXP_SHARED_BASIS"] = "0"
         op2 = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, device=local_rank, condense=not args.no_condense,
@@ -278,146 +349,162 @@ def main():
         os.environ.pop("KEXP_SHARED_BASIS", None)
         ce2 = kx.cheby_exp(op2, None, None, NCHEB0, TOL, L, spectral_radius=workload.eig if economise else None)
         f_in, f_out, g_in, g_out = op2.batch(B), op2.batch(B), op2.batch(B), op2.batch(B)
-        f_in.upload(hx, shared=True)
-        g_in.set_order(np.argsort(np.abs(t), kind="stable"))
-        g_in.upload(hX)
+        f_in.upload(sh.hx, shared=True)
+        g_in.set_order(np.argsort(np.abs(sh.t), kind="stable"))
+        g_in.upload(sh.hX)
         for _ in range(3):
-            ce2.apply_dev(f_in, f_out, t); ce2.apply_dev(g_in, g_out, -t)
+            ce2.apply_dev(f_in, f_out, sh.t); ce2.apply_dev(g_in, g_out, -sh.t)
         op2.synchronize()
         op2.timer_start()
         for _ in range(3):
-            ce2.apply_dev(f_in, f_out, t); ce2.apply_dev(g_in, g_out, -t)
-            g_out.average_into(w, v.data_ptr())
+            ce2.apply_dev(f_in, f_out, sh.t); ce2.apply_dev(g_in, g_out, -sh.t)
+            g_out.average_into(sh.w, sh.v.data_ptr())
         ms2 = op2.timer_stop() / 3
         for b_ in (f_in, f_out, g_in, g_out):
             b_.close()
         op2.close()
         return 2 * B / (ms2 * 1e-3)
 
-    # ------------------------------------------------------------ the averaged evaluation with the fused
-    # backward half: forward batch as above, then sum_k w_k exp(-t_k L) N_k by ONE Clenshaw recurrence
-    # (kexp_cheby_average_fused_dev) -- what timestepping_methods.py:7-11 needs; the 64 backward results
-    # are never formed, so this is reported beside `value`, not as it
+    extras = not args.no_extras and not args.no_roofline
+    # ------------------------------------------------------------ the averaged evaluation with the fused backward half:
+    # forward batch as above, then sum_k w_k exp(-t_k L) N_k by ONE Clenshaw recurrence (kexp_cheby_average_fused_dev) --
+    # what timestepping_methods.py:7-11 needs; the backward results are never formed, so it is reported beside `value`
     fused = None
-    if rank == 0 and not args.no_roofline:
+    if extras:
         def step_fused():
-            ce.apply_dev(b_fwd_in, b_fwd_out, t)
-            ce.average_dev(b_bwd_in, -t, w, v.data_ptr())
-        for _ in range(3):
-            step_fused()
-        op.synchronize()
-        v_sep = torch.empty_like(v)
-        ce.apply_dev(b_bwd_in, b_bwd_out, -t)
-        b_bwd_out.average_into(w, v_sep.data_ptr())
-        op.synchronize()
-        dv = float(torch.linalg.norm(v - v_sep) / torch.linalg.norm(v_sep))
-        op.timer_start()
-        for _ in range(max(args.steps, 5)):
-            step_fused()
-        ms_f = op.timer_stop() / max(args.steps, 5)
-        fused = {"ms_per_averaged_evaluation": ms_f, "equivalent_applications_per_s": 2 * B / (ms_f * 1e-3),
-                 "rel_l2_vs_separate_applications": dv,
-                 "what": "forward shared-input batch (64 results delivered) + fused Clenshaw weighted average of the 64 backward "
-                         "applications (only their sum is formed)"}
+            ce.apply_dev(sh.f_in, sh.f_out, sh.t)
+            ce.average_dev(sh.b_in, -sh.t, sh.w, sh.v.data_ptr())
+            if world > 1 and lib_comm:
+                op._check(op.lib.kexp_allreduce_sum_dev(op.ctx, sh.v.data_ptr(), n), "kexp_allreduce_sum_dev")
+        if world == 1 or lib_comm:
+            for _ in range(3):
+                step_fused()
+            op.synchronize()
+            v_f = sh.v.clone()
+            sh.step_dev()
+            op.synchronize()
+            dv = float(torch.linalg.norm(v_f - sh.v) / torch.linalg.norm(sh.v))
+            ks = max(args.steps, 5)
+            ms_f, _ = sh.timed(step_fused, ks)
+            ms_f /= ks
+            fused = {"ms_per_averaged_evaluation": ms_f, "equivalent_applications_per_s": apps_per_step / (ms_f * 1e-3),
+                     "rel_l2_vs_separate_applications": dv,
+                     "what": "forward shared-input batch (all results delivered) + fused Clenshaw weighted average of the "
+                             "backward applications (only their sum is formed)"}
 
     value_indep = value_full = None
-    if rank == 0 and not args.no_roofline:
+    if extras and rank == 0 and world == 1:
         value_indep = plain_variant(shared_basis=False, economise=not args.full_series)
         value_full = plain_variant(shared_basis=False, economise=False)
 
     # ------------------------------------------------------------ e2e through host pointers
     e2e = None
     if not args.no_e2e:
-        def step_host():
-            ce.apply_batch(hx, t, shared=True, out=hY)              # H2D 1 vector, D2H B vectors
-            return ce.apply_average(hX, -t, w, allreduce=False)     # H2D B vectors, D2H 1 vector
-        step_host()
-        barrier()
-        t0 = time.perf_counter()
+        sh.step_host()
+        sh.step_host()
         ksteps = max(2, min(args.steps, 5))
-        for _ in range(ksteps):
-            vh = step_host()
-            if world > 1:
-                tv = torch.from_numpy(vh).to(f"cuda:{local_rank}")
-                dist.all_reduce(tv)
-                vh = tv.cpu().numpy()
-        barrier()
-        e_ms = (time.perf_counter() - t0) * 1e3 / ksteps
-        if world > 1:
-            tt = torch.tensor([e_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e_ms = float(tt.item())
+        _, e_host = sh.timed(sh.step_host, ksteps)
+        e_ms = e_host / ksteps
         e2e = {"value": apps_per_step / (e_ms * 1e-3), "unit": "applications/s",
-               "h2d_bytes_per_step": int(8 * n * (B + 1)), "d2h_bytes_per_step": int(8 * n * (B + 1)),
-               "ms_per_step": e_ms, "timing": "host clock around synchronous C-ABI calls (copies included)"}
+               "h2d_bytes_per_step": int(8 * n * (B + 1)) * world, "d2h_bytes_per_step": int(8 * n * (B + 1)) * world,
+               "ms_per_step": e_ms,
+               "timing": "host clock around the host-pointer C-ABI calls (pinned buffers; the D2H of the forward results overlaps "
+                         "the backward half; all-reduce on the device), barrier + synchronize on both sides, max over ranks"}
 
-    # ------------------------------------------------------------ roofline of the dominant kernel
+    # ------------------------------------------------------------ weak-scaling side measurement (N > 1, strong run)
+    weak = None
+    if extras and world > 1 and not args.weak:
+        shw = Shard(args.samples * world)
+        for _ in range(2):
+            shw.step_dev()
+        kw = max(2, min(args.steps, 3))
+        msw_dev, msw_host = shw.timed(shw.step_dev, kw)
+        msw = (msw_dev if lib_comm else msw_host) / kw
+        weak = {"value": 2 * args.samples * world / (msw * 1e-3), "unit": "applications/s", "samples_per_gpu": args.samples,
+                "ms_per_step": msw, "scaling": "weak"}
+        shw.close()
+
+    # ------------------------------------------------------------ roofline of the dominant kernel (rank 0)
     roofline, kernels = None, None
     if not args.no_roofline and rank == 0:
         peak, peak_src = measured_peak_gbs()
+        op.set_async(False)
         op.set_kernel_timing(True)
         op.stats_reset()
-        ce.apply_dev(b_bwd_in, b_bwd_out, -t)
+        ce.apply_dev(sh.b_in, sh.b_out, -sh.t)
         op.synchronize()
         st_t = op.stats()
+        path_t = int(st_t["solve_path"])
         kernels = {}
         total_ms = 0.0
-        names = ("spmm_K", "cg_init", "spmm_cg", "cheb_update") if args.solver == "chebyshev" else \
-                ("spmm_K", "cg_init", "spmm_cg", "cg_update_xr", "cheb_update")
+        names = ("spmm_K", "cg_init", "spmm_cg", "cheb_update", "misc") if args.solver == "chebyshev" else \
+                ("spmm_K", "cg_init", "spmm_cg", "cg_update_xr", "cheb_update", "misc")
+        Wp = B / sh.b_in.num_panels
         for name in names:
             cs = op.class_stats(name)
             executed = cs["launches"]
             if name in ("spmm_cg", "cg_update_xr", "cg_update_p"):
-                executed = st_t["cg_iterations"]      # launches after convergence return at once
+                executed = st_t["cg_iterations"]      # PCG: launches after convergence return at once
                 if args.solver == "chebyshev":        # K iterations per solve = 1 start kernel + K-1 fused kernels
                     executed = (st_t["cg_iterations"] - st_t["cg_solves"]) if name == "spmm_cg" else 0
-            bytes_launch = cs["bytes_per_col"] * (B / b_bwd_in.num_panels) + cs["matrix_bytes"]
-            if name == "cheb_update":                 # three row-range launches form one pass
+            bytes_launch = cs["bytes_per_col"] * Wp + cs["matrix_bytes"]
+            if name == "cheb_update":                 # the row-range launches of one term form one pass
                 executed = st_t["op_applications"]
-            if name == "spmm_cg" and args.solver == "chebyshev" and cs["launches"] == st_t["cg_solves"] and cs["launches"] > 0:
+            if name == "spmm_cg" and path_t == 2 and cs["launches"] > 0:
                 # cooperative kernel: ONE launch per mass solve = start + (K-1) iterations, matrix staged once
                 executed = cs["launches"]
                 K = st_t["cg_iterations"] / st_t["cg_solves"]
-                Wp = B / b_bwd_in.num_panels
                 bytes_launch = ((K - 1) * 32.0 + 24.0) * op.n_solve * Wp + cs["matrix_bytes"]
-            avg_ms = cs["ms"] / max(executed, 1)
+            if executed <= 0 or cs["ms"] <= 0:
+                continue
+            avg_ms = cs["ms"] / executed
             kernels[name] = {"ms_total": cs["ms"], "launches": int(executed), "avg_us": avg_ms * 1e3,
-                             "algorithmic_bytes": bytes_launch, "gbs": bytes_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else None}
+                             "algorithmic_bytes": bytes_launch, "gbs": bytes_launch / (avg_ms * 1e-3) / 1e9 if bytes_launch > 0 else None}
             total_ms += cs["ms"]
         for k in kernels.values():
             k["share"] = k["ms_total"] / total_ms if total_ms > 0 else None
-        kernels = {k: v for k, v in kernels.items() if v["launches"] > 0}
+        solve_label = {0: "bsr3_spmm_kernel<W,1> (q = S p + fused dots)", 1: "bsr3_cheb_iter_kernel (one Chebyshev iteration of the mass solve per launch)",
+                       2: "cheb_solve_coop_kernel (one whole mass solve per launch)", 3: "cheb_apply_narrow_kernel (one whole apply per launch)"}
         label = {"spmm_K": "bsr3_spmm_kernel<W,0> (T = K~ S)", "cg_init": "cheb_solve_init_kernel / cg_init_kernel",
-                 "spmm_cg": ("cheb_solve_coop_kernel (one whole mass solve per launch)" if args.solver == "chebyshev"
-                             else "bsr3_spmm_kernel<W,1> (q = S p + fused dots)"),
-                 "cg_update_xr": "cg_update_kernel", "cheb_update": "cheb_update_kernel (recurrence + accumulate)"}
+                 "spmm_cg": solve_label.get(path_t, "?"), "cg_update_xr": "cg_update_kernel",
+                 "cheb_update": "cheb_update_kernel (recurrence + accumulate)", "misc": "pack / combine / column sums"}
         for k in kernels:
             kernels[k]["kernel"] = label[k]
-        dom = max(kernels, key=lambda k: kernels[k]["ms_total"])
+        cand = [k for k in kernels if kernels[k]["gbs"]]
+        dom = max(cand, key=lambda k: kernels[k]["ms_total"])
         kd = kernels[dom]
-        roofline = {"bound": "hbm", "kernel": kernels[dom]["kernel"], "achieved": kd["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kd["gbs"] / peak if kd["gbs"] else None, "traffic": None, "peak_source": peak_src,
+        roofline = {"bound": "hbm", "kernel": kd["kernel"], "achieved": kd["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kd["gbs"] / peak, "traffic": None, "peak_source": peak_src,
                     "avg_launch_us": kd["avg_us"], "algorithmic_bytes_per_launch": kd["algorithmic_bytes"],
-                    "share_of_step": kd["share"]}
+                    "share_of_step": kd["share"], "panel_columns": Wp}
         # whole-apply effective bandwidth from the byte model (all kernels)
         model_bytes = sum(k["algorithmic_bytes"] * k["launches"] for k in kernels.values())
         roofline["whole_apply_gbs"] = model_bytes / (total_ms * 1e-3) / 1e9 if total_ms > 0 else None
         roofline["whole_apply_frac"] = roofline["whole_apply_gbs"] / peak if total_ms > 0 else None
         op.set_kernel_timing(False)
-        traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-        if os.path.exists(traffic_file):
-            try:
-                roofline["traffic"] = json.load(open(traffic_file)).get(dom)
-                roofline["note"] = ("traffic = ncu dram bytes per launch (profiles/r01e_summary.md, captured at K = 33 iterations: first read of b and last write of x, "
-                                    "it does not grow with K): the 32-column panel of the mass "
-                                    "solve is L2 resident, so `achieved` is effective (algorithmic) bandwidth, not HBM traffic")
-            except Exception:
-                pass
+        # measured DRAM traffic of the dominant kernel and the measured L2 bandwidth (profiles/, regenerated per round by
+        # profiles/make_traffic_json.py from the ncu --set full capture and profiles/micro/l2_bandwidth.cu)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+            ent = tr.get(dom) if path_t == tr.get("solve_path", 2) and args.ref_level == tr.get("ref_level", 5) else None
+            if isinstance(ent, dict):
+                roofline["traffic"] = ent.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = ent.get("source")
+                if ent.get("l2_bytes_per_launch") and tr.get("l2_peak_gbs"):
+                    l2_gbs = ent["l2_bytes_per_launch"] / (kd["avg_us"] * 1e-6) / 1e9
+                    roofline["l2_achieved_gbs"] = l2_gbs
+                    roofline["l2_peak_gbs"] = tr["l2_peak_gbs"]
+                    roofline["l2_frac"] = l2_gbs / tr["l2_peak_gbs"]
+                roofline["note"] = ("the panel of the mass solve is L2 resident by design, so `achieved`/`frac` are EFFECTIVE (algorithmic) "
+                                    "bandwidth against the HBM copy peak, `traffic` is the measured DRAM traffic per launch (ncu) and "
+                                    "`l2_frac` the measured L2 traffic rate against the measured L2 bandwidth")
+        except Exception:
+            pass
 
     # ------------------------------------------------------------ CPU baseline (rank 0, N = 1)
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
-        times, nthreads, ncheb = cpu_reference_run(sw, L, t, x, cores, 1, 1, nthreads=cores)
+        times, nthreads, ncheb = cpu_reference_run(sw, L, sh.t, x, cores, 1, 1, nthreads=cores)
         cpu = {"value": cores / float(np.mean(times)), "unit": "applications/s", "cores": nthreads, "kind": "port",
                "sample": f"{cores} backward applications (one per host thread), literal 2*ncheb-1={2 * ncheb - 1} solves, "
                          f"block-Jacobi CG rtol 1e-5; oracle/cpu_cheby.c"}
@@ -425,29 +512,35 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "applications/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3) + 1, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if args.weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name, "ncheb": int(ce.ncheb), "L": L, "N": int(n), "applications_per_step": apps_per_step,
-                       "l2": "inputs/outputs of a step ~0.9 GB per GPU (>> 126 MB L2), no explicit flush; inside one mass solve "
-                             "the 32-column panel (3 x 23.6 MB + matrix) is deliberately kept L2 resident, so the roofline "
+                       "window_samples": Btot, "samples_per_gpu": B,
+                       "l2": "inputs/outputs of a step ~0.9 GB at 64 samples per GPU (>> 126 MB L2), no explicit flush; inside one mass "
+                             "solve the 32-column panel (3 x 23.6 MB + matrix) is deliberately kept L2 resident, so the roofline "
                              "figure is effective (algorithmic) bandwidth",
                        "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi {'Chebyshev iteration' if args.solver == 'chebyshev' else 'PCG'} rtol {args.cg_rtol:g}, "
-                                     f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}",
-                       "parallelism": f"samples sharded cyclically (sample k on rank k mod N), {B}/GPU", "panels_per_batch": b_bwd_in.num_panels,
-                       "forward_batch": "shared input: recurrence for ONE column on the common operator + dense re-expansion to the 64 "
+                                     f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}; path: {solve_path}",
+                       "parallelism": f"window of {Btot} samples sharded cyclically (sample k on rank k mod N), {B}/GPU; one all-reduce of N "
+                                      f"doubles per step ({'NCCL on the library stream' if lib_comm else 'torch.distributed'})",
+                       "panels_per_batch": sh.b_in.num_panels,
+                       "forward_batch": "shared input: recurrence for ONE column on the common operator + dense re-expansion to the "
                                         "sample times (exact, DESIGN.md); value_independent_columns = same step without it",
                        "series": ("full reference series for every column" if args.full_series else
                                   "per-column economised re-expansion of the reference series (same polynomial, dropped tail "
                                   "<= 1e-13; t_valid = L/eig = dt*rho); value_full_series = all 29 terms for all 128 columns, "
                                   "no shared-input basis"),
-                       "terms_per_panel": terms_per_panel},
+                       "operator_applications_per_step": terms_per_step},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "parity_vs_single_gpu": parity,
             "value_independent_columns": value_indep, "value_full_series": value_full,
-            "averaged_evaluation_fused": fused,
+            "averaged_evaluation_fused": fused, "weak_scaling": weak,
             "timing": {"device_ms": ms_dev, "host_ms": ms_host},
         }
         print(json.dumps(out))
+    sh.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

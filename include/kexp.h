@@ -44,6 +44,9 @@ typedef struct kexp_stats_t {
                                       its apply repeat itself with more iterations, or fail at max_it) */
     double  worst_rel_residual;    /* largest ||r||/||b|| of any such solve */
     int64_t mass_iterations_per_solve; /* current fixed length of a Chebyshev mass solve / cap of a PCG solve */
+    int64_t solve_path;            /* kernel path of the most recently enqueued (or graph-captured) mass solve: 0 batched PCG,
+                                      1 Chebyshev, one kernel per iteration (bsr3_cheb_iter_kernel), 2 Chebyshev, one cooperative
+                                      kernel per solve (cheb_solve_coop_kernel), 3 persistent narrow-panel apply kernel */
 } kexp_stats_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -136,6 +139,13 @@ int kexp_batch_num_panels(kexp_batch* b);     /* a batch is stored as panels of 
 int kexp_batch_set_order(kexp_batch* b, const int32_t* order);
 int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared);   /* host -> HBM */
 int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy);                        /* HBM -> host */
+/* Asynchronous forms: the device-to-host copy is left in flight on its own stream and overlaps whatever is enqueued
+ * next (the backward half of an averaged evaluation, its uploads); Y is complete after kexp_wait_transfers and must
+ * stay valid until then (pinned memory for a truly asynchronous copy). */
+int kexp_batch_download_async(kexp_batch* b, double* Y, int64_t ldy);
+int kexp_cheby_apply_batch_async(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
+                                 double* Y, int64_t ldy, const double* t, int B);
+int kexp_wait_transfers(kexp_ctx* ctx);
 int kexp_cheby_apply_dev(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t);
 /* device-resident form of kexp_cheby_apply_average_fused; v_dev as in kexp_batch_average_dev */
 int kexp_cheby_average_fused_dev(kexp_ctx* ctx, int id, kexp_batch* in, const double* t, const double* w, double* v_dev);

@@ -20,7 +20,7 @@ class Stats(C.Structure):
                 ("last_max_rel_residual", C.c_double), ("model_bytes", C.c_double),
                 ("spmm_cg_bytes", C.c_double), ("spmm_cg_launches", C.c_int64),
                 ("unconverged_solves", C.c_int64), ("worst_rel_residual", C.c_double),
-                ("mass_iterations_per_solve", C.c_int64)]
+                ("mass_iterations_per_solve", C.c_int64), ("solve_path", C.c_int64)]
 
 
 _p = C.c_void_p
@@ -50,6 +50,9 @@ PROTOTYPES = {
     "kexp_batch_set_order": (C.c_int, [_p, _p]),
     "kexp_batch_upload": (C.c_int, [_p, _p, C.c_int64, C.c_int]),
     "kexp_batch_download": (C.c_int, [_p, _p, C.c_int64]),
+    "kexp_batch_download_async": (C.c_int, [_p, _p, C.c_int64]),
+    "kexp_cheby_apply_batch_async": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, C.c_int]),
+    "kexp_wait_transfers": (C.c_int, [_p]),
     "kexp_cheby_apply_dev": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "kexp_batch_average_dev": (C.c_int, [_p, _p, _p]),
     "kexp_cheby_average_fused_dev": (C.c_int, [_p, C.c_int, _p, _p, _p, _p]),

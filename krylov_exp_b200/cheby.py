@@ -121,8 +121,10 @@ class cheby_exp(object):
         write_back(y, yout)
 
     # ---- batched over the averaging samples --------------------------------------
-    def apply_batch(self, X, t, shared=False, out=None):
-        """Rows of X (B x n) advanced by their own t[k]; shared=True: one x for every t[k]."""
+    def apply_batch(self, X, t, shared=False, out=None, wait=True):
+        """Rows of X (B x n) advanced by their own t[k]; shared=True: one x for every t[k].
+        wait=False leaves the device-to-host copy of `out` in flight (it overlaps the calls that follow); `out` is
+        complete after Operator.wait_transfers() and should be pinned memory."""
         t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
         B = t.shape[0]
         n = self.op.n
@@ -143,8 +145,9 @@ class cheby_exp(object):
               or out.strides[1] != 8 or out.strides[0] % 8 or out.strides[0] < 8 * n or not out.flags.writeable):
             raise ValueError(f"out must be a writeable float64 array of shape ({B}, {n}) with unit inner stride")
         lib = self.op.lib
-        self.op._check(lib.kexp_cheby_apply_batch(self.op.ctx, self.id, _lib.ptr(X), ldx, int(shared),
-                                                  _lib.ptr(out), out.strides[0] // 8, _lib.ptr(t), B), "kexp_cheby_apply_batch")
+        fn = lib.kexp_cheby_apply_batch if wait else lib.kexp_cheby_apply_batch_async
+        self.op._check(fn(self.op.ctx, self.id, _lib.ptr(X), ldx, int(shared),
+                          _lib.ptr(out), out.strides[0] // 8, _lib.ptr(t), B), "kexp_cheby_apply_batch")
         return out
 
     def apply_average(self, X, t, w, shared=False, allreduce=False, fused=False):

@@ -340,9 +340,11 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
                 cudaLaunchKernelEx(&cfg, k, (const int*)A.browptr, (const double*)A.blocks, (const double*)ctx->T, xk, xm,
                                    (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, rtol2, A.diag_first ? 1 : 0, ctx->d_sc, ctx->d_partials, ctx->d_counter);
                 ctx->st_op_apps++;
+                ctx->solve_path = 2;
                 return;
             }
         }
+        ctx->solve_path = 1;
         {
             auto k = cheb_solve_init_kernel<W, kCptVec>;
             int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
@@ -371,6 +373,7 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
         ctx->st_op_apps++;
         return;
     }
+    ctx->solve_path = 0;
     {
         auto k = cg_init_kernel<W, kCptVec>;
         int grid = std::min(std::min(max_grid(ctx, k), red_grid), blocks_for(ntri, LPB));
@@ -799,6 +802,10 @@ int kexp_destroy(kexp_ctx* ctx) {
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->ev_prev) cudaEventDestroy(ctx->ev_prev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
+    if (ctx->ev_unpacked) cudaEventDestroy(ctx->ev_unpacked);
+    if (ctx->ev_d2h_done) cudaEventDestroy(ctx->ev_d2h_done);
+    cudaFree(ctx->d_stage_out);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_chk) cudaEventDestroy(ctx->ev_chk);
@@ -1132,6 +1139,58 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
                                       cudaMemcpyDeviceToHost, ctx->stream));
     }
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return poll_deferred(ctx, true);
+}
+
+// Asynchronous download: the panels are unpacked on the compute stream into a staging buffer of their own, the
+// device-to-host copies run on a separate stream behind them, and the call returns at once -- the copy overlaps
+// whatever is enqueued next (e.g. the backward half of an averaged evaluation and its uploads; PCIe is full duplex).
+// Y must stay valid until kexp_wait_transfers (pinned memory for a truly asynchronous copy).
+int kexp_batch_download_async(kexp_batch* b, double* Y, int64_t ldy) {
+    if (!b || !Y) return 1;
+    kexp_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    if (ldy < ctx->n) return kexp::fail(ctx, "ldy < n");
+    if (b->is_shared && ctx->use_shared_basis) return kexp::fail(ctx, "a shared-input batch holds one vector; nothing to download");
+    if (finish_upload(b)) return 1;
+    const size_t bytes = sizeof(double) * (size_t)ctx->n * b->B;
+    if (!ctx->d2h_stream) {
+        KEXP_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        KEXP_CUDA(cudaEventCreateWithFlags(&ctx->ev_unpacked, cudaEventDisableTiming));
+        KEXP_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h_done, cudaEventDisableTiming));
+    }
+    if (bytes > ctx->stage_out_bytes) {
+        KEXP_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+        KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_stage_out); ctx->d_stage_out = nullptr; ctx->stage_out_bytes = 0;
+        KEXP_CUDA(cudaMalloc(&ctx->d_stage_out, bytes));
+        ctx->stage_out_bytes = bytes;
+    }
+    if (ctx->d2h_pending) KEXP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h_done, 0));   // staging still being read
+    for (size_t p = 0; p < b->panel.size(); ++p)
+        if (unpack_panel(ctx, b->panel[p], ctx->d_stage_out, ctx->n, b->B, (int)p * b->stride, b->panelW[p])) return 1;
+    KEXP_CUDA(cudaEventRecord(ctx->ev_unpacked, ctx->stream));
+    KEXP_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_unpacked, 0));
+    if (b->order.empty()) {
+        KEXP_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, ctx->d_stage_out, sizeof(double) * ctx->n, sizeof(double) * ctx->n, b->B,
+                                    cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    } else {
+        for (int j = 0; j < b->B; ++j)
+            KEXP_CUDA(cudaMemcpyAsync(Y + (size_t)b->order[j] * ldy, ctx->d_stage_out + (size_t)j * ctx->n, sizeof(double) * ctx->n,
+                                      cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    KEXP_CUDA(cudaEventRecord(ctx->ev_d2h_done, ctx->d2h_stream));
+    ctx->d2h_pending = true;
+    return 0;
+}
+
+int kexp_wait_transfers(kexp_ctx* ctx) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (ctx->d2h_pending) {
+        KEXP_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+        ctx->d2h_pending = false;
+    }
     return poll_deferred(ctx, true);
 }
 
@@ -1765,6 +1824,22 @@ int kexp_cheby_apply_batch(kexp_ctx* ctx, int id, const double* X, int64_t ldx, 
     return rc;
 }
 
+// kexp_cheby_apply_batch whose device-to-host copy of Y is left in flight: returns once everything is enqueued and
+// the compute has been checked; Y is complete after kexp_wait_transfers.
+int kexp_cheby_apply_batch_async(kexp_ctx* ctx, int id, const double* X, int64_t ldx, int x_is_shared,
+                                 double* Y, int64_t ldy, const double* t, int B) {
+    if (check_ready(ctx, id)) return 1;
+    if (!X || !Y || !t || B < 1) return kexp::fail(ctx, "bad arguments");
+    if (X == Y) return kexp::fail(ctx, "x and y must not alias (cheby_exp.py:119,127)");
+    kexp_batch *bi = nullptr, *bo = nullptr;
+    int rc = scratch_batches(ctx, B, &bi, &bo);
+    if (!rc) rc = set_scratch_order(ctx, id, bi, bo, t, B);
+    if (!rc) rc = batch_upload_impl(bi, X, ldx, x_is_shared, false);
+    if (!rc) rc = kexp_cheby_apply_dev(ctx, id, bi, bo, t);
+    if (!rc) rc = kexp_batch_download_async(bo, Y, ldy);
+    return rc;
+}
+
 int kexp_cheby_apply(kexp_ctx* ctx, int id, const double* x, double* y, double t) {
     if (!ctx) return 1;
     return kexp_cheby_apply_batch(ctx, id, x, ctx->n, 0, y, ctx->n, &t, 1);
@@ -1962,6 +2037,7 @@ int kexp_stats(kexp_ctx* ctx, kexp_stats_t* out) {
     });
     if (rc) return rc;
     out->mass_iterations_per_solve = ctx->graph_its;
+    out->solve_path = ctx->solve_path;
     if (poll_deferred(ctx, true)) return 1;
     out->op_applications = ctx->st_op_apps;
     out->kernel_launches = ctx->st_launches;

@@ -119,6 +119,7 @@ struct kexp_ctx {
     int unconverged_seen = 0;
     // deferred convergence check (kexp_set_async): the counters of an apply are copied to pinned memory behind it
     // and looked at by the next call that finds the copy finished, at the latest by kexp_synchronize / download
+    int solve_path = -1;           // how the most recently enqueued / captured mass solve runs (kexp_stats_t.solve_path)
     bool async_checks = false;
     kexp::CgScalars* h_sc = nullptr;       // pinned
     cudaEvent_t ev_chk = nullptr;
@@ -182,6 +183,12 @@ struct kexp_ctx {
     int panel_cap = 64;            // widest panel a new batch gets (32 with two lanes)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prev = nullptr;
     cudaStream_t copy_stream = nullptr;   // host->device uploads overlap the compute of the previous panel
+    // asynchronous downloads (kexp_batch_download_async): own staging buffer and stream
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t ev_unpacked = nullptr, ev_d2h_done = nullptr;
+    double* d_stage_out = nullptr;
+    size_t stage_out_bytes = 0;
+    bool d2h_pending = false;
 
     // krylov
     kexp::KrylovState* kry = nullptr;

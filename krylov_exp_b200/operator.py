@@ -221,6 +221,10 @@ class Operator:
         later call (at the latest synchronize / download / stats), which raises if a solve missed rtol."""
         self._check(self.lib.kexp_set_async(self.ctx, int(bool(on))), "kexp_set_async")
 
+    def wait_transfers(self):
+        """Completes the asynchronous device-to-host copies (cheby_exp.apply_batch(wait=False), DeviceBatch.download(wait=False))."""
+        self._check(self.lib.kexp_wait_transfers(self.ctx), "kexp_wait_transfers")
+
     def synchronize(self):
         self._check(self.lib.kexp_synchronize(self.ctx), "kexp_synchronize")
 
@@ -337,11 +341,12 @@ class DeviceBatch:
             ld = X.strides[0] // 8
         self.op._check(self.op.lib.kexp_batch_upload(self.handle, X.ctypes.data_as(C.c_void_p), ld, int(shared)), "kexp_batch_upload")
 
-    def download(self, out=None):
+    def download(self, out=None, wait=True):
         if out is None:
             out = np.empty((self.B, self.op.n))
-        assert out.shape == (self.B, self.op.n) and out.strides[1] == 8
-        self.op._check(self.op.lib.kexp_batch_download(self.handle, out.ctypes.data_as(C.c_void_p), out.strides[0] // 8), "kexp_batch_download")
+        assert out.dtype == np.float64 and out.shape == (self.B, self.op.n) and out.strides[1] == 8
+        fn = self.op.lib.kexp_batch_download if wait else self.op.lib.kexp_batch_download_async
+        self.op._check(fn(self.handle, out.ctypes.data_as(C.c_void_p), out.strides[0] // 8), "kexp_batch_download")
         return out
 
     def average_into(self, w, v_dev_ptr):
