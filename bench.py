@@ -455,6 +455,14 @@ def main():
                 executed = cs["launches"]
                 K = st_t["cg_iterations"] / st_t["cg_solves"]
                 bytes_launch = ((K - 1) * 32.0 + 24.0) * op.n_solve * Wp + cs["matrix_bytes"]
+            if name == "spmm_cg" and path_t == 3 and cs["launches"] > 0:
+                # persistent narrow-panel kernel: ONE launch per apply = all terms (K~ product, mass solve, updates)
+                executed = cs["launches"]
+                K = st_t["cg_iterations"] / st_t["cg_solves"]
+                terms = st_t["op_applications"] / cs["launches"]
+                mk = op.class_stats("spmm_K")["matrix_bytes"]
+                mr = op.class_stats("cheb_update")["matrix_bytes"]
+                bytes_launch = terms * ((16.0 * n + 40.0 * n) * Wp + mk + mr + ((K - 1) * 32.0 + 24.0) * op.n_solve * Wp)
             if executed <= 0 or cs["ms"] <= 0:
                 continue
             avg_ms = cs["ms"] / executed

@@ -142,12 +142,12 @@ class cheby_exp(object):
         if out is None:
             out = np.empty((B, n))
         elif (not isinstance(out, np.ndarray) or out.dtype != np.float64 or out.shape != (B, n)
-              or out.strides[1] != 8 or out.strides[0] % 8 or out.strides[0] < 8 * n or not out.flags.writeable):
+              or out.strides[1] != 8 or out.strides[0] % 8 or (B > 1 and out.strides[0] < 8 * n) or not out.flags.writeable):
             raise ValueError(f"out must be a writeable float64 array of shape ({B}, {n}) with unit inner stride")
         lib = self.op.lib
         fn = lib.kexp_cheby_apply_batch if wait else lib.kexp_cheby_apply_batch_async
         self.op._check(fn(self.op.ctx, self.id, _lib.ptr(X), ldx, int(shared),
-                          _lib.ptr(out), out.strides[0] // 8, _lib.ptr(t), B), "kexp_cheby_apply_batch")
+                          _lib.ptr(out), out.strides[0] // 8 if B > 1 else n, _lib.ptr(t), B), "kexp_cheby_apply_batch")
         return out
 
     def apply_average(self, X, t, w, shared=False, allreduce=False, fused=False):

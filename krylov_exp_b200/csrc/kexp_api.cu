@@ -107,8 +107,9 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
         KEXP_CUDA(cudaMemcpy(d.rowmap, rowmap.data(), sizeof(int) * (size_t)nbr, cudaMemcpyHostToDevice));
     }
     d.nbr = nbr; d.nblocks = nblocks; d.max_bpr = max_bpr;
+    d.h_browptr = browptr;
     d.diag_first = force && nrows == ncols && all_diag;
-    if (max_bpr > kSpmmSmemBlocks) { cudaFree(d.browptr); cudaFree(d.blocks); d.browptr = nullptr; d.blocks = nullptr; }
+    if (max_bpr > kSpmmSmemBlocks) { cudaFree(d.browptr); cudaFree(d.blocks); d.browptr = nullptr; d.blocks = nullptr; d.h_browptr.clear(); }
     return 0;
 }
 
@@ -125,6 +126,7 @@ int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp
     KEXP_CUDA(cudaMemcpy(d.rowptr, rp, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.col, ci, sizeof(int) * (size_t)d.nnz, cudaMemcpyHostToDevice));
     KEXP_CUDA(cudaMemcpy(d.val, v, sizeof(double) * (size_t)d.nnz, cudaMemcpyHostToDevice));
+    d.h_rowptr.assign(rp, rp + nrows + 1);
     return build_bsr3(ctx, d, nrows, ncols, rp, ci, v, force_bsr);
 }
 
@@ -493,7 +495,27 @@ void enqueue_cheby(kexp_ctx* ctx, const PanelPlan& plan) {
         default: return kexp::fail(ctx, "unsupported panel width"); \
     }
 
+// iterations and squared tolerance of the mass solve of a term whose tolerance is relaxed by `relax`
+inline int cheb_iterations(const kexp_ctx* ctx, double relax) {
+    const double sigma1 = (ctx->cheb_hi + ctx->cheb_lo) / (ctx->cheb_hi - ctx->cheb_lo);
+    return std::max(2, ctx->graph_its - (int)std::floor(std::log(relax) / std::acosh(sigma1)));
+}
+
 int run_cheby_panel(kexp_ctx* ctx, int id, int W, const PanelPlan& plan) {
+    if (narrow_eligible(ctx, W)) {
+        // narrow panels are latency bound: the whole apply is ONE persistent cooperative kernel (kexp_narrow.cu)
+        std::vector<int> kterm((size_t)plan.M + 1, 2);
+        std::vector<double> r2((size_t)plan.M + 1, 0.0);
+        for (int n = 1; n <= plan.M; ++n) {
+            const double relax = ctx->use_relax ? plan.relax[n] : 1.0;
+            kterm[n] = cheb_iterations(ctx, relax);
+            r2[n] = (ctx->rtol * relax) * (ctx->rtol * relax);
+        }
+        TimedLaunch tl(ctx, KC_SPMM_CG);
+        if (launch_narrow_apply(ctx, W, plan.M, 0, kterm.data(), r2.data(), ctx->capture_basis, nullptr)) return 1;
+        ctx->st_op_apps += plan.M;
+        return 0;
+    }
     if (ctx->timing || !ctx->use_graph) {
         DISPATCH_W(W, enqueue_cheby<kW>(ctx, plan));
         KEXP_CUDA(cudaGetLastError());
@@ -749,6 +771,8 @@ int kexp_create(kexp_ctx** out, int device) {
     const char* ln = getenv("KEXP_LANES");
     if (ln && ln[0] == '1') { ctx->nlanes = 1; ctx->panel_cap = 64; }
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
+    if (const char* nw = getenv("KEXP_NARROW")) ctx->use_narrow = (nw[0] != '0');
+    if (const char* nm = getenv("KEXP_NARROW_MAXW")) { const int v = atoi(nm); if (v >= 2 && v <= 16) ctx->narrow_max_w = v; }
     const char* rl = getenv("KEXP_RELAX");
     if (rl) ctx->use_relax = (rl[0] == '1');
     const char* co = getenv("KEXP_COOP");
@@ -793,6 +817,7 @@ int kexp_destroy(kexp_ctx* ctx) {
                       ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_v, ctx->d_basis, ctx->d_D};
     for (double* b : bufs) cudaFree(b);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sc); cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_nk); cudaFree(ctx->d_nrtol2); cudaFree(ctx->d_npartials);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1441,6 +1466,20 @@ static int cheby_apply_shared(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch*
 // ---------------------------------------------------------------------------------------------
 static int run_clenshaw(kexp_ctx* ctx, int id, const PanelPlan& plan) {
     constexpr int W = 2;
+    if (narrow_eligible(ctx, W)) {
+        // step j = 1..M of the persistent kernel runs Clenshaw index m = M - j (relaxation is stored by m)
+        std::vector<int> kterm((size_t)plan.M + 1, 2);
+        std::vector<double> r2((size_t)plan.M + 1, 0.0);
+        for (int j = 1; j <= plan.M; ++j) {
+            const double relax = ctx->use_relax ? plan.relax[plan.M - j] : 1.0;
+            kterm[j] = cheb_iterations(ctx, relax);
+            r2[j] = (ctx->rtol * relax) * (ctx->rtol * relax);
+        }
+        TimedLaunch tl(ctx, KC_SPMM_CG);
+        if (launch_narrow_apply(ctx, W, plan.M, 1, kterm.data(), r2.data(), true, nullptr)) return 1;
+        ctx->st_op_apps += plan.M;
+        return 0;
+    }
     if (ctx->timing || !ctx->use_graph) {
         enqueue_clenshaw<W>(ctx, plan);
         KEXP_CUDA(cudaGetLastError());

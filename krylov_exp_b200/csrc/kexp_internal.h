@@ -26,6 +26,8 @@ struct DevCsr {
     int max_bpr = 1;               // most blocks in any block row
     bool diag_first = false;       // every block row starts with its diagonal block
     int64_t nblocks = 0;
+    std::vector<int> h_browptr;    // host copy of browptr (stored row order): shared-memory budgeting of the persistent kernels
+    std::vector<int> h_rowptr;     // host copy of rowptr
     bool bsr() const { return blocks != nullptr; }
     double bytes() const {
         return bsr() ? 80.0 * (double)nblocks + 4.0 * (double)(nbr + 1) : 12.0 * (double)nnz + 4.0 * (double)(nrows + 1);
@@ -119,6 +121,12 @@ struct kexp_ctx {
     int unconverged_seen = 0;
     // deferred convergence check (kexp_set_async): the counters of an apply are copied to pinned memory behind it
     // and looked at by the next call that finds the copy finished, at the latest by kexp_synchronize / download
+    // persistent narrow-panel apply kernel (kexp_narrow.cu)
+    bool use_narrow = true;        // KEXP_NARROW=0: always the multi-launch path
+    int narrow_max_w = 8;          // widest panel that takes it (KEXP_NARROW_MAXW)
+    int* d_nk = nullptr;           // per-step iteration counts
+    double* d_nrtol2 = nullptr;    // per-step squared tolerances
+    double* d_npartials = nullptr; // per-CTA block sums
     int solve_path = -1;           // how the most recently enqueued / captured mass solve runs (kexp_stats_t.solve_path)
     bool async_checks = false;
     kexp::CgScalars* h_sc = nullptr;       // pinned
@@ -221,6 +229,9 @@ int upload_csr(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int32_t* rp
 void free_csr(DevCsr& d);
 int pick_W(int B);
 void krylov_free(kexp_ctx* ctx);
+// kexp_narrow.cu
+bool narrow_eligible(kexp_ctx* ctx, int W);
+int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm, const double* rtol2, bool with_basis, const double** result);
 }  // namespace kexp
 
 #define KEXP_CUDA(call)                                                                       \

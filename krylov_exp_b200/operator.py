@@ -336,9 +336,9 @@ class DeviceBatch:
         else:
             X = np.atleast_2d(X)
             assert X.shape == (self.B, self.op.n), (X.shape, self.B, self.op.n)
-            if X.strides[1] != 8 or X.strides[0] % 8:
+            if X.strides[1] != 8 or X.strides[0] % 8 or (self.B > 1 and X.strides[0] < 8 * self.op.n):
                 X = np.ascontiguousarray(X)
-            ld = X.strides[0] // 8
+            ld = X.strides[0] // 8 if self.B > 1 else self.op.n     # a single row: NumPy's stride[0] is arbitrary (0 for x[None, :])
         self.op._check(self.op.lib.kexp_batch_upload(self.handle, X.ctypes.data_as(C.c_void_p), ld, int(shared)), "kexp_batch_upload")
 
     def download(self, out=None, wait=True):
@@ -346,7 +346,9 @@ class DeviceBatch:
             out = np.empty((self.B, self.op.n))
         assert out.dtype == np.float64 and out.shape == (self.B, self.op.n) and out.strides[1] == 8
         fn = self.op.lib.kexp_batch_download if wait else self.op.lib.kexp_batch_download_async
-        self.op._check(fn(self.handle, out.ctypes.data_as(C.c_void_p), out.strides[0] // 8), "kexp_batch_download")
+        ld = out.strides[0] // 8 if self.B > 1 else self.op.n
+        assert ld >= self.op.n
+        self.op._check(fn(self.handle, out.ctypes.data_as(C.c_void_p), ld), "kexp_batch_download")
         return out
 
     def average_into(self, w, v_dev_ptr):

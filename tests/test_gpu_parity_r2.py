@@ -41,7 +41,8 @@ def _m1_inputs(sw, B, seed=1234):
 # ------------------------------------------------------------------------------------------------
 # (a) per-iteration mass-solve path and the other environment-switched variants
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("env,path", [({"KEXP_COOP": "0"}, 1), ({"KEXP_COOP": "0", "KEXP_NO_GRAPH": "1"}, 1),
+@pytest.mark.parametrize("env,path", [({"KEXP_COOP": "0", "KEXP_NARROW": "0"}, 1), ({"KEXP_COOP": "0", "KEXP_NO_GRAPH": "1", "KEXP_NARROW": "0"}, 1),
+                                      ({"KEXP_NARROW": "0"}, 2), ({"KEXP_NARROW_MAXW": "16", "KEXP_PANEL_CAP": "16"}, 3),
                                       ({"KEXP_LANES": "2"}, None), ({"KEXP_PANEL_CAP": "16"}, None),
                                       ({"KEXP_RELAX": "0", "KEXP_PDL": "0"}, None)])
 def test_switched_variants_ref3_against_oracle(sw3, monkeypatch, env, path):
@@ -343,4 +344,94 @@ def test_async_mode_defers_the_check_not_the_error(sw2):
     assert np.array_equal(bo.download(), Y_sync)
     op.set_async(False)
     bi.close(); bo.close()
+    op.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# persistent narrow-panel apply kernel (kexp_narrow.cu) against the multi-launch path and the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 3, 4, 7, 8])
+def test_narrow_kernel_equals_multi_launch_path(sw3, monkeypatch, B):
+    """Same rows, same order of operations: the persistent kernel must reproduce the multi-launch path to round-off
+    (forward recurrence, shared-input basis run, fused Clenshaw average), with the same iteration counts."""
+    import krylov_exp_b200 as kx
+    sw = sw3
+    dt, rho = 3600.0, 1.0
+    L = kx.EIGS[0] * dt * rho
+    t, w = kx.sample_times_weights(B, dt, rho)
+    x, X = _m1_inputs(sw, B)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KEXP_NARROW", mode)
+        op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-12, max_it=60, solver="chebyshev")
+        ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L, spectral_radius=kx.EIGS[0])
+        Y = ce.apply_batch(X, -t)
+        path = op.stats()["solve_path"]
+        F = ce.apply_batch(x, t, shared=True)
+        v = ce.apply_average(X, -t, w, fused=True)
+        st = op.stats()
+        out[mode] = (Y, F, v, path, st["cg_iterations"], st["cg_solves"], st["unconverged_solves"])
+        op.close()
+    assert out["1"][3] == 3 and out["0"][3] in (1, 2)
+    assert out["1"][4:] == out["0"][4:]
+    M = sw.M()
+    for i in range(3):
+        a, b = np.atleast_2d(out["1"][i]), np.atleast_2d(out["0"][i])
+        assert max(_relM(M, a[k], b[k]) for k in range(a.shape[0])) < 1e-14, i
+
+
+@pytest.mark.parametrize("condense", [True, False])
+def test_narrow_kernel_against_oracle(sw3, condense):
+    """Both operator plans (statically condensed; plain K, M_u, M_eta^-1 with the 3x3 depth blocks in the epilogue)."""
+    import krylov_exp_b200 as kx
+    from oracle import coeffs, cheby_ref
+    sw = sw3
+    dt, rho, B = 5400.0, 1.0, 6
+    L = kx.EIGS[0] * dt * rho
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13, max_it=80, solver="chebyshev", condense=condense)
+    ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L)
+    t, w = kx.sample_times_weights(B, dt, rho)
+    x, X = _m1_inputs(sw, B)
+    Y = ce.apply_batch(X, -t)
+    assert op.stats()["solve_path"] == 3
+    c, n = coeffs.cheby_coeffs(10000, 1e-8, L)
+    a = coeffs.real_recurrence_coeffs(c, n)
+    lu = splu(sw.M().tocsc())
+    ref = cheby_ref.apply_batch(a, L, lambda V: lu.solve(sw.K @ V), X.T, -t).T
+    M = sw.M()
+    assert max(_relM(M, Y[k], ref[k]) for k in range(B)) < TOL
+    y1 = np.empty(sw.n)
+    ce.apply(X[2], y1, -t[2])                              # the reference's own call form: B = 1
+    assert _relM(M, y1, ref[2]) < TOL
+    op.close()
+
+
+def test_narrow_kernel_ref5_columns_against_cpu_port():
+    """The strong-scaling share of M1 (8 of the 64 samples on one GPU) through the persistent kernel at full size."""
+    import krylov_exp_b200 as kx
+    from oracle import coeffs, norms
+    from oracle.cpu_port import CpuCheby
+    sw = get_sw(5)
+    DT, RHO = 900.0, 1.0
+    eig = kx.EIGS[2]
+    L = eig * DT * RHO
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-11, max_it=40, solver="chebyshev")
+    ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L, spectral_radius=eig)
+    t_all, w_all = kx.sample_times_weights(64, DT, RHO)
+    cols = np.arange(5, 64, 8)
+    t = np.ascontiguousarray(t_all[cols])
+    x, Xall = _m1_inputs(sw, 64)
+    X = Xall[cols]
+    Y = ce.apply_batch(X, -t)
+    assert op.stats()["solve_path"] == 3
+    F = ce.apply_batch(x, t, shared=True)
+    c, n = coeffs.cheby_coeffs(10000, 1e-8, L)
+    a = coeffs.real_recurrence_coeffs(c, n)
+    cpu = CpuCheby(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13)
+    ref, _ = cpu.apply_batch(a, n, L, X, -t)
+    reff, _ = cpu.apply_batch(a, n, L, x[None, :], t, shared=True)
+    for k in range(len(cols)):
+        assert max(norms.calculate_norm(sw, Y[k], ref[k])) < TOL, k
+        assert max(norms.calculate_norm(sw, F[k], reff[k])) < TOL, k
+    assert op.stats()["unconverged_solves"] == 0
     op.close()
