@@ -44,6 +44,8 @@ typedef struct kexp_stats_t {
                                       its apply repeat itself with more iterations, or fail at max_it) */
     double  worst_rel_residual;    /* largest ||r||/||b|| of any such solve */
     int64_t mass_iterations_per_solve; /* current fixed length of a Chebyshev mass solve / cap of a PCG solve */
+    int64_t h2d_vector_bytes;      /* state-vector bytes copied host -> device / device -> host by the batch and host-pointer */
+    int64_t d2h_vector_bytes;      /* entry points since last reset (a device-resident time step keeps both at 0) */
     int64_t solve_path;            /* kernel path of the most recently enqueued (or graph-captured) mass solve: 0 batched PCG,
                                       1 Chebyshev, one kernel per iteration (bsr3_cheb_iter_kernel), 2 Chebyshev, one cooperative
                                       kernel per solve (cheb_solve_coop_kernel), 3 persistent narrow-panel apply kernel */
@@ -139,6 +141,14 @@ int kexp_batch_num_panels(kexp_batch* b);     /* a batch is stored as panels of 
 int kexp_batch_set_order(kexp_batch* b, const int32_t* order);
 int kexp_batch_upload(kexp_batch* b, const double* X, int64_t ldx, int x_is_shared);   /* host -> HBM */
 int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy);                        /* HBM -> host */
+/* The same with DEVICE arrays in the caller's layout (B vectors of n doubles, user dof order, vector k at d + k*ld; e.g. a
+ * torch tensor): enqueued on the library's stream, no host copy, no synchronisation.  Together with kexp_get_stream this
+ * keeps a whole averaged time step (timestepping_methods.py:34-77) in HBM: the nonlinear slow right-hand side
+ * (SlowSolver.solve(), averaged_sw_explicit.py:177-213) runs as the caller's own device code between
+ * kexp_batch_export_dev and kexp_batch_upload_dev. */
+int kexp_batch_upload_dev(kexp_batch* b, const double* d_X, int64_t ldx, int x_is_shared);
+int kexp_batch_export_dev(kexp_batch* b, double* d_Y, int64_t ldy);
+int kexp_get_stream(kexp_ctx* ctx, void** cuda_stream_out);
 /* Asynchronous forms: the device-to-host copy is left in flight on its own stream and overlaps whatever is enqueued
  * next (the backward half of an averaged evaluation, its uploads); Y is complete after kexp_wait_transfers and must
  * stay valid until then (pinned memory for a truly asynchronous copy). */
@@ -193,6 +203,12 @@ int kexp_set_krylov_operator(kexp_ctx* ctx, double gamma,
  * (the "Residual" prints of krylov_exp.py:95-101) or NULL to skip that diagnostic. */
 int kexp_krylov_apply(kexp_ctx* ctx, const double* x, double* y, double t, int kdim, int its,
                       double* H_out, double* u_out, double* residuals_out);
+/* B sample times at once.  x_is_shared != 0: the shift-and-invert Krylov space does not depend on t, so ONE Arnoldi
+ * process serves every t_k (only expm(-t_k H1) e1 and the final combination differ); distinct inputs run their Arnoldi
+ * processes back to back on the device queue.  The Arnoldi loop itself never waits for the host: ||w||_M, H and the
+ * normalisation scalars stay on the device, breakdown / non-convergence are recorded there and reported at the end. */
+int kexp_krylov_apply_batch(kexp_ctx* ctx, const double* X, int64_t ldx, int x_is_shared, double* Y, int64_t ldy,
+                            const double* t, int B, int kdim, int its);
 /* device small dense expm (Pade-13 scaling and squaring), exposed for tests:
  * E = expm(A), A m x m row-major, m <= 64 */
 int kexp_dense_expm(kexp_ctx* ctx, const double* A, int m, double* E);

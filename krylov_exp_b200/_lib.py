@@ -20,7 +20,8 @@ class Stats(C.Structure):
                 ("last_max_rel_residual", C.c_double), ("model_bytes", C.c_double),
                 ("spmm_cg_bytes", C.c_double), ("spmm_cg_launches", C.c_int64),
                 ("unconverged_solves", C.c_int64), ("worst_rel_residual", C.c_double),
-                ("mass_iterations_per_solve", C.c_int64), ("solve_path", C.c_int64)]
+                ("mass_iterations_per_solve", C.c_int64), ("h2d_vector_bytes", C.c_int64), ("d2h_vector_bytes", C.c_int64),
+                ("solve_path", C.c_int64)]
 
 
 _p = C.c_void_p
@@ -50,6 +51,9 @@ PROTOTYPES = {
     "kexp_batch_set_order": (C.c_int, [_p, _p]),
     "kexp_batch_upload": (C.c_int, [_p, _p, C.c_int64, C.c_int]),
     "kexp_batch_download": (C.c_int, [_p, _p, C.c_int64]),
+    "kexp_batch_upload_dev": (C.c_int, [_p, _p, C.c_int64, C.c_int]),
+    "kexp_batch_export_dev": (C.c_int, [_p, _p, C.c_int64]),
+    "kexp_get_stream": (C.c_int, [_p, C.POINTER(_p)]),
     "kexp_batch_download_async": (C.c_int, [_p, _p, C.c_int64]),
     "kexp_cheby_apply_batch_async": (C.c_int, [_p, C.c_int, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, C.c_int]),
     "kexp_wait_transfers": (C.c_int, [_p]),
@@ -67,6 +71,7 @@ PROTOTYPES = {
     "kexp_spmm_K_dev": (C.c_int, [_p, _p, _p]),
     "kexp_set_krylov_operator": (C.c_int, [_p, C.c_double] + [_p] * 12 + [C.c_double, C.c_int]),
     "kexp_krylov_apply": (C.c_int, [_p, _p, _p, C.c_double, C.c_int, C.c_int, _p, _p, _p]),
+    "kexp_krylov_apply_batch": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, C.c_int, C.c_int, C.c_int]),
     "kexp_dense_expm": (C.c_int, [_p, _p, C.c_int, _p]),
     "kexp_comm_unique_id": (C.c_int, [_p]),
     "kexp_comm_init": (C.c_int, [_p, _p, C.c_int, C.c_int]),

@@ -729,6 +729,7 @@ int for_each_lane(kexp_ctx* ctx, F f) {     // run f with every allocated lane a
 extern "C" {
 
 static int poll_deferred(kexp_ctx* ctx, bool block);      // deferred convergence check of asynchronous applies (below)
+static bool panels_unset(const kexp_batch* b);
 static int unconverged_error(kexp_ctx* ctx, double worst, bool deferred);
 static void raise_iterations(kexp_ctx* ctx);
 
@@ -755,6 +756,10 @@ int kexp_create(kexp_ctx** out, int device) {
         fprintf(stderr, "kexp_create: device %d is sm_%d%d; this build targets sm_100a (B200)\n", device, prop.major, prop.minor);
         delete ctx;
         return 5;
+    }
+    {
+        static int next_slot = 0;                   // constant-memory argument slots of the persistent kernel (kexp_narrow.cu)
+        ctx->narrow_slot = (next_slot++) % 8;
     }
     ctx->lane_store[0].allocated = true;
     bool ok = alloc_lane_scalars(ctx) == 0;
@@ -1087,6 +1092,7 @@ static int batch_upload_impl(kexp_batch* b, const double* X, int64_t ldx, int x_
     if (swap_lane(ctx, 0)) return 1;
     const int nvec = x_is_shared ? 1 : b->B;
     if (!x_is_shared && ldx < ctx->n) return kexp::fail(ctx, "ldx < n");
+    ctx->st_h2d_bytes += (int64_t)sizeof(double) * ctx->n * nvec;
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * nvec)) return 1;
     b->is_shared = x_is_shared != 0;
     if (finish_upload(b)) return 1;
@@ -1153,6 +1159,7 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
     if (b->is_shared && ctx->use_shared_basis) return kexp::fail(ctx, "a shared-input batch holds one vector; nothing to download");
     if (finish_upload(b)) return 1;
     if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
+    ctx->st_d2h_bytes += (int64_t)sizeof(double) * ctx->n * b->B;
     for (size_t p = 0; p < b->panel.size(); ++p)
         if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * b->stride, b->panelW[p])) return 1;
     if (b->order.empty()) {
@@ -1167,6 +1174,71 @@ int kexp_batch_download(kexp_batch* b, double* Y, int64_t ldy) {
     return poll_deferred(ctx, true);
 }
 
+// Device-resident vectors in the caller's layout (B vectors of n doubles in user dof order, vector k at d + k*ld; e.g. a
+// torch tensor): device -> panels and panels -> device, enqueued on the library's stream, no host copy, no synchronisation.
+int kexp_batch_upload_dev(kexp_batch* b, const double* d_X, int64_t ldx, int x_is_shared) {
+    if (!b || !d_X) return 1;
+    kexp_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    if (swap_lane(ctx, 0)) return 1;
+    if (!x_is_shared && ldx < ctx->n) return kexp::fail(ctx, "ldx < n");
+    if (finish_upload(b)) return 1;
+    b->is_shared = x_is_shared != 0;
+    if (b->is_shared) {
+        if (ctx->use_shared_basis) {
+            if (!b->shared_vec) KEXP_CUDA(cudaMalloc(&b->shared_vec, sizeof(double) * 2 * (size_t)ctx->n));
+            return pack_panel(ctx, d_X, ctx->n, 1, 1, 0, 2, b->shared_vec);
+        }
+        for (size_t p = 0; p < b->panel.size(); ++p)
+            if (pack_panel(ctx, d_X, ctx->n, 1, b->B, (int)p * b->stride, b->panelW[p], b->panel[p])) return 1;
+        return 0;
+    }
+    const double* src = d_X;
+    int64_t ld = ldx;
+    if (!b->order.empty()) {                       // stored column j holds the caller's column order[j]
+        if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
+        for (int j = 0; j < b->B; ++j)
+            KEXP_CUDA(cudaMemcpyAsync(ctx->d_stage + (size_t)j * ctx->n, d_X + (size_t)b->order[j] * ldx, sizeof(double) * ctx->n,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+        src = ctx->d_stage; ld = ctx->n;
+    }
+    for (size_t p = 0; p < b->panel.size(); ++p)
+        if (pack_panel(ctx, src, ld, 0, b->B, (int)p * b->stride, b->panelW[p], b->panel[p])) return 1;
+    KEXP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kexp_batch_export_dev(kexp_batch* b, double* d_Y, int64_t ldy) {
+    if (!b || !d_Y) return 1;
+    kexp_ctx* ctx = b->ctx;
+    cudaSetDevice(ctx->device);
+    if (ldy < ctx->n) return kexp::fail(ctx, "ldy < n");
+    if (panels_unset(b)) return kexp::fail(ctx, "a shared-input batch holds one vector; nothing to export");
+    if (finish_upload(b)) return 1;
+    if (b->order.empty()) {
+        for (size_t p = 0; p < b->panel.size(); ++p)
+            if (unpack_panel(ctx, b->panel[p], d_Y, ldy, b->B, (int)p * b->stride, b->panelW[p])) return 1;
+    } else {
+        if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * b->B)) return 1;
+        for (size_t p = 0; p < b->panel.size(); ++p)
+            if (unpack_panel(ctx, b->panel[p], ctx->d_stage, ctx->n, b->B, (int)p * b->stride, b->panelW[p])) return 1;
+        for (int j = 0; j < b->B; ++j)
+            KEXP_CUDA(cudaMemcpyAsync(d_Y + (size_t)b->order[j] * ldy, ctx->d_stage + (size_t)j * ctx->n, sizeof(double) * ctx->n,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    KEXP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// The library's compute stream (cudaStream_t), so that a caller can enqueue its own device work -- the nonlinear slow
+// right-hand side between the two exponentials, stage combinations -- in order with the library's, without host joins.
+int kexp_get_stream(kexp_ctx* ctx, void** stream_out) {
+    if (!ctx || !stream_out) return 1;
+    if (swap_lane(ctx, 0)) return 1;
+    *stream_out = (void*)ctx->stream;
+    return 0;
+}
+
 // Asynchronous download: the panels are unpacked on the compute stream into a staging buffer of their own, the
 // device-to-host copies run on a separate stream behind them, and the call returns at once -- the copy overlaps
 // whatever is enqueued next (e.g. the backward half of an averaged evaluation and its uploads; PCIe is full duplex).
@@ -1179,6 +1251,7 @@ int kexp_batch_download_async(kexp_batch* b, double* Y, int64_t ldy) {
     if (b->is_shared && ctx->use_shared_basis) return kexp::fail(ctx, "a shared-input batch holds one vector; nothing to download");
     if (finish_upload(b)) return 1;
     const size_t bytes = sizeof(double) * (size_t)ctx->n * b->B;
+    ctx->st_d2h_bytes += (int64_t)bytes;
     if (!ctx->d2h_stream) {
         KEXP_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         KEXP_CUDA(cudaEventCreateWithFlags(&ctx->ev_unpacked, cudaEventDisableTiming));
@@ -1898,6 +1971,7 @@ int kexp_cheby_apply_average(kexp_ctx* ctx, int id, const double* X, int64_t ldx
     if (!rc) rc = kexp_batch_average_dev(bo, w, ctx->d_v);
     if (!rc && do_allreduce) rc = kexp_allreduce_sum_dev(ctx, ctx->d_v, ctx->n);
     if (!rc) {
+        ctx->st_d2h_bytes += (int64_t)sizeof(double) * ctx->n;
         cudaError_t e = cudaMemcpyAsync(v_out, ctx->d_v, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = kexp::fail(ctx, cudaGetErrorString(e));
@@ -1939,6 +2013,7 @@ int kexp_cheby_apply_average_fused(kexp_ctx* ctx, int id, const double* X, int64
     if (!rc) rc = kexp_cheby_average_fused_dev(ctx, id, bi, t, w, ctx->d_v);
     if (!rc && do_allreduce) rc = kexp_allreduce_sum_dev(ctx, ctx->d_v, ctx->n);
     if (!rc) {
+        ctx->st_d2h_bytes += (int64_t)sizeof(double) * ctx->n;
         cudaError_t e = cudaMemcpyAsync(v_out, ctx->d_v, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = kexp::fail(ctx, cudaGetErrorString(e));
@@ -2076,6 +2151,8 @@ int kexp_stats(kexp_ctx* ctx, kexp_stats_t* out) {
     });
     if (rc) return rc;
     out->mass_iterations_per_solve = ctx->graph_its;
+    out->h2d_vector_bytes = ctx->st_h2d_bytes;
+    out->d2h_vector_bytes = ctx->st_d2h_bytes;
     out->solve_path = ctx->solve_path;
     if (poll_deferred(ctx, true)) return 1;
     out->op_applications = ctx->st_op_apps;
@@ -2099,6 +2176,7 @@ int kexp_stats_reset(kexp_ctx* ctx) {
     });
     if (rc) return rc;
     ctx->st_op_apps = 0; ctx->st_launches = 0; ctx->st_bicg = 0;
+    ctx->st_h2d_bytes = 0; ctx->st_d2h_bytes = 0;
     for (int i = 0; i < KC_COUNT; ++i) ctx->cls[i] = ClassStat();
     return 0;
 }

@@ -124,6 +124,7 @@ struct kexp_ctx {
     // persistent narrow-panel apply kernel (kexp_narrow.cu)
     bool use_narrow = true;        // KEXP_NARROW=0: always the multi-launch path
     int narrow_max_w = 8;          // widest panel that takes it (KEXP_NARROW_MAXW)
+    int narrow_slot = 0;           // constant-memory argument slot of this context
     int* d_nk = nullptr;           // per-step iteration counts
     double* d_nrtol2 = nullptr;    // per-step squared tolerances
     double* d_npartials = nullptr; // per-CTA block sums
@@ -180,6 +181,7 @@ struct kexp_ctx {
     struct kexp_batch* tmp_out = nullptr;
     double last_ms = 0.0;
     int64_t st_op_apps = 0, st_launches = 0, st_bicg = 0;
+    int64_t st_h2d_bytes = 0, st_d2h_bytes = 0;    // state-vector bytes copied between host and device since reset
     unsigned long long base_iters = 0, base_solves = 0;
     std::map<const void*, int> occ_cache;
 

@@ -40,6 +40,12 @@ struct KrylovState {
     double* d_u = nullptr;
     double* d_fac = nullptr;
     double* d_svals = nullptr;
+    double* d_scal = nullptr;          // [0] 1/||x||_M, [1] ||x||_M, [2] 1/H[j+1][j], [3] H[j+1][j]   (device scalars of the loop)
+    double* d_res = nullptr;           // residual estimates (64)
+    double* d_out = nullptr;           // batch results [B][n]
+    double* d_ub = nullptr;            // batch coefficient vectors [B][64]
+    size_t out_cap = 0;
+
     int grid = 148;
     int coop_grid = 148;
     // one-kernel BiCGStab (default); KEXP_BICG_HOST=1 keeps the host-driven loop for comparison
@@ -61,7 +67,7 @@ static void free_state(KrylovState* k) {
     if (!k) return;
     free_csr(k->Ash); free_csr(k->Brhs); free_csr(k->Eback); free_csr(k->M);
     double* bufs[] = {k->d_Pinv, k->V, k->Z, k->w, k->mw, k->tmp, k->b, k->x, k->r, k->r0, k->p, k->v, k->s, k->t, k->y, k->z,
-                      k->d_dots, k->d_partials, k->d_H, k->d_small, k->d_u, k->d_fac, k->d_svals};
+                      k->d_dots, k->d_partials, k->d_H, k->d_small, k->d_u, k->d_fac, k->d_svals, k->d_scal, k->d_res, k->d_out, k->d_ub};
     for (double* b : bufs) cudaFree(b);
     cudaFree(k->d_counter);
     cudaFree(k->d_bicg_partials);
@@ -212,19 +218,6 @@ int shifted_solve(kexp_ctx* ctx, const double* vin, double* wout) {
     KEXP_CUDA(cudaMemcpyAsync(wout, k->x, sizeof(double) * nu, cudaMemcpyDeviceToDevice, ctx->stream));
     spmv(ctx, k->Eback, k->x, k->tmp);
     lincomb(ctx, wout + nu, 1.0, vin + nu, 1.0, k->tmp, 0.0, nullptr, n - nu);
-    return 0;
-}
-
-// after a stream synchronisation: outcome of the cooperative solves enqueued since the last check
-int check_solves(kexp_ctx* ctx) {
-    KrylovState* k = ctx->kry;
-    if (!k->info_pending) return 0;
-    k->info_pending = false;
-    ctx->st_bicg += k->h_info[0];
-    const int status = k->h_info[1];
-    KEXP_CUDA(cudaMemsetAsync(k->d_info, 0, sizeof(int) * 4, ctx->stream));
-    if (status == 2) return kexp::fail(ctx, "BiCGStab breakdown in the shifted solve");
-    if (status == 1) return kexp::fail(ctx, "shifted solve did not converge (raise solve_max_it)");
     return 0;
 }
 
@@ -437,48 +430,31 @@ int kexp_dense_expm(kexp_ctx* ctx, const double* A, int m, double* E) {
     return 0;
 }
 
-int kexp_krylov_apply(kexp_ctx* ctx, const double* x, double* y, double t, int kdim, int its,
-                      double* H_out, double* u_out, double* residuals_out) {
-    if (!ctx) return 1;
-    cudaSetDevice(ctx->device);
+// ---------------------------------------------------------------------------------------------
+// Arnoldi process of krylov_exp.py:58-80 for ONE start vector that is already on the device (k->w), entirely on
+// the library's stream: H (device), V, Z = M V and ||x||_M (k->d_scal[1]) are left in the state; nothing here
+// waits for the device except the optional residual diagnostic (its operator application checks its mass solve).
+// ---------------------------------------------------------------------------------------------
+static int arnoldi_dev(kexp_ctx* ctx, int kdim, int its, double t, double* d_res /* device, its doubles, or null */) {
     KrylovState* k = ctx->kry;
-    if (!k) return kexp::fail(ctx, "krylov operator not set (kexp_set_krylov_operator)");
-    if (!x || !y) return kexp::fail(ctx, "null vector");
-    if (x == y) return kexp::fail(ctx, "x and y must not alias");
-    if (kdim < 1 || kdim > 63) return kexp::fail(ctx, "kdim must be in 1..63");
-    if (its < 0) its = kdim;                                         // krylov_exp.py:66-67
-    if (its > kdim) return kexp::fail(ctx, "its <= kdim violated (krylov_exp.py:68)");
-    if (its < 1) return kexp::fail(ctx, "its must be >= 1");
     const int n = (int)k->n;
-    if (k->kdim < kdim) {
-        cudaFree(k->V); cudaFree(k->Z); cudaFree(k->d_H);
-        k->V = k->Z = k->d_H = nullptr;
-        if (alloc_d(ctx, &k->V, (size_t)(kdim + 1) * n) || alloc_d(ctx, &k->Z, (size_t)(kdim + 1) * n) ||
-            alloc_d(ctx, &k->d_H, (size_t)(kdim + 1) * kdim)) return 1;
-        k->kdim = kdim;
-    }
     const int ldh = kdim;
     KEXP_CUDA(cudaMemsetAsync(k->d_H, 0, sizeof(double) * (size_t)(kdim + 1) * kdim, ctx->stream));
-    std::vector<double> Hh((size_t)(kdim + 1) * kdim, 0.0);
     // beta = ||x||_M, V0 = x / beta, Z0 = M V0
-    KEXP_CUDA(cudaMemcpyAsync(k->w, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     spmv(ctx, k->M, k->w, k->mw);
-    double xmx = 0.0;
-    if (dot1(ctx, k->w, k->mw, n, &xmx)) return 1;
-    if (!(xmx > 0.0)) {                                              // zero input: exp(.) 0 = 0
-        memset(y, 0, sizeof(double) * n);
-        if (H_out) memset(H_out, 0, sizeof(double) * (size_t)(kdim + 1) * kdim);
-        if (u_out) memset(u_out, 0, sizeof(double) * its);
-        if (residuals_out) memset(residuals_out, 0, sizeof(double) * its);
-        return 0;
+    {
+        DotArgs args;
+        memset(&args, 0, sizeof(args));
+        args.count = 1; args.a[0] = k->w; args.b[0] = k->mw; args.n[0] = n;
+        multidot_kernel<<<k->grid, kKryThreads, 0, ctx->stream>>>(args, k->d_partials, k->d_counter, k->d_dots);
+        arnoldi_norm_kernel<<<1, 1, 0, ctx->stream>>>(k->d_dots, nullptr, k->d_scal, nullptr);
+        scale2_kernel<<<grid_for(n, 4 * k->grid), kKryThreads, 0, ctx->stream>>>(k->V, k->Z, k->w, k->mw, k->d_scal, n);
+        ctx->st_launches += 3;
     }
-    const double beta = sqrt(xmx);
-    lincomb(ctx, k->V, 1.0 / beta, k->w, 0.0, nullptr, 0.0, nullptr, n);
-    lincomb(ctx, k->Z, 1.0 / beta, k->mw, 0.0, nullptr, 0.0, nullptr, n);
     const double svals[3] = {1.0 / 3.0, 2.0 / 3.0, 1.0};            // krylov_exp.py:90
     KEXP_CUDA(cudaMemcpyAsync(k->d_svals, svals, sizeof(svals), cudaMemcpyHostToDevice, ctx->stream));
     kexp_batch *bi = nullptr, *bo = nullptr;
-    if (residuals_out) {
+    if (d_res) {
         if (kexp_batch_create(ctx, 1, &bi) || kexp_batch_create(ctx, 1, &bo)) return 1;
     }
     int rc = 0;
@@ -499,49 +475,151 @@ int kexp_krylov_apply(kexp_ctx* ctx, const double* x, double* y, double t, int k
             e = cudaMemcpy2DAsync(k->d_H + j, sizeof(double) * ldh, Hcol, sizeof(double), sizeof(double), j + 1, cudaMemcpyDeviceToDevice, ctx->stream);
             if (e != cudaSuccess) { rc = kexp::fail(ctx, cudaGetErrorString(e)); break; }
         }
+        // H[j+1,j] = ||w||_M  (krylov_exp.py:78), V_{j+1} = w / H[j+1,j], Z_{j+1} = M V_{j+1}: scalars stay on the device
         spmv(ctx, k->M, k->w, k->mw);
-        double wmw = 0.0;
-        if (dot1(ctx, k->w, k->mw, n, &wmw)) { rc = 1; break; }
-        if (check_solves(ctx)) { rc = 1; break; }
-        const double hn = sqrt(std::max(wmw, 0.0));                  // H[j+1,j] = ||w||_M  (krylov_exp.py:78)
-        if (cudaMemcpyAsync(k->d_H + (size_t)(j + 1) * ldh + j, &hn, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = 1; break; }
-        if (!(hn > 0.0)) { rc = kexp::fail(ctx, "Arnoldi breakdown (invariant subspace reached)"); break; }
-        lincomb(ctx, k->V + (size_t)(j + 1) * n, 1.0 / hn, k->w, 0.0, nullptr, 0.0, nullptr, n);
-        lincomb(ctx, k->Z + (size_t)(j + 1) * n, 1.0 / hn, k->mw, 0.0, nullptr, 0.0, nullptr, n);
-        const bool last = (j == its - 1);
-        if (residuals_out || last) {
-            // small dense part on one CTA: inv(H), expm(-H1 s t) e1 for s = 1/3, 2/3, 1
+        {
+            DotArgs args;
+            memset(&args, 0, sizeof(args));
+            args.count = 1; args.a[0] = k->w; args.b[0] = k->mw; args.n[0] = n;
+            multidot_kernel<<<k->grid, kKryThreads, 0, ctx->stream>>>(args, k->d_partials, k->d_counter, k->d_dots);
+            arnoldi_norm_kernel<<<1, 1, 0, ctx->stream>>>(k->d_dots, k->d_H + (size_t)(j + 1) * ldh + j, k->d_scal + 2, k->d_info);
+            scale2_kernel<<<grid_for(n, 4 * k->grid), kKryThreads, 0, ctx->stream>>>(k->V + (size_t)(j + 1) * n, k->Z + (size_t)(j + 1) * n,
+                                                                                      k->w, k->mw, k->d_scal + 2, n);
+            ctx->st_launches += 3;
+        }
+        if (d_res) {
+            // small dense part on one CTA: inv(H), expm(-H1 s t) e1 for s = 1/3, 2/3, 1   (krylov_exp.py:87-99)
             hessenberg_exp_kernel<<<1, kDenseThreads, 0, ctx->stream>>>(k->d_H, ldh, j + 1, k->gamma, t, k->d_svals, 3, k->d_u, k->d_fac, k->d_small);
             ctx->st_launches++;
-        }
-        if (residuals_out) {
-            // C = || M^-1 K w ||_M  with w the orthogonalised, unnormalised vector (krylov_exp.py:92-94)
-            cudaStreamSynchronize(ctx->stream);
-            std::vector<double> hw((size_t)n), how((size_t)n);
-            if (cudaMemcpy(hw.data(), k->w, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = 1; break; }
-            if (kexp_batch_upload(bi, hw.data(), n, 0) || kexp_operator_apply_dev(ctx, bi, bo) || kexp_batch_download(bo, how.data(), n)) { rc = 1; break; }
-            if (cudaMemcpyAsync(k->tmp, how.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = 1; break; }
+            // C = || M^-1 K w ||_M with w the orthogonalised, unnormalised vector (krylov_exp.py:92-94); w stays on the
+            // device.  NOTE: the operator is this context's M^-1 K (kexp_set_operator); the reference applies whatever
+            // operator_solver the caller passed -- see DESIGN.md for this documented deviation.
+            if (kexp_batch_upload_dev(bi, k->w, n, 0) || kexp_operator_apply_dev(ctx, bi, bo) || kexp_batch_export_dev(bo, k->tmp, n)) { rc = 1; break; }
             spmv(ctx, k->M, k->tmp, k->mw);
-            double c2 = 0.0;
-            if (dot1(ctx, k->tmp, k->mw, n, &c2)) { rc = 1; break; }
-            double fac[3];
-            if (cudaMemcpy(fac, k->d_fac, sizeof(fac), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = 1; break; }
-            const double C = sqrt(std::max(c2, 0.0));
-            double res = 0.0;
-            for (int q = 0; q < 3; ++q) res = std::max(res, fabs(C / k->gamma * fac[q]));   // krylov_exp.py:99-100
-            residuals_out[j] = res;
+            DotArgs args;
+            memset(&args, 0, sizeof(args));
+            args.count = 1; args.a[0] = k->tmp; args.b[0] = k->mw; args.n[0] = n;
+            multidot_kernel<<<k->grid, kKryThreads, 0, ctx->stream>>>(args, k->d_partials, k->d_counter, k->d_dots);
+            residual_kernel<<<1, 1, 0, ctx->stream>>>(k->d_dots, k->gamma, k->d_fac, 3, d_res + j);
+            ctx->st_launches += 2;
         }
     }
     if (bi) kexp_batch_destroy(bi);
     if (bo) kexp_batch_destroy(bo);
-    if (rc) return rc;
-    combine_kernel<<<grid_for(n, 4 * k->grid), kKryThreads, 0, ctx->stream>>>(k->V, n, k->d_u, its, beta, k->tmp, n);
-    ctx->st_launches++;
+    if (!rc) KEXP_CUDA(cudaGetLastError());
+    return rc;
+}
+
+static int krylov_prepare(kexp_ctx* ctx, int kdim, int* its) {
+    KrylovState* k = ctx->kry;
+    if (!k) return kexp::fail(ctx, "krylov operator not set (kexp_set_krylov_operator)");
+    if (kdim < 1 || kdim > 63) return kexp::fail(ctx, "kdim must be in 1..63");
+    if (*its < 0) *its = kdim;                                       // krylov_exp.py:66-67
+    if (*its > kdim) return kexp::fail(ctx, "its <= kdim violated (krylov_exp.py:68)");
+    if (*its < 1) return kexp::fail(ctx, "its must be >= 1");
+    const int n = (int)k->n;
+    if (k->kdim < kdim) {
+        cudaFree(k->V); cudaFree(k->Z); cudaFree(k->d_H);
+        k->V = k->Z = k->d_H = nullptr;
+        if (alloc_d(ctx, &k->V, (size_t)(kdim + 1) * n) || alloc_d(ctx, &k->Z, (size_t)(kdim + 1) * n) ||
+            alloc_d(ctx, &k->d_H, (size_t)(kdim + 1) * kdim)) return 1;
+        k->kdim = kdim;
+    }
+    if (!k->d_scal) {
+        if (alloc_d(ctx, &k->d_scal, 8) || alloc_d(ctx, &k->d_res, 64)) return 1;
+    }
+    return 0;
+}
+
+// after the closing synchronisation: breakdown / non-convergence recorded on the device during the loop
+static int krylov_outcome(kexp_ctx* ctx, bool* zero_input) {
+    KrylovState* k = ctx->kry;
+    double scal[4];
+    int info[4];
+    KEXP_CUDA(cudaMemcpy(scal, k->d_scal, sizeof(scal), cudaMemcpyDeviceToHost));
+    KEXP_CUDA(cudaMemcpy(info, k->d_info, sizeof(info), cudaMemcpyDeviceToHost));
+    KEXP_CUDA(cudaMemsetAsync(k->d_info, 0, sizeof(int) * 4, ctx->stream));
+    k->info_pending = false;
+    ctx->st_bicg += info[0];
+    *zero_input = !(scal[1] > 0.0);
+    if (*zero_input) return 0;                                       // exp(.) 0 = 0, no error
+    if (info[1] == 2) return kexp::fail(ctx, "BiCGStab breakdown in the shifted solve");
+    if (info[1] == 1) return kexp::fail(ctx, "shifted solve did not converge (raise solve_max_it)");
+    if (info[3]) return kexp::fail(ctx, "Arnoldi breakdown (invariant subspace reached)");
+    return 0;
+}
+
+int kexp_krylov_apply(kexp_ctx* ctx, const double* x, double* y, double t, int kdim, int its,
+                      double* H_out, double* u_out, double* residuals_out) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (!x || !y) return kexp::fail(ctx, "null vector");
+    if (x == y) return kexp::fail(ctx, "x and y must not alias");
+    if (krylov_prepare(ctx, kdim, &its)) return 1;
+    KrylovState* k = ctx->kry;
+    const int n = (int)k->n;
+    KEXP_CUDA(cudaMemcpyAsync(k->w, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (arnoldi_dev(ctx, kdim, its, t, residuals_out ? k->d_res : nullptr)) return 1;
+    // inv(H), expm(-H1 t) e1 (krylov_exp.py:87-99 at s = 1), y = beta sum_j u_j V_j (:102-109)
+    hessenberg_exp_kernel<<<1, kDenseThreads, 0, ctx->stream>>>(k->d_H, kdim, its, k->gamma, t, k->d_svals, 3, k->d_u, k->d_fac, k->d_small);
+    combine_batch_kernel<<<grid_for(n, 4 * k->grid), kKryThreads, sizeof(double) * its, ctx->stream>>>(k->V, n, k->d_u, its, 1, k->d_scal, k->tmp, n, n);
+    ctx->st_launches += 2;
     KEXP_CUDA(cudaMemcpyAsync(y, k->tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (H_out) KEXP_CUDA(cudaMemcpyAsync(H_out, k->d_H, sizeof(double) * (size_t)(kdim + 1) * kdim, cudaMemcpyDeviceToHost, ctx->stream));
     if (u_out) KEXP_CUDA(cudaMemcpyAsync(u_out, k->d_u, sizeof(double) * its, cudaMemcpyDeviceToHost, ctx->stream));
+    if (residuals_out) KEXP_CUDA(cudaMemcpyAsync(residuals_out, k->d_res, sizeof(double) * its, cudaMemcpyDeviceToHost, ctx->stream));
     KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
     KEXP_CUDA(cudaGetLastError());
+    bool zero = false;
+    if (krylov_outcome(ctx, &zero)) return 1;
+    if (zero) {                                                      // zero input: exp(.) 0 = 0
+        memset(y, 0, sizeof(double) * n);
+        if (H_out) memset(H_out, 0, sizeof(double) * (size_t)(kdim + 1) * kdim);
+        if (u_out) memset(u_out, 0, sizeof(double) * its);
+        if (residuals_out) memset(residuals_out, 0, sizeof(double) * its);
+    }
+    return 0;
+}
+
+// B sample times at once (krylov_exp.apply for every ensemble member, averaged_sw_explicit.py:233-235 with the
+// Krylov propagator).  x_is_shared: the shift-and-invert Krylov space K_m((I + gamma A)^-1, x) does not depend on t, so
+// ONE Arnoldi process serves every t_k and only the small exponentials expm(-t_k H1) e1 and the final combination
+// differ.  Distinct inputs run their Arnoldi processes back to back on the device queue (no host wait in between).
+int kexp_krylov_apply_batch(kexp_ctx* ctx, const double* X, int64_t ldx, int x_is_shared, double* Y, int64_t ldy,
+                            const double* t, int B, int kdim, int its) {
+    if (!ctx) return 1;
+    cudaSetDevice(ctx->device);
+    if (!X || !Y || !t || B < 1) return kexp::fail(ctx, "bad arguments");
+    if (krylov_prepare(ctx, kdim, &its)) return 1;
+    KrylovState* k = ctx->kry;
+    const int n = (int)k->n;
+    if (ldy < n || (!x_is_shared && ldx < n)) return kexp::fail(ctx, "leading dimension < n");
+    if (k->out_cap < (size_t)B * n) {
+        cudaFree(k->d_out); cudaFree(k->d_ub);
+        k->d_out = k->d_ub = nullptr; k->out_cap = 0;
+        if (alloc_d(ctx, &k->d_out, (size_t)B * n) || alloc_d(ctx, &k->d_ub, (size_t)B * 64)) return 1;
+        k->out_cap = (size_t)B * n;
+    }
+    const int cgrid = grid_for(n, 4 * k->grid);
+    const int nproc = x_is_shared ? 1 : B;
+    for (int p = 0; p < nproc; ++p) {
+        KEXP_CUDA(cudaMemcpyAsync(k->w, X + (size_t)p * (x_is_shared ? 0 : ldx), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        if (arnoldi_dev(ctx, kdim, its, 0.0, nullptr)) return 1;
+        const int c0 = x_is_shared ? 0 : p, c1 = x_is_shared ? B : p + 1;
+        for (int c = c0; c < c1; ++c) {
+            hessenberg_exp_kernel<<<1, kDenseThreads, 0, ctx->stream>>>(k->d_H, kdim, its, k->gamma, t[c], k->d_svals + 2, 1,
+                                                                      k->d_ub + (size_t)c * 64, k->d_fac, k->d_small);
+            ctx->st_launches++;
+        }
+        combine_batch_kernel<<<cgrid, kKryThreads, sizeof(double) * its * (c1 - c0), ctx->stream>>>(
+            k->V, n, k->d_ub + (size_t)c0 * 64, its, c1 - c0, k->d_scal, k->d_out + (size_t)c0 * n, n, n);
+        ctx->st_launches++;
+    }
+    KEXP_CUDA(cudaMemcpy2DAsync(Y, sizeof(double) * ldy, k->d_out, sizeof(double) * n, sizeof(double) * n, B, cudaMemcpyDeviceToHost, ctx->stream));
+    KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
+    KEXP_CUDA(cudaGetLastError());
+    bool zero = false;
+    if (krylov_outcome(ctx, &zero)) return 1;      // sticky status over all columns; `zero` refers to the last start vector
     return 0;
 }
 

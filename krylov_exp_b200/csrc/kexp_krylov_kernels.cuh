@@ -601,6 +601,62 @@ bicgstab_smem_kernel(BicgSmemArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Device-side glue of the Arnoldi loop (no host round trip per step):
+//   arnoldi_norm_kernel   hn = sqrt(max(w.Mw, 0)) -> H[j+1][j], scal = 1/hn (0 and a breakdown flag when hn = 0)
+//   scale2_kernel         V_{j+1} = scal w,  Z_{j+1} = scal Mw        (krylov_exp.py:78-80)
+//   residual_kernel       res[j] = max_q |sqrt(c2)/gamma * fac[q]|    (krylov_exp.py:99-100)
+// ------------------------------------------------------------------------------------
+__global__ void arnoldi_norm_kernel(const double* __restrict__ dot, double* __restrict__ Hentry, double* __restrict__ scal, int* __restrict__ info) {
+    const double hn = sqrt(fmax(dot[0], 0.0));
+    if (Hentry) *Hentry = hn;
+    scal[0] = (hn > 0.0) ? 1.0 / hn : 0.0;
+    scal[1] = hn;
+    if (!(hn > 0.0) && info) info[3] = 1;
+}
+
+__global__ void __launch_bounds__(kKryThreads)
+scale2_kernel(double* __restrict__ o1, double* __restrict__ o2, const double* __restrict__ x1, const double* __restrict__ x2,
+              const double* __restrict__ scal, int n) {
+    const double a = scal[0];
+    for (int i = blockIdx.x * kKryThreads + threadIdx.x; i < n; i += gridDim.x * kKryThreads) {
+        o1[i] = a * x1[i];
+        o2[i] = a * x2[i];
+    }
+}
+
+__global__ void residual_kernel(const double* __restrict__ c2, double gamma, const double* __restrict__ fac, int nfac, double* __restrict__ out) {
+    const double C = sqrt(fmax(c2[0], 0.0));
+    double r = 0.0;
+    for (int q = 0; q < nfac; ++q) r = fmax(r, fabs(C / gamma * fac[q]));
+    *out = r;
+}
+
+// Y[k][i] = beta * sum_{j<its} u[k][j] V_j[i]  for B coefficient vectors at once (the sample times of one shared input
+// live in ONE Krylov space: only the small exponential depends on t_k).  u: [B][64], beta from device memory.
+__global__ void __launch_bounds__(kKryThreads)
+combine_batch_kernel(const double* __restrict__ V, int64_t ldv, const double* __restrict__ u, int its, int B, const double* __restrict__ scal,
+                     double* __restrict__ Y, int64_t ldy, int n) {
+    extern __shared__ double su[];                    // [B][its]
+    for (int e = threadIdx.x; e < B * its; e += kKryThreads) su[e] = u[(size_t)(e / its) * 64 + (e % its)];
+    __syncthreads();
+    const double beta = scal[1];
+    for (int i = blockIdx.x * kKryThreads + threadIdx.x; i < n; i += gridDim.x * kKryThreads) {
+        for (int k0 = 0; k0 < B; k0 += 8) {
+            double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < its; ++j) {
+                const double v = V[(size_t)j * ldv + i];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (k0 + q < B) acc[q] = fma(su[(k0 + q) * its + j], v, acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (k0 + q < B) Y[(size_t)(k0 + q) * ldy + i] = (beta > 0.0) ? beta * acc[q] : 0.0;     // zero input: exp(.) 0 = 0
+        }
+    }
+}
+
 // y = beta * sum_{j<its} u_j V_j     (krylov_exp.py:102-109)
 __global__ void __launch_bounds__(kKryThreads)
 combine_kernel(const double* __restrict__ V, int64_t ldv, const double* __restrict__ u, int its, double beta,

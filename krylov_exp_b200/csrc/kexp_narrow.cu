@@ -29,12 +29,10 @@ namespace cg = cooperative_groups;
 
 namespace kexp {
 
-// threads per CTA: a single column pair per block row (W = 2) needs 256 threads for the 208 block rows a CTA owns at
-// ref 5 and may then use 255 registers; wider panels take 512 threads (128 registers)
 template <int W> struct NarrowCfg {
-    static constexpr int NT = (W == 2) ? 256 : 512;
-    static constexpr int GK = (W == 2) ? 4 : 3;      // gathered blocks of K~ in flight per row
-    static constexpr int GS = (W == 2) ? 5 : 3;      // the same for S (5 blocks per BDM2 edge row)
+    static constexpr int NT = 256;                   // 1 CTA per SM: up to 255 registers per thread, no spills in the hot loops
+    static constexpr int GK = 4;                     // gathered blocks of K~ in flight per row
+    static constexpr int GS = 5;                     // the same for S (5 blocks per BDM2 edge row: the whole row at once)
 };
 constexpr int kNTmax = 512;
 constexpr int kNWarpsMax = kNTmax / 32;
@@ -57,9 +55,49 @@ struct NarrowArgs {
     double* basis; int basis_ld;         // mode 0: store column 0 of S_n (or null);  mode 1: z_m (required)
     double alpha, mu;                    // Chebyshev acceleration of the mass solve
     CgScalars* sc; double* partials;     // [gridDim][2][W] block sums of ||r||^2, ||b||^2
+    unsigned* barrier;                   // grid barrier counter (zeroed before the launch)
     // shared-memory layout (element counts, maxima over the CTAs)
     int cap_s_blocks, cap_s_rows, cap_kt_rows, cap_kt_blocks, cap_r_rows, cap_r_nnz;
 };
+
+// The arguments live in constant memory (one slot per context, round-robin): the phases below are separate, NOT
+// inlined functions -- each gets its own register allocation instead of one body that keeps the loop invariants of all
+// phases alive and spills -- and read their arguments from the constant bank.  (Passing the ADDRESS of a by-value
+// kernel parameter to out-of-line functions makes the compiler keep a per-thread copy in local memory: every pointer
+// load of the hot loops became a dependent L1/L2 access, measured 4x slower.)
+constexpr int kArgSlots = 8;
+__constant__ NarrowArgs c_nargs[kArgSlots];
+
+// Grid-wide barrier of the persistent kernel.  Every value that crosses CTAs is read with ld.global.cg (L2, the coherence
+// point), so the barrier does NOT need the L1 invalidation that cooperative_groups' grid.sync() performs (CCTL.IVALL behind
+// its acquire) -- and must not have it: the invalidation also drops the thread-private stack lines, after which every
+// spilled value of the loop state costs an L2 round trip per phase.  Release: bar.sync + one gpu-scope fence + atomic
+// arrive by thread 0; wait: volatile poll of the monotonic counter (zeroed at launch), then bar.sync.
+#ifndef KEXP_NARROW_SYNC
+#define KEXP_NARROW_SYNC 1         // 0: cooperative_groups grid.sync()
+#endif
+#ifndef KEXP_NARROW_INLINE
+#define KEXP_NARROW_INLINE 0       // 1: phases inlined into one kernel body
+#endif
+#if KEXP_NARROW_INLINE
+#define KEXP_PHASE_FN __device__ __forceinline__
+#else
+#define KEXP_PHASE_FN __device__ __noinline__
+#endif
+__device__ __forceinline__ void narrow_barrier(cg::grid_group& grid, unsigned* counter, unsigned& target) {
+#if KEXP_NARROW_SYNC
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
+    }
+    __syncthreads();
+#else
+    grid.sync();
+#endif
+}
 
 __device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
@@ -97,7 +135,7 @@ struct StepCtx {
 };
 
 template <int W>
-__device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& sx, int lane_pair) {
+__device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& sx, int lane_pair) {   // a: constant bank
     UpdCtx u;
     u.has_old = sx.has_old; u.mode = a.mode; u.term = sx.term; u.Snew = sx.Snew; u.Y = a.Y; u.ld = a.basis_ld;
     u.zsrc = (a.mode == 1) ? a.basis + sx.term : nullptr;
@@ -108,12 +146,11 @@ __device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& s
     return u;
 }
 
-// The phases are separate (not inlined) functions so that each gets its own register allocation: the kernel as one body
-// keeps the loop invariants of all three phases alive at once and spills.
 // ---- phase A: T = K~ S_{n-1}; depth rows (no solve) take their recurrence update in the epilogue
 template <int W>
-__device__ __noinline__ void narrow_phase_a(const NarrowArgs& a, const StepCtx& sx, const int* __restrict__ kptr, const int* __restrict__ kcol,
-                                            int k0r, int k1r, int kt_b0) {
+KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restrict__ kptr, const int* __restrict__ kcol,
+                                         int k0r, int k1r, int kt_b0) {
+    const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
     constexpr int kNT = NarrowCfg<W>::NT, kNWarps = kNT / 32, kGatherK = NarrowCfg<W>::GK;
@@ -177,7 +214,8 @@ __device__ __noinline__ void narrow_phase_a(const NarrowArgs& a, const StepCtx& 
 
 // ---- phase B, start: x_0 = 0, x_1 = alpha P^-1 b on the own rows; returns the thread's share of ||b||^2
 template <int W>
-__device__ __noinline__ double2 narrow_solve_start(const NarrowArgs& a, double* xk, double* xm, const double* __restrict__ sP, int s0, int s1) {
+KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* xk, double* xm, const double* __restrict__ sP, int s0, int s1) {
+    const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
     constexpr int BPC = (NarrowCfg<W>::NT / 32) * BRW;
@@ -211,9 +249,10 @@ __device__ __noinline__ double2 narrow_solve_start(const NarrowArgs& a, double* 
 // ---- phase B, one Chebyshev iteration on the own rows: x_{k+1} overwrites x_{k-1}; LAST also forms ||b - S x_k||^2 and
 // the recurrence update of the edge rows (W = x_K)
 template <int W, bool LAST>
-__device__ __noinline__ double2 narrow_solve_iter(const NarrowArgs& a, const StepCtx& sx, const double* xk, double* xm, double omega,
-                                                  const double2* __restrict__ sblk, const double* __restrict__ sP, const int* __restrict__ sptr,
-                                                  int s0, int s1) {
+KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double* xk, double* xm, double omega,
+                                                 const double2* __restrict__ sblk, const double* __restrict__ sP, const int* __restrict__ sptr,
+                                                 int s0, int s1) {
+    const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
     constexpr int BPC = (NarrowCfg<W>::NT / 32) * BRW, kGatherS = NarrowCfg<W>::GS;
@@ -289,8 +328,9 @@ __device__ __noinline__ double2 narrow_solve_iter(const NarrowArgs& a, const Ste
 
 // ---- phase C: interior rows  w_I = T_I + R x_K  and their recurrence update
 template <int W>
-__device__ __noinline__ void narrow_phase_c(const NarrowArgs& a, const StepCtx& sx, const int* __restrict__ rptr, const int* __restrict__ rcol,
-                                            int r0, int r1) {
+KEXP_PHASE_FN void narrow_phase_c(int slot, const StepCtx sx, const int* __restrict__ rptr, const int* __restrict__ rcol,
+                                         int r0, int r1) {
+    const NarrowArgs& a = c_nargs[slot];
     constexpr int LPR = W / 2;
     constexpr int RPC = NarrowCfg<W>::NT / LPR;
     const int lr = threadIdx.x % LPR;
@@ -320,7 +360,8 @@ __device__ __noinline__ void narrow_phase_c(const NarrowArgs& a, const StepCtx& 
 
 // ---- convergence record of one solve (CTA 0, fixed summation order over the per-CTA block sums)
 template <int W>
-__device__ __noinline__ void narrow_check(const NarrowArgs& a, double* fin, int K, double rtol2, int* s_bad) {
+KEXP_PHASE_FN void narrow_check(int slot, double* fin, int K, double rtol2, int* s_bad) {
+    const NarrowArgs& a = c_nargs[slot];
     constexpr int kNT = NarrowCfg<W>::NT;
     constexpr int TPV = kNT / (2 * W) > 32 ? 32 : kNT / (2 * W);      // threads per value
     const int val = threadIdx.x / TPV, part = threadIdx.x % TPV;
@@ -366,7 +407,8 @@ __device__ __noinline__ void narrow_check(const NarrowArgs& a, double* fin, int 
 
 template <int W>
 __global__ void __launch_bounds__(NarrowCfg<W>::NT, 1)
-cheb_apply_narrow_kernel(const __grid_constant__ NarrowArgs a) {
+cheb_apply_narrow_kernel(const int slot) {
+    const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int kNT = NarrowCfg<W>::NT, kNWarps = kNT / 32;
     constexpr int LPB = C::LPB;
@@ -428,8 +470,8 @@ cheb_apply_narrow_kernel(const __grid_constant__ NarrowArgs a) {
             }
         }
     }
-    __syncthreads();
-    grid.sync();
+    unsigned bar_target = 0;
+    narrow_barrier(grid, a.barrier, bar_target);
 
     StepCtx sx;
     sx.Sin = a.SA;               // S_{n-1}
@@ -442,21 +484,21 @@ cheb_apply_narrow_kernel(const __grid_constant__ NarrowArgs a) {
         sx.has_old = (a.mode == 0) ? (step >= 2) : 1;
         sx.crow = a.coef + (size_t)((a.mode == 0) ? sx.term : 0) * kMaxW;
 
-        narrow_phase_a<W>(a, sx, kptr, kcol, k0r, k1r, kt_b0);
-        grid.sync();
+        narrow_phase_a<W>(slot, sx, kptr, kcol, k0r, k1r, kt_b0);
+        narrow_barrier(grid, a.barrier, bar_target);
 
         // mass solve on the own rows of S (Chebyshev semi-iteration), K - 1 iterations behind x_1
         const int K = a.kterm[step];
         double* xk = (K % 2 == 1) ? a.X : a.P;               // x_1 here, x_K ends up in a.X
         double* xm = (xk == a.X) ? a.P : a.X;
-        double2 accb = narrow_solve_start<W>(a, xk, xm, sP, s0, s1);
+        double2 accb = narrow_solve_start<W>(slot, xk, xm, sP, s0, s1);
         double2 accr = make_double2(0.0, 0.0);
         double omega = 1.0;
         for (int it = 1; it < K; ++it) {
-            grid.sync();
+            narrow_barrier(grid, a.barrier, bar_target);
             omega = (it == 1) ? 1.0 / (1.0 - 0.5 * a.mu * a.mu) : 1.0 / (1.0 - 0.25 * a.mu * a.mu * omega);
-            if (it == K - 1) accr = narrow_solve_iter<W, true>(a, sx, xk, xm, omega, sblk, sP, sptr, s0, s1);
-            else narrow_solve_iter<W, false>(a, sx, xk, xm, omega, sblk, sP, sptr, s0, s1);
+            if (it == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, xk, xm, omega, sblk, sP, sptr, s0, s1);
+            else narrow_solve_iter<W, false>(slot, sx, xk, xm, omega, sblk, sP, sptr, s0, s1);
             double* tsw = xk; xk = xm; xm = tsw;
         }
         // block sums of ||r||^2 and ||b||^2 per column (fixed order): shuffles over the groups of a warp, then the warps
@@ -480,12 +522,12 @@ cheb_apply_narrow_kernel(const __grid_constant__ NarrowArgs a) {
                 a.partials[((size_t)blockIdx.x * 2 + q) * W + c] = s;
             }
         }
-        grid.sync();                                           // x_K, the edge rows of S_n and the block sums are visible
-        if (blockIdx.x == 0) narrow_check<W>(a, sred + 2 * kNWarpsMax * W, K, a.rtol2[step], &s_bad);
+        narrow_barrier(grid, a.barrier, bar_target);                                           // x_K, the edge rows of S_n and the block sums are visible
+        if (blockIdx.x == 0) narrow_check<W>(slot, sred + 2 * kNWarpsMax * W, K, a.rtol2[step], &s_bad);
 
         if (a.n_b > 0) {
-            narrow_phase_c<W>(a, sx, rptr, rcol, r0, r1);
-            grid.sync();                                       // S_n complete
+            narrow_phase_c<W>(slot, sx, rptr, rcol, r0, r1);
+            narrow_barrier(grid, a.barrier, bar_target);                                       // S_n complete
         }
         double* tsw = sx.Sin; sx.Sin = sx.Snew; sx.Snew = tsw;
     }
@@ -541,7 +583,10 @@ static int launch_narrow_w(kexp_ctx* ctx, NarrowArgs& a, const NarrowCaps& caps)
         }
         attr_smem = smem;
     }
-    void* args[] = {&a};
+    int slot = ctx->narrow_slot;
+    if (cudaMemcpyToSymbolAsync(c_nargs, &a, sizeof(NarrowArgs), sizeof(NarrowArgs) * (size_t)slot, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        return kexp::fail(ctx, "narrow apply kernel: argument upload failed");
+    void* args[] = {&slot};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k, dim3(ctx->num_sms), dim3(NarrowCfg<W>::NT), args, smem, ctx->stream);
     if (e != cudaSuccess) return kexp::fail(ctx, std::string("narrow apply kernel launch: ") + cudaGetErrorString(e));
     return 0;
@@ -576,7 +621,7 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     if (!ctx->d_nk) {
         KEXP_CUDA(cudaMalloc(&ctx->d_nk, sizeof(int) * kMaxTerms));
         KEXP_CUDA(cudaMalloc(&ctx->d_nrtol2, sizeof(double) * kMaxTerms));
-        KEXP_CUDA(cudaMalloc(&ctx->d_npartials, sizeof(double) * 2 * kMaxW * (size_t)ctx->num_sms));
+        KEXP_CUDA(cudaMalloc(&ctx->d_npartials, sizeof(double) * 2 * kMaxW * (size_t)ctx->num_sms + 64));
     }
     // pageable sources: the driver stages them before the call returns, so the host vectors may be reused at once
     KEXP_CUDA(cudaMemcpyAsync(ctx->d_nk, kterm, sizeof(int) * (size_t)(M + 1), cudaMemcpyHostToDevice, ctx->stream));
@@ -593,6 +638,8 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     a.alpha = 2.0 / (ctx->cheb_hi + ctx->cheb_lo);
     a.mu = (ctx->cheb_hi - ctx->cheb_lo) / (ctx->cheb_hi + ctx->cheb_lo);
     a.sc = ctx->d_sc; a.partials = ctx->d_npartials;
+    a.barrier = reinterpret_cast<unsigned*>(ctx->d_npartials + 2 * kMaxW * (size_t)ctx->num_sms);
+    KEXP_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), ctx->stream));
     a.cap_s_blocks = caps.s_blocks; a.cap_s_rows = caps.s_rows; a.cap_kt_rows = caps.kt_rows; a.cap_kt_blocks = caps.kt_blocks;
     a.cap_r_rows = caps.r_rows; a.cap_r_nnz = caps.r_nnz;
     int rc = 1;

@@ -47,12 +47,29 @@ class ShiftedOperator:
             float(rtol), int(max_it)), "kexp_set_krylov_operator")
 
 
+def _shifted_from(solver, solver_in, gamma, operator_solver):
+    """The reference's call form (test_krylov.py:44-62,89-90): `solver` is whatever solves (M + gamma K') w = M v.
+    Accepted besides a ShiftedOperator:
+      * an object with `kexp_matrices()` -> (K, Mu, Meta_blocks) -- the matrices of M^-1 K in this package's layout
+        (any host assembler; the tests use it as the stand-in for Firedrake);
+      * a Firedrake LinearVariationalSolver: the bilinear form of its problem IS M + gamma K and its right-hand side
+        is M solver_in, so both are exported once as AIJ/CSR (firedrake_adapter.shifted_matrices_from_firedrake,
+        following L_eigs.py:44-45) and K = (A_shifted - M) / gamma."""
+    g = gamma.evaluate(0, 0, 0, 0) if hasattr(gamma, "evaluate") else float(gamma)   # krylov_exp.py:59
+    if hasattr(solver, "kexp_matrices"):
+        K, Mu, Meta_blocks = solver.kexp_matrices()
+    else:
+        from .firedrake_adapter import shifted_matrices_from_firedrake
+        K, Mu, Meta_blocks = shifted_matrices_from_firedrake(solver, solver_in, g)
+    op = operator_solver if isinstance(operator_solver, Operator) else Operator(K, Mu, np.linalg.inv(Meta_blocks))
+    return ShiftedOperator(op, K, Mu, Meta_blocks, g)
+
+
 class krylov_exp(object):
     def __init__(self, solver, solver_in, solver_out, gamma,
                  kdim, operator_solver, operator_in, operator_out):
         if not isinstance(solver, ShiftedOperator):
-            raise TypeError("solver must be a krylov_exp_b200.ShiftedOperator (build it from K, M and gamma; "
-                            "with Firedrake use firedrake_adapter to export K and M first)")
+            solver = _shifted_from(solver, solver_in, gamma, operator_solver)
         self.solver = solver
         self.solver_in, self.solver_out = solver_in, solver_out
         g = gamma.evaluate(0, 0, 0, 0) if hasattr(gamma, "evaluate") else float(gamma)   # krylov_exp.py:59
@@ -81,3 +98,21 @@ class krylov_exp(object):
                                              _lib.ptr(self.H), _lib.ptr(u), _lib.ptr(res)), "kexp_krylov_apply")
         self.u, self.residuals = u, res
         write_back(y, yout)
+
+    def apply_batch(self, X, t, shared=False, its=-999):
+        """exp(-t_k M^-1 K) for B sample times at once.  shared=True: one input x for every t_k -- the shift-and-invert
+        Krylov space does not depend on t, so ONE Arnoldi process serves all sample times; otherwise row k of X (B x n)
+        is advanced by t[k] (Arnoldi processes back to back on the device queue)."""
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
+        B = t.shape[0]
+        n = self.op.n
+        if its < 0:
+            its = self.kdim
+        assert its <= self.kdim                                      # krylov_exp.py:68
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1) if shared else np.atleast_2d(X), dtype=np.float64)
+        if X.shape != ((n,) if shared else (B, n)):
+            raise ValueError(f"X must have shape {'(n,)' if shared else '(B, n)'} with n = {n}, B = {B}; got {X.shape}")
+        Y = np.empty((B, n))
+        self.op._check(self.op.lib.kexp_krylov_apply_batch(self.op.ctx, _lib.ptr(X), n, int(shared), _lib.ptr(Y), n, _lib.ptr(t), B,
+                                                           self.kdim, int(its)), "kexp_krylov_apply_batch")
+        return Y

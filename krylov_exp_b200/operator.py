@@ -221,6 +221,12 @@ class Operator:
         later call (at the latest synchronize / download / stats), which raises if a solve missed rtol."""
         self._check(self.lib.kexp_set_async(self.ctx, int(bool(on))), "kexp_set_async")
 
+    def stream_ptr(self):
+        """The library's compute stream (cudaStream_t as an int), e.g. for torch.cuda.ExternalStream."""
+        st = C.c_void_p()
+        self._check(self.lib.kexp_get_stream(self.ctx, C.byref(st)), "kexp_get_stream")
+        return int(st.value or 0)
+
     def wait_transfers(self):
         """Completes the asynchronous device-to-host copies (cheby_exp.apply_batch(wait=False), DeviceBatch.download(wait=False))."""
         self._check(self.lib.kexp_wait_transfers(self.ctx), "kexp_wait_transfers")
@@ -340,6 +346,41 @@ class DeviceBatch:
                 X = np.ascontiguousarray(X)
             ld = X.strides[0] // 8 if self.B > 1 else self.op.n     # a single row: NumPy's stride[0] is arbitrary (0 for x[None, :])
         self.op._check(self.op.lib.kexp_batch_upload(self.handle, X.ctypes.data_as(C.c_void_p), ld, int(shared)), "kexp_batch_upload")
+
+    # -- device-resident vectors in the caller's layout (e.g. torch tensors): no host copy, no synchronisation
+    @staticmethod
+    def _dev_array(T, rows, n):
+        """(data pointer, leading dimension) of a CUDA float64 tensor / __cuda_array_interface__ object of shape (rows, n) or (n,)."""
+        if hasattr(T, "data_ptr"):                                    # torch.Tensor
+            import torch
+            if T.dtype != torch.float64 or not T.is_cuda:
+                raise ValueError("device vectors must be CUDA float64 tensors")
+            shape, strides, ptr = tuple(T.shape), tuple(T.stride()), T.data_ptr()
+        else:
+            ci = T.__cuda_array_interface__
+            if ci["typestr"] not in ("<f8", "=f8"):
+                raise ValueError("device vectors must be float64")
+            shape, ptr = tuple(ci["shape"]), ci["data"][0]
+            strides = tuple(s // 8 for s in ci["strides"]) if ci.get("strides") else None
+            if strides is None:
+                strides = (shape[1], 1) if len(shape) == 2 else (1,)
+        if len(shape) == 1:
+            if shape[0] != n or strides[0] != 1 or rows != 1:
+                raise ValueError(f"expected a contiguous vector of n = {n} values")
+            return ptr, n
+        if shape != (rows, n) or strides[1] != 1 or (rows > 1 and strides[0] < n):
+            raise ValueError(f"expected shape ({rows}, {n}) with unit inner stride, got {shape} / {strides}")
+        return ptr, (strides[0] if rows > 1 else n)
+
+    def upload_dev(self, T, shared=False):
+        """Device array (B, n) -- or one shared vector (n,) -- in user dof order -> panels; enqueued on the library stream."""
+        ptr, ld = self._dev_array(T, 1 if shared else self.B, self.op.n)
+        self.op._check(self.op.lib.kexp_batch_upload_dev(self.handle, C.c_void_p(ptr), ld, int(shared)), "kexp_batch_upload_dev")
+
+    def export_dev(self, T):
+        """Panels -> device array (B, n) in user dof order; enqueued on the library stream."""
+        ptr, ld = self._dev_array(T, self.B, self.op.n)
+        self.op._check(self.op.lib.kexp_batch_export_dev(self.handle, C.c_void_p(ptr), ld), "kexp_batch_export_dev")
 
     def download(self, out=None, wait=True):
         if out is None:

@@ -153,3 +153,72 @@ def test_one_kernel_bicgstab_matches_host_driven_loop(sw3, monkeypatch):
         assert _relM(M, out[mode][0], out["host"][0]) < 1e-9, mode
         assert np.abs(out[mode][1] - out["host"][1]).max() <= 1e-9 * np.abs(out["host"][1]).max(), mode
         assert out[mode][2] > 0 and abs(out[mode][2] - out["host"][2]) <= 0.2 * out["host"][2], mode
+
+
+def test_krylov_batch_over_sample_times(sw3):
+    """kexp_krylov_apply_batch: one Arnoldi process serves every sample time of a shared input (the shift-and-invert
+    Krylov space does not depend on t); distinct inputs run back to back on the device queue.  Both must reproduce the
+    un-batched apply, and the un-batched apply the oracle."""
+    import krylov_exp_b200 as kx
+    from oracle import krylov_ref
+    from oracle.assemble_sw import test_pulse
+    sw = sw3
+    T = 3600.0
+    gamma = T / 10.0
+    kdim = 18
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13, max_it=80)
+    sh = kx.ShiftedOperator(op, sw.K, sw.Mu, sw.Meta_blocks, gamma, rtol=1e-13)
+    ke = kx.krylov_exp(sh, None, None, gamma, kdim, op, None, None)
+    x = test_pulse(sw)
+    t, w = kx.sample_times_weights(7, T, 1.0)
+    M = sw.M()
+    Ys = ke.apply_batch(x, t, shared=True)
+    singles = []
+    for k in range(len(t)):
+        y = np.empty(sw.n)
+        ke.apply(x, y, float(t[k]), residuals=False)
+        singles.append(y)
+        assert _relM(M, Ys[k], y) < 1e-12, k
+    X = np.stack([x * (1.0 + 0.3 * k) + 0.05 * np.roll(x, 7 * k) for k in range(len(t))])
+    Yd = ke.apply_batch(X, t)
+    for k in (0, 3, 6):
+        y = np.empty(sw.n)
+        ke.apply(X[k], y, float(t[k]), residuals=False)
+        assert _relM(M, Yd[k], y) < 1e-12, k
+    X[2] = 0.0                                           # a zero column: exp(.) 0 = 0, no breakdown error
+    Yz = ke.apply_batch(X, t)
+    assert np.all(Yz[2] == 0.0) and _relM(M, Yz[5], Yd[5]) < 1e-12
+    lu_s = splu((M + gamma * sw.K).tocsc())
+    lu_m = splu(M.tocsc())
+    yo, Ho, uo, _ = krylov_ref.krylov_apply(lambda v: lu_s.solve(M @ v), lambda v: lu_m.solve(sw.K @ v),
+                                            lambda a, b: a @ (M @ b), x, float(t[5]), gamma, kdim, residuals=False)
+    assert _relM(M, singles[5], yo) < 1e-8
+    op.close()
+
+
+def test_krylov_reference_call_form(sw3):
+    """krylov_exp(solver, solver_in, solver_out, gamma, kdim, operator_solver, ...) with a `solver` that is NOT a
+    ShiftedOperator (test_krylov.py:44-62,89-90): anything that can hand over the matrices (a Firedrake
+    LinearVariationalSolver through firedrake_adapter, or an object with kexp_matrices()) is accepted."""
+    import krylov_exp_b200 as kx
+    from oracle.assemble_sw import test_pulse
+    sw = sw3
+
+    class HostSolver:                                    # stand-in for the Firedrake solver of the shifted problem
+        def kexp_matrices(self):
+            return sw.K, sw.Mu, sw.Meta_blocks
+
+    T = 3600.0
+    gamma = T / 10.0
+    ke = kx.krylov_exp(HostSolver(), None, None, gamma, 12, None, None, None)
+    x = test_pulse(sw)
+    y = np.empty(sw.n)
+    ke.apply(x, y, T, residuals=False)
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13, max_it=80)
+    sh = kx.ShiftedOperator(op, sw.K, sw.Mu, sw.Meta_blocks, gamma)
+    ke2 = kx.krylov_exp(sh, None, None, gamma, 12, op, None, None)
+    y2 = np.empty(sw.n)
+    ke2.apply(x, y2, T, residuals=False)
+    assert _relM(sw.M(), y, y2) < 1e-10
+    op.close()
+    ke.op.close()

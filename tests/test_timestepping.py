@@ -98,3 +98,50 @@ def test_gpu_time_step_matches_reference_ensemble(scheme, fused):
         d = U_old - ts["leapfrog_Uold"]
         assert np.sqrt((d @ (M @ d)) / (ts["leapfrog_Uold"] @ (M @ ts["leapfrog_Uold"]))) < 1e-10
     op.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_device_resident_time_step(scheme):
+    """DeviceAveragedStepper: state, stages, ensemble batches and cheby2 results stay in HBM, `slow` is a device
+    callback (torch ops on the library's stream).  Matches the reference ensemble's golden step and copies no state
+    vector between host and device during the step."""
+    import torch
+    import krylov_exp_b200 as kx
+    from krylov_exp_b200.timestepping import DeviceAveragedStepper
+    g, ts, K, M, nu, ne = _load()
+    Mbar, dt, rho, Lc, asselin = ts["meta"]
+    Mu = M[:nu][:, :nu].tocsr()
+    Meta = M[nu:][:, nu:].tobsr(blocksize=(3, 3)).data
+    op = kx.Operator(K, Mu, np.linalg.inv(Meta), rtol=1e-13, max_it=100)
+    cheby = kx.cheby_exp(op, None, None, 10000, 1e-8, Lc)
+    cheby2 = kx.cheby_exp(op, None, None, 10000, 1e-8, Lc)
+    t, w = kx.sample_times_weights(int(Mbar), dt, rho)
+    scale = float(np.abs(ts["U0"]).max())
+    slow_dev = lambda F: 1e-2 * F * torch.roll(F, 1, dims=-1) / scale        # the golden's synthetic N(.) on the device
+    st = DeviceAveragedStepper(cheby, cheby2, slow_dev, t, w, dt)
+    U = torch.tensor(ts["U0"], dtype=torch.float64, device="cuda")
+    U_old = torch.tensor(0.97 * ts["U0"], dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    if scheme == "leapfrog":                                 # warm-up step on copies (allocations, iteration tuning)
+        st.leapfrog(U.clone(), U_old.clone(), float(asselin))
+    else:
+        getattr(st, scheme)(U.clone())
+    st.synchronize()
+    op.stats_reset()
+    if scheme == "leapfrog":
+        st.leapfrog(U, U_old, float(asselin))
+    else:
+        getattr(st, scheme)(U)
+    st.synchronize()
+    stats = op.stats()
+    assert stats["h2d_vector_bytes"] == 0 and stats["d2h_vector_bytes"] == 0
+    Uh = U.cpu().numpy()
+    ref = ts[f"{scheme}_U"]
+    d = Uh - ref
+    assert np.sqrt((d @ (M @ d)) / (ref @ (M @ ref))) < 1e-10
+    if scheme == "leapfrog":
+        d = U_old.cpu().numpy() - ts["leapfrog_Uold"]
+        assert np.sqrt((d @ (M @ d)) / (ts["leapfrog_Uold"] @ (M @ ts["leapfrog_Uold"]))) < 1e-10
+    st.close()
+    op.close()
