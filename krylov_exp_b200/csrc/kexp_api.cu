@@ -108,6 +108,7 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
     }
     d.nbr = nbr; d.nblocks = nblocks; d.max_bpr = max_bpr;
     d.h_browptr = browptr;
+    if (force && nrows == ncols) d.h_blocks = blocks;
     d.diag_first = force && nrows == ncols && all_diag;
     if (max_bpr > kSpmmSmemBlocks) { cudaFree(d.browptr); cudaFree(d.blocks); d.browptr = nullptr; d.blocks = nullptr; d.h_browptr.clear(); }
     return 0;
@@ -278,6 +279,11 @@ int ensure_stage(kexp_ctx* ctx, size_t bytes) {
 #define KEXP_GB 1
 #endif
 constexpr int kSpmmGB = KEXP_GB;                 // gathered blocks in flight per block row
+// Narrow panels are latency bound (one L2 round trip per gathered group): they gather four of the five blocks of a row of S at once (two round trips instead of five; five spill at 128 registers).
+#ifndef KEXP_GB_NARROW
+#define KEXP_GB_NARROW 4
+#endif
+constexpr int solve_gb(int W) { return W <= 8 ? KEXP_GB_NARROW : KEXP_GB; }
 #ifndef KEXP_GB0
 #define KEXP_GB0 3
 #endif
@@ -326,7 +332,7 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
         double* xm = (xk == ctx->X) ? ctx->P : ctx->X;
         {   // one cooperative kernel for the whole solve when every CTA's row range fits its shared-memory stage
             const DevCsr& A = ctx->As;
-            auto k = cheb_solve_coop_kernel<W, kSpmmGB>;
+            auto k = cheb_solve_coop_kernel<W, solve_gb(W)>;
             // as many CTAs as can be co-resident (narrow panels would otherwise get few, long row ranges)
             const int grid = std::max(1, std::min(max_grid(ctx, k, kSpmmSmemBytes), A.nbr));
             const int rows_cta = (A.nbr + grid - 1) / grid;
@@ -360,12 +366,12 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
             omega = (it == 1) ? 1.0 / (1.0 - 0.5 * mu * mu) : 1.0 / (1.0 - 0.25 * mu * mu * omega);
             TimedLaunch tl(ctx, KC_SPMM_CG);
             if (it == K - 1) {
-                auto k = bsr3_cheb_iter_kernel<W, 1, kSpmmGB>;
+                auto k = bsr3_cheb_iter_kernel<W, 1, solve_gb(W)>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
                          omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
             } else {
-                auto k = bsr3_cheb_iter_kernel<W, 0, kSpmmGB>;
+                auto k = bsr3_cheb_iter_kernel<W, 0, solve_gb(W)>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
                          omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
@@ -566,8 +572,8 @@ void warm_occupancy(kexp_ctx* ctx) {
     max_grid(ctx, bsr3_spmm_kernel<W, 0, kSpmm0GB>, kSpmmSmemBytes); max_grid(ctx, bsr3_spmm_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
     max_grid(ctx, cg_init_kernel<W, kCptVec>); max_grid(ctx, cg_update_kernel<W, kCptVec>);
     max_grid(ctx, cheb_solve_init_kernel<W, kCptVec>);
-    max_grid(ctx, cheb_solve_coop_kernel<W, kSpmmGB>, kSpmmSmemBytes);
-    max_grid(ctx, bsr3_cheb_iter_kernel<W, 0, kSpmmGB>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter_kernel<W, 1, kSpmmGB>, kSpmmSmemBytes);
+    max_grid(ctx, cheb_solve_coop_kernel<W, solve_gb(W)>, kSpmmSmemBytes);
+    max_grid(ctx, bsr3_cheb_iter_kernel<W, 0, solve_gb(W)>, kSpmmSmemBytes); max_grid(ctx, bsr3_cheb_iter_kernel<W, 1, solve_gb(W)>, kSpmmSmemBytes);
     max_grid(ctx, cheb_update_kernel<W, 0>); max_grid(ctx, cheb_update_kernel<W, 1>); max_grid(ctx, cheb_update_kernel<W, 2>);
 }
 
@@ -823,6 +829,7 @@ int kexp_destroy(kexp_ctx* ctx) {
     for (double* b : bufs) cudaFree(b);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sc); cudaFree(ctx->d_counter);
     cudaFree(ctx->d_nk); cudaFree(ctx->d_nrtol2); cudaFree(ctx->d_npartials);
+    cudaFree(ctx->d_nlblocks); cudaFree(ctx->d_nhalo_ptr); cudaFree(ctx->d_nhalo_cols);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -898,6 +905,7 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
     invalidate_graphs(ctx);
     if (ctx->tmp_in) { kexp_batch_destroy(ctx->tmp_in); kexp_batch_destroy(ctx->tmp_out); ctx->tmp_in = ctx->tmp_out = nullptr; }
     ctx->have_op = false;
+    ctx->narrow_plan_G = 0;        // the CTA-local numbering of S belongs to the old operator
     ctx->n = n; ctx->n_s = n_s; ctx->n_b = n_b; ctx->n_d = n_d;
     ctx->curW = 0;   // panels are re-allocated for the new size
     ctx->lane_store[1 - ctx->cur_lane].curW = 0;

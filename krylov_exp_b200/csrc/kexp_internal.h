@@ -28,6 +28,7 @@ struct DevCsr {
     int64_t nblocks = 0;
     std::vector<int> h_browptr;    // host copy of browptr (stored row order): shared-memory budgeting of the persistent kernels
     std::vector<int> h_rowptr;     // host copy of rowptr
+    std::vector<double> h_blocks;  // host copy of the blocks (square matrices only: S)
     bool bsr() const { return blocks != nullptr; }
     double bytes() const {
         return bsr() ? 80.0 * (double)nblocks + 4.0 * (double)(nbr + 1) : 12.0 * (double)nnz + 4.0 * (double)(nrows + 1);
@@ -123,8 +124,12 @@ struct kexp_ctx {
     // and looked at by the next call that finds the copy finished, at the latest by kexp_synchronize / download
     // persistent narrow-panel apply kernel (kexp_narrow.cu)
     bool use_narrow = true;        // KEXP_NARROW=0: always the multi-launch path
-    int narrow_max_w = 8;          // widest panel that takes it (KEXP_NARROW_MAXW)
+    int narrow_max_w = 4;          // widest panel that takes it (KEXP_NARROW_MAXW; wider ones do not fit shared memory at ref 5)
     int narrow_slot = 0;           // constant-memory argument slot of this context
+    double* d_nlblocks = nullptr;  // S blocks with CTA-local column slots (kexp_narrow.cu: build_narrow_plan)
+    int* d_nhalo_ptr = nullptr;    // per CTA: range of its halo in d_nhalo_cols
+    int* d_nhalo_cols = nullptr;
+    int narrow_plan_G = 0, narrow_max_slots = 0, narrow_max_halo = 0;
     int* d_nk = nullptr;           // per-step iteration counts
     double* d_nrtol2 = nullptr;    // per-step squared tolerances
     double* d_npartials = nullptr; // per-CTA block sums

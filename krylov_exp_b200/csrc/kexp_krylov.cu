@@ -447,7 +447,7 @@ static int arnoldi_dev(kexp_ctx* ctx, int kdim, int its, double t, double* d_res
         memset(&args, 0, sizeof(args));
         args.count = 1; args.a[0] = k->w; args.b[0] = k->mw; args.n[0] = n;
         multidot_kernel<<<k->grid, kKryThreads, 0, ctx->stream>>>(args, k->d_partials, k->d_counter, k->d_dots);
-        arnoldi_norm_kernel<<<1, 1, 0, ctx->stream>>>(k->d_dots, nullptr, k->d_scal, nullptr);
+        arnoldi_norm_kernel<<<1, 1, 0, ctx->stream>>>(k->d_dots, nullptr, k->d_scal, nullptr, nullptr);
         scale2_kernel<<<grid_for(n, 4 * k->grid), kKryThreads, 0, ctx->stream>>>(k->V, k->Z, k->w, k->mw, k->d_scal, n);
         ctx->st_launches += 3;
     }
@@ -482,7 +482,7 @@ static int arnoldi_dev(kexp_ctx* ctx, int kdim, int its, double t, double* d_res
             memset(&args, 0, sizeof(args));
             args.count = 1; args.a[0] = k->w; args.b[0] = k->mw; args.n[0] = n;
             multidot_kernel<<<k->grid, kKryThreads, 0, ctx->stream>>>(args, k->d_partials, k->d_counter, k->d_dots);
-            arnoldi_norm_kernel<<<1, 1, 0, ctx->stream>>>(k->d_dots, k->d_H + (size_t)(j + 1) * ldh + j, k->d_scal + 2, k->d_info);
+            arnoldi_norm_kernel<<<1, 1, 0, ctx->stream>>>(k->d_dots, k->d_H + (size_t)(j + 1) * ldh + j, k->d_scal + 2, k->d_info, k->d_scal + 1);
             scale2_kernel<<<grid_for(n, 4 * k->grid), kKryThreads, 0, ctx->stream>>>(k->V + (size_t)(j + 1) * n, k->Z + (size_t)(j + 1) * n,
                                                                                       k->w, k->mw, k->d_scal + 2, n);
             ctx->st_launches += 3;

@@ -607,12 +607,14 @@ bicgstab_smem_kernel(BicgSmemArgs a) {
 //   scale2_kernel         V_{j+1} = scal w,  Z_{j+1} = scal Mw        (krylov_exp.py:78-80)
 //   residual_kernel       res[j] = max_q |sqrt(c2)/gamma * fac[q]|    (krylov_exp.py:99-100)
 // ------------------------------------------------------------------------------------
-__global__ void arnoldi_norm_kernel(const double* __restrict__ dot, double* __restrict__ Hentry, double* __restrict__ scal, int* __restrict__ info) {
+__global__ void arnoldi_norm_kernel(const double* __restrict__ dot, double* __restrict__ Hentry, double* __restrict__ scal, int* __restrict__ info,
+                                    const double* __restrict__ beta) {
     const double hn = sqrt(fmax(dot[0], 0.0));
     if (Hentry) *Hentry = hn;
     scal[0] = (hn > 0.0) ? 1.0 / hn : 0.0;
     scal[1] = hn;
-    if (!(hn > 0.0) && info) info[3] = 1;
+    // an invariant subspace is a breakdown; a zero start vector (beta = 0: exp(.) 0 = 0) is not
+    if (!(hn > 0.0) && info && beta && beta[0] > 0.0) info[3] = 1;
 }
 
 __global__ void __launch_bounds__(kKryThreads)

@@ -12,8 +12,12 @@
 //   * phases separated by grid-wide barriers only:   per term   A: T = K~ S_{n-1} (depth rows updated in the epilogue)
 //     | B: K-1 Chebyshev iterations of the mass solve, the edge-row recurrence update fused into the last one
 //     | C: interior rows  w_I = T_I + R w_E  and their update   -> K + 2 barriers per term;
-//   * every gather of a block row is issued before the first use (the whole 5-block row of S in flight at once);
-//   * data written by other CTAs is read with ld.global.cg (L2), everything else through the normal path;
+//   * inside the mass solve the iterate lives in SHARED memory: x_k for the CTA's own rows plus the halo rows its
+//     blocks reference (local slot numbers precomputed on the host), x_{k-1} / x_{k+1} for the own rows, and b.  Per
+//     iteration a CTA reads only its halo (each row once, coalesced, ld.global.cg) and publishes its own rows; the
+//     products read shared memory, so there is no gather latency chain, no L1 coherence question and hardly any
+//     register pressure;
+//   * data written by other CTAs is read with ld.global.cg (L2, the coherence point), everything else normally;
 //   * the convergence record of every mass solve (||b - S x||/||b|| per column against the relaxed tolerance of
 //     its term) is reduced in fixed order by CTA 0 behind the barrier that follows the solve.
 // The arithmetic per row is the same as in the wide-panel kernels (kexp_kernels.cuh): same three-term Chebyshev
@@ -21,6 +25,7 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 #include "kexp_internal.h"
@@ -30,9 +35,8 @@ namespace cg = cooperative_groups;
 namespace kexp {
 
 template <int W> struct NarrowCfg {
-    static constexpr int NT = 256;                   // 1 CTA per SM: up to 255 registers per thread, no spills in the hot loops
+    static constexpr int NT = 512;                   // 1 CTA per SM, 128 registers per thread
     static constexpr int GK = 4;                     // gathered blocks of K~ in flight per row
-    static constexpr int GS = 5;                     // the same for S (5 blocks per BDM2 edge row: the whole row at once)
 };
 constexpr int kNTmax = 512;
 constexpr int kNWarpsMax = kNTmax / 32;
@@ -43,6 +47,9 @@ struct NarrowArgs {
     const int* kt_browptr; const double* kt_blocks; const int* kt_rowmap; int kt_nbr;
     // S (BSR 3x3, diagonal block first), block-Jacobi inverse
     const int* s_browptr; const double* s_blocks; const double* Pinv; int s_nbr;
+    // s_blocks here is the LOCALLY indexed copy: the 10th double of a block holds the shared-memory slot of its column
+    // (own rows first, then the CTA's halo rows); halo_ptr[c] .. halo_ptr[c+1]: global block rows of CTA c's halo
+    const int* halo_ptr; const int* halo_cols;
     // R (CSR, n_b x n_s) or null; Dblk (n_d/3 blocks) or null
     const int* r_rowptr; const int* r_col; const double* r_val; const double* Dblk;
     int n, n_s, n_b, n_d;
@@ -57,7 +64,8 @@ struct NarrowArgs {
     CgScalars* sc; double* partials;     // [gridDim][2][W] block sums of ||r||^2, ||b||^2
     unsigned* barrier;                   // grid barrier counter (zeroed before the launch)
     // shared-memory layout (element counts, maxima over the CTAs)
-    int cap_s_blocks, cap_s_rows, cap_kt_rows, cap_kt_blocks, cap_r_rows, cap_r_nnz;
+    int cap_s_blocks, cap_s_rows, cap_kt_rows, cap_kt_blocks, cap_r_rows, cap_r_nnz, cap_slots, cap_halo;
+    int xs_offset;                       // first double of the iterate buffers in dynamic shared memory
 };
 
 // The arguments live in constant memory (one slot per context, round-robin): the phases below are separate, NOT
@@ -212,9 +220,12 @@ KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restr
     }
 }
 
-// ---- phase B, start: x_0 = 0, x_1 = alpha P^-1 b on the own rows; returns the thread's share of ||b||^2
+// Shared-memory state of the mass solve (per CTA): xa = x_k on [own rows | halo rows], xb = x_{k-1} on the own rows (it
+// becomes x_{k+1}; its halo part is filled after the next barrier), bs = b on the own rows.  Row r of a slot starts at
+// (3*slot + r) * W doubles.
+// ---- phase B, start: x_0 = 0, x_1 = alpha P^-1 b on the own rows (shared memory + published); returns ||b||^2 share
 template <int W>
-KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* xk, double* xm, const double* __restrict__ sP, int s0, int s1) {
+KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* xg, double* xa, double* xb, double* bs, const double* __restrict__ sP, int s0, int s1) {
     const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -226,10 +237,12 @@ KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* xk, double* xm, const
         const int br = base + warp * BRW + g;
         if (br < s1) {
             const size_t o = (size_t)(3 * br) * W + 2 * l;
+            const int ls = (3 * (br - s0)) * W + 2 * l;
             double2 bv[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 bv[i] = ldcg2(a.T + o + (size_t)i * W);
+                *reinterpret_cast<double2*>(bs + ls + i * W) = bv[i];
                 accb.x = fma(bv[i].x, bv[i].x, accb.x); accb.y = fma(bv[i].y, bv[i].y, accb.y);
             }
             const double* Pb = sP + 9 * (br - s0);
@@ -238,24 +251,38 @@ KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* xk, double* xm, const
                 double2 z;
                 z.x = a.alpha * fma(Pb[3 * i], bv[0].x, fma(Pb[3 * i + 1], bv[1].x, Pb[3 * i + 2] * bv[2].x));
                 z.y = a.alpha * fma(Pb[3 * i], bv[0].y, fma(Pb[3 * i + 1], bv[1].y, Pb[3 * i + 2] * bv[2].y));
-                *reinterpret_cast<double2*>(xk + o + (size_t)i * W) = z;
-                *reinterpret_cast<double2*>(xm + o + (size_t)i * W) = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2*>(xa + ls + i * W) = z;
+                *reinterpret_cast<double2*>(xb + ls + i * W) = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2*>(xg + o + (size_t)i * W) = z;
             }
         }
     }
     return accb;
 }
 
-// ---- phase B, one Chebyshev iteration on the own rows: x_{k+1} overwrites x_{k-1}; LAST also forms ||b - S x_k||^2 and
-// the recurrence update of the edge rows (W = x_K)
+// ---- phase B, halo: the rows of x_k this CTA's blocks reference outside its own range, global -> shared (each row once,
+// 16-byte pieces, coalesced within a row)
+template <int W>
+KEXP_PHASE_FN void narrow_load_halo(const double* xg, double* xa, const int* __restrict__ hcols, int n_own, int n_halo) {
+    constexpr int PPR = 3 * W / 2;                     // 16-byte pieces per block row (3 rows x W doubles, contiguous)
+    constexpr int NT = NarrowCfg<W>::NT;
+    for (int e = threadIdx.x; e < n_halo * PPR; e += NT) {
+        const int h = e / PPR, p = e % PPR;
+        const double2 v = ldcg2(xg + (size_t)(3 * hcols[h]) * W + 2 * p);
+        *reinterpret_cast<double2*>(xa + (size_t)(3 * (n_own + h)) * W + 2 * p) = v;
+    }
+}
+
+// ---- phase B, one Chebyshev iteration on the own rows, everything read from shared memory: x_{k+1} overwrites x_{k-1}
+// (shared) and is published to xg_out; LAST also forms ||b - S x_k||^2 and the recurrence update of the edge rows (W = x_K)
 template <int W, bool LAST>
-KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double* xk, double* xm, double omega,
-                                                 const double2* __restrict__ sblk, const double* __restrict__ sP, const int* __restrict__ sptr,
-                                                 int s0, int s1) {
+KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double* xa, double* xb, const double* bs, double* xg_out, double omega,
+                                        const double2* __restrict__ sblk, const double* __restrict__ sP, const int* __restrict__ sptr,
+                                        int s0, int s1) {
     const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
-    constexpr int BPC = (NarrowCfg<W>::NT / 32) * BRW, kGatherS = NarrowCfg<W>::GS;
+    constexpr int BPC = (NarrowCfg<W>::NT / 32) * BRW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane % LPB, g = lane / LPB;
     UpdCtx u;
@@ -265,60 +292,41 @@ KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double
         const int br = base + warp * BRW + g;
         if (br < s1) {
             const int q0 = sptr[br - s0], q1 = sptr[br - s0 + 1];
-            const size_t o = (size_t)(3 * br) * W + 2 * l;
+            const int ls = (3 * (br - s0)) * W + 2 * l;
             double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
-            double2 xo[3], bv[3], xmv[3];
-            // everything this row needs is requested before the first use: the own rows of b and x_{k-1} and the gathered
-            // rows of up to kGatherS blocks (the first one is the diagonal block: the row's own x_k)
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                bv[i] = ldcg2(a.T + o + (size_t)i * W);
-                xmv[i] = ldcg2(xm + o + (size_t)i * W);
-            }
-            for (int q = q0; q < q1; q += kGatherS) {
-                double2 x[kGatherS][3];
-#pragma unroll
-                for (int j = 0; j < kGatherS; ++j)
-                    if (q + j < q1) {
-                        const int c = __double2loint(sblk[5 * (q + j) + 4].y);
-                        const double* xr = xk + (size_t)(3 * c) * W + 2 * l;
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) x[j][r] = ldcg2(xr + (size_t)r * W);
-                    }
-                if (q == q0) {
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) xo[i] = x[0][i];
-                }
-#pragma unroll
-                for (int j = 0; j < kGatherS; ++j)
-                    if (q + j < q1) {
-                        const double2* bp = sblk + 5 * (q + j);
-                        const double2 v01 = bp[0], v23 = bp[1], v45 = bp[2], v67 = bp[3], v8c = bp[4];
-                        const double m[3][3] = {{v01.x, v01.y, v23.x}, {v23.y, v45.x, v45.y}, {v67.x, v67.y, v8c.x}};
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                acc[i].x = fma(m[i][r], x[j][r].x, acc[i].x);
-                                acc[i].y = fma(m[i][r], x[j][r].y, acc[i].y);
-                            }
-                    }
+            for (int q = q0; q < q1; ++q) {
+                const double2* bp = sblk + 5 * q;
+                const double2 v01 = bp[0], v23 = bp[1], v45 = bp[2], v67 = bp[3], v8c = bp[4];
+                const double* xr = xa + (3 * __double2loint(v8c.y)) * W + 2 * l;
+                const double2 x0 = *reinterpret_cast<const double2*>(xr), x1 = *reinterpret_cast<const double2*>(xr + W),
+                              x2 = *reinterpret_cast<const double2*>(xr + 2 * W);
+                acc[0].x = fma(v01.x, x0.x, fma(v01.y, x1.x, fma(v23.x, x2.x, acc[0].x)));
+                acc[0].y = fma(v01.x, x0.y, fma(v01.y, x1.y, fma(v23.x, x2.y, acc[0].y)));
+                acc[1].x = fma(v23.y, x0.x, fma(v45.x, x1.x, fma(v45.y, x2.x, acc[1].x)));
+                acc[1].y = fma(v23.y, x0.y, fma(v45.x, x1.y, fma(v45.y, x2.y, acc[1].y)));
+                acc[2].x = fma(v67.x, x0.x, fma(v67.y, x1.x, fma(v8c.x, x2.x, acc[2].x)));
+                acc[2].y = fma(v67.x, x0.y, fma(v67.y, x1.y, fma(v8c.x, x2.y, acc[2].y)));
             }
             double2 rv[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                rv[i].x = bv[i].x - acc[i].x; rv[i].y = bv[i].y - acc[i].y;
+                const double2 bv = *reinterpret_cast<const double2*>(bs + ls + i * W);
+                rv[i].x = bv.x - acc[i].x; rv[i].y = bv.y - acc[i].y;
                 if (LAST) { accr.x = fma(rv[i].x, rv[i].x, accr.x); accr.y = fma(rv[i].y, rv[i].y, accr.y); }
             }
             const double* Pb = sP + 9 * (br - s0);
+            const size_t o = (size_t)(3 * br) * W + 2 * l;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
+                const double2 xo = *reinterpret_cast<const double2*>(xa + ls + i * W);
+                const double2 xmv = *reinterpret_cast<const double2*>(xb + ls + i * W);
                 double2 z, xn;
                 z.x = fma(Pb[3 * i], rv[0].x, fma(Pb[3 * i + 1], rv[1].x, Pb[3 * i + 2] * rv[2].x));
                 z.y = fma(Pb[3 * i], rv[0].y, fma(Pb[3 * i + 1], rv[1].y, Pb[3 * i + 2] * rv[2].y));
-                xn.x = fma(omega, fma(a.alpha, z.x, xo[i].x) - xmv[i].x, xmv[i].x);
-                xn.y = fma(omega, fma(a.alpha, z.y, xo[i].y) - xmv[i].y, xmv[i].y);
-                *reinterpret_cast<double2*>(xm + o + (size_t)i * W) = xn;
+                xn.x = fma(omega, fma(a.alpha, z.x, xo.x) - xmv.x, xmv.x);
+                xn.y = fma(omega, fma(a.alpha, z.y, xo.y) - xmv.y, xmv.y);
+                *reinterpret_cast<double2*>(xb + ls + i * W) = xn;
+                *reinterpret_cast<double2*>(xg_out + o + (size_t)i * W) = xn;
                 if (LAST) row_update(u, o + (size_t)i * W, (size_t)(3 * br + i), xn);     // edge rows: W = x_K
             }
         }
@@ -425,6 +433,11 @@ cheb_apply_narrow_kernel(const int slot) {
     int* kcol = kptr + a.cap_kt_rows + 1;
     int* rptr = kcol + a.cap_kt_blocks;
     int* rcol = rptr + a.cap_r_rows + 1;
+    int* hcol = rcol + a.cap_r_nnz;
+    // mass-solve state: two iterate buffers over [own | halo] slots and b on the own rows (16-byte aligned)
+    double* xs0 = reinterpret_cast<double*>(smem2) + a.xs_offset;
+    double* xs1 = xs0 + (size_t)3 * W * a.cap_slots;
+    double* bsm = xs1 + (size_t)3 * W * a.cap_slots;
     __shared__ int s_bad;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -452,6 +465,9 @@ cheb_apply_narrow_kernel(const int slot) {
             for (int i = threadIdx.x; i < q1 - q0; i += kNT) rcol[i] = __ldg(a.r_col + q0 + i);
         }
     }
+    const int h0 = __ldg(a.halo_ptr + blockIdx.x), n_halo = __ldg(a.halo_ptr + blockIdx.x + 1) - h0;
+    for (int i = threadIdx.x; i < n_halo; i += kNT) hcol[i] = __ldg(a.halo_cols + h0 + i);
+    const int n_own = s1 - s0;
     // ---- prologue on a linear slice of the rows:  mode 0: Y = a_0 S_0 (and basis[:,0]);  mode 1: SA = z_M e_0, SB = 0
     {
         int p0, p1;
@@ -489,17 +505,22 @@ cheb_apply_narrow_kernel(const int slot) {
 
         // mass solve on the own rows of S (Chebyshev semi-iteration), K - 1 iterations behind x_1
         const int K = a.kterm[step];
-        double* xk = (K % 2 == 1) ? a.X : a.P;               // x_1 here, x_K ends up in a.X
+        double* xk = (K % 2 == 1) ? a.X : a.P;               // x_1 is published here, x_K ends up in a.X
         double* xm = (xk == a.X) ? a.P : a.X;
-        double2 accb = narrow_solve_start<W>(slot, xk, xm, sP, s0, s1);
+        double* xa = xs0;                                    // shared: x_k on [own | halo]
+        double* xb = xs1;                                    // shared: x_{k-1} on the own rows -> x_{k+1}
+        double2 accb = narrow_solve_start<W>(slot, xk, xa, xb, bsm, sP, s0, s1);
         double2 accr = make_double2(0.0, 0.0);
         double omega = 1.0;
         for (int it = 1; it < K; ++it) {
-            narrow_barrier(grid, a.barrier, bar_target);
+            narrow_barrier(grid, a.barrier, bar_target);     // x_k of every CTA is published (and this CTA's shared copy complete)
+            narrow_load_halo<W>(xk, xa, hcol, n_own, n_halo);
+            __syncthreads();
             omega = (it == 1) ? 1.0 / (1.0 - 0.5 * a.mu * a.mu) : 1.0 / (1.0 - 0.25 * a.mu * a.mu * omega);
-            if (it == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, xk, xm, omega, sblk, sP, sptr, s0, s1);
-            else narrow_solve_iter<W, false>(slot, sx, xk, xm, omega, sblk, sP, sptr, s0, s1);
+            if (it == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, xa, xb, bsm, xm, omega, sblk, sP, sptr, s0, s1);
+            else narrow_solve_iter<W, false>(slot, sx, xa, xb, bsm, xm, omega, sblk, sP, sptr, s0, s1);
             double* tsw = xk; xk = xm; xm = tsw;
+            tsw = xa; xa = xb; xb = tsw;
         }
         // block sums of ||r||^2 and ||b||^2 per column (fixed order): shuffles over the groups of a warp, then the warps
         {
@@ -534,7 +555,7 @@ cheb_apply_narrow_kernel(const int slot) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct NarrowCaps { int s_blocks, s_rows, kt_rows, kt_blocks, r_rows, r_nnz; size_t smem; };
+struct NarrowCaps { int s_blocks, s_rows, kt_rows, kt_blocks, r_rows, r_nnz, slots, halo; size_t smem; };
 
 static void range_of(int nrows, int c, int G, int& start, int& end) {
     const int per = nrows / G, rem = nrows % G;
@@ -542,21 +563,75 @@ static void range_of(int nrows, int c, int G, int& start, int& end) {
     end = start + per + (c < rem ? 1 : 0);
 }
 
+// bytes of the constant part (matrix, index arrays, scratch), rounded to 16: the iterate buffers start there
 template <int W>
-static size_t narrow_smem(const NarrowCaps& c) {
+static size_t narrow_smem_fixed(const NarrowCaps& c) {
     size_t b = sizeof(double2) * 5 * (size_t)c.s_blocks + sizeof(double) * 9 * (size_t)c.s_rows;
     b += sizeof(double) * (2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);
-    b += sizeof(int) * ((size_t)c.s_rows + 1 + c.kt_rows + 1 + c.kt_blocks + c.r_rows + 1 + c.r_nnz);
+    b += sizeof(int) * ((size_t)c.s_rows + 1 + c.kt_rows + 1 + c.kt_blocks + c.r_rows + 1 + c.r_nnz + c.halo);
     return (b + 15) & ~(size_t)15;
 }
 
+template <int W>
+static size_t narrow_smem(const NarrowCaps& c) {
+    return narrow_smem_fixed<W>(c) + sizeof(double) * 3 * W * ((size_t)2 * c.slots + c.s_rows);
+}
+
 // Shared-memory capacities for a grid of G CTAs (from the host copies of the row pointers kept at upload time).
+// Per-CTA local numbering of S for a grid of G CTAs: own rows take slots 0..n_own-1, the halo (block columns referenced
+// outside the own range, sorted) the slots behind them; the device gets a copy of the blocks with the slot in place of the
+// global block column.  Built once per operator.
+static int build_narrow_plan(kexp_ctx* ctx, int G) {
+    if (ctx->narrow_plan_G == G && ctx->d_nlblocks) return 0;
+    const std::vector<int>& sb = ctx->As.h_browptr;
+    const std::vector<double>& blk = ctx->As.h_blocks;
+    if (sb.empty() || blk.empty()) return kexp::fail(ctx, "narrow apply: host copy of S not available");
+    const int nbr = (int)sb.size() - 1;
+    std::vector<double> lb(blk);
+    std::vector<int> hptr((size_t)G + 1, 0), hcols, halo;
+    int max_slots = 0, max_halo = 0;
+    for (int c = 0; c < G; ++c) {
+        int r0, r1;
+        range_of(nbr, c, G, r0, r1);
+        halo.clear();
+        for (int k = sb[r0]; k < sb[r1]; ++k) {
+            int64_t bits; memcpy(&bits, &blk[(size_t)k * 10 + 9], 8);
+            const int col = (int)bits;
+            if (col < r0 || col >= r1) halo.push_back(col);
+        }
+        std::sort(halo.begin(), halo.end());
+        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+        for (int k = sb[r0]; k < sb[r1]; ++k) {
+            int64_t bits; memcpy(&bits, &blk[(size_t)k * 10 + 9], 8);
+            const int col = (int)bits;
+            int64_t slot = (col >= r0 && col < r1) ? col - r0
+                                                   : (r1 - r0) + (int)(std::lower_bound(halo.begin(), halo.end(), col) - halo.begin());
+            memcpy(&lb[(size_t)k * 10 + 9], &slot, 8);
+        }
+        hcols.insert(hcols.end(), halo.begin(), halo.end());
+        hptr[c + 1] = (int)hcols.size();
+        max_slots = std::max(max_slots, r1 - r0 + (int)halo.size());
+        max_halo = std::max(max_halo, (int)halo.size());
+    }
+    cudaFree(ctx->d_nlblocks); cudaFree(ctx->d_nhalo_ptr); cudaFree(ctx->d_nhalo_cols);
+    ctx->d_nlblocks = nullptr; ctx->d_nhalo_ptr = ctx->d_nhalo_cols = nullptr;
+    KEXP_CUDA(cudaMalloc(&ctx->d_nlblocks, sizeof(double) * lb.size()));
+    KEXP_CUDA(cudaMalloc(&ctx->d_nhalo_ptr, sizeof(int) * hptr.size()));
+    KEXP_CUDA(cudaMalloc(&ctx->d_nhalo_cols, sizeof(int) * std::max<size_t>(hcols.size(), 1)));
+    KEXP_CUDA(cudaMemcpy(ctx->d_nlblocks, lb.data(), sizeof(double) * lb.size(), cudaMemcpyHostToDevice));
+    KEXP_CUDA(cudaMemcpy(ctx->d_nhalo_ptr, hptr.data(), sizeof(int) * hptr.size(), cudaMemcpyHostToDevice));
+    KEXP_CUDA(cudaMemcpy(ctx->d_nhalo_cols, hcols.data(), sizeof(int) * hcols.size(), cudaMemcpyHostToDevice));
+    ctx->narrow_plan_G = G; ctx->narrow_max_slots = max_slots; ctx->narrow_max_halo = max_halo;
+    return 0;
+}
+
 bool narrow_caps(kexp_ctx* ctx, int G, NarrowCaps& c) {
     const std::vector<int>& sb = ctx->As.h_browptr;
     const std::vector<int>& kb = ctx->Kt.h_browptr;
     const std::vector<int>& rp = ctx->Rt.h_rowptr;
     if (sb.empty() || kb.empty()) return false;
-    c = NarrowCaps{0, 0, 0, 0, 0, 0, 0};
+    if (build_narrow_plan(ctx, G)) return false;
+    c = NarrowCaps{0, 0, 0, 0, 0, 0, ctx->narrow_max_slots, ctx->narrow_max_halo, 0};
     for (int i = 0; i < G; ++i) {
         int a, b;
         range_of((int)sb.size() - 1, i, G, a, b);
@@ -628,7 +703,8 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     KEXP_CUDA(cudaMemcpyAsync(ctx->d_nrtol2, rtol2, sizeof(double) * (size_t)(M + 1), cudaMemcpyHostToDevice, ctx->stream));
     NarrowArgs a;
     a.kt_browptr = ctx->Kt.browptr; a.kt_blocks = ctx->Kt.blocks; a.kt_rowmap = ctx->Kt.rowmap; a.kt_nbr = ctx->Kt.nbr;
-    a.s_browptr = ctx->As.browptr; a.s_blocks = ctx->As.blocks; a.Pinv = ctx->d_Pinv; a.s_nbr = ctx->As.nbr;
+    a.s_browptr = ctx->As.browptr; a.s_blocks = ctx->d_nlblocks; a.Pinv = ctx->d_Pinv; a.s_nbr = ctx->As.nbr;
+    a.halo_ptr = ctx->d_nhalo_ptr; a.halo_cols = ctx->d_nhalo_cols;
     a.r_rowptr = ctx->Rt.rowptr; a.r_col = ctx->Rt.col; a.r_val = ctx->Rt.val; a.Dblk = ctx->d_Dblk;
     a.n = (int)ctx->n; a.n_s = (int)ctx->n_s; a.n_b = (int)ctx->n_b; a.n_d = (int)ctx->n_d;
     a.SA = ctx->S0; a.SB = ctx->S1; a.Y = ctx->Y; a.T = ctx->T; a.X = ctx->X; a.P = ctx->P;
@@ -641,7 +717,13 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     a.barrier = reinterpret_cast<unsigned*>(ctx->d_npartials + 2 * kMaxW * (size_t)ctx->num_sms);
     KEXP_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), ctx->stream));
     a.cap_s_blocks = caps.s_blocks; a.cap_s_rows = caps.s_rows; a.cap_kt_rows = caps.kt_rows; a.cap_kt_blocks = caps.kt_blocks;
-    a.cap_r_rows = caps.r_rows; a.cap_r_nnz = caps.r_nnz;
+    a.cap_r_rows = caps.r_rows; a.cap_r_nnz = caps.r_nnz; a.cap_slots = caps.slots; a.cap_halo = caps.halo;
+    switch (W) {
+        case 2: a.xs_offset = (int)(narrow_smem_fixed<2>(caps) / sizeof(double)); break;
+        case 4: a.xs_offset = (int)(narrow_smem_fixed<4>(caps) / sizeof(double)); break;
+        case 8: a.xs_offset = (int)(narrow_smem_fixed<8>(caps) / sizeof(double)); break;
+        default: a.xs_offset = (int)(narrow_smem_fixed<16>(caps) / sizeof(double)); break;
+    }
     int rc = 1;
     switch (W) {
         case 2: rc = launch_narrow_w<2>(ctx, a, caps); break;

@@ -42,7 +42,7 @@ def _m1_inputs(sw, B, seed=1234):
 # (a) per-iteration mass-solve path and the other environment-switched variants
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env,path", [({"KEXP_COOP": "0", "KEXP_NARROW": "0"}, 1), ({"KEXP_COOP": "0", "KEXP_NO_GRAPH": "1", "KEXP_NARROW": "0"}, 1),
-                                      ({"KEXP_NARROW": "0"}, 2), ({"KEXP_NARROW_MAXW": "16", "KEXP_PANEL_CAP": "16"}, 3),
+                                      ({"KEXP_NARROW": "0"}, 2), ({"KEXP_NARROW_MAXW": "8"}, 3),
                                       ({"KEXP_LANES": "2"}, None), ({"KEXP_PANEL_CAP": "16"}, None),
                                       ({"KEXP_RELAX": "0", "KEXP_PDL": "0"}, None)])
 def test_switched_variants_ref3_against_oracle(sw3, monkeypatch, env, path):
@@ -352,6 +352,7 @@ def test_async_mode_defers_the_check_not_the_error(sw2):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B", [1, 3, 4, 7, 8])
 def test_narrow_kernel_equals_multi_launch_path(sw3, monkeypatch, B):
+    monkeypatch.setenv("KEXP_NARROW_MAXW", "8")           # ref 3: panels of up to 8 columns fit shared memory
     """Same rows, same order of operations: the persistent kernel must reproduce the multi-launch path to round-off
     (forward recurrence, shared-input basis run, fused Clenshaw average), with the same iteration counts."""
     import krylov_exp_b200 as kx
@@ -390,6 +391,7 @@ def test_narrow_kernel_against_oracle(sw3, condense):
     L = kx.EIGS[0] * dt * rho
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-13, max_it=80, solver="chebyshev", condense=condense)
     ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L)
+    B = 4                                                  # default: panels of up to 4 columns take the persistent kernel
     t, w = kx.sample_times_weights(B, dt, rho)
     x, X = _m1_inputs(sw, B)
     Y = ce.apply_batch(X, -t)
@@ -407,7 +409,8 @@ def test_narrow_kernel_against_oracle(sw3, condense):
 
 
 def test_narrow_kernel_ref5_columns_against_cpu_port():
-    """The strong-scaling share of M1 (8 of the 64 samples on one GPU) through the persistent kernel at full size."""
+    """A strong-scaling share of M1 (4 of the 64 samples, and the shared-input forward pass) through the persistent kernel
+    at full size."""
     import krylov_exp_b200 as kx
     from oracle import coeffs, norms
     from oracle.cpu_port import CpuCheby
@@ -418,7 +421,7 @@ def test_narrow_kernel_ref5_columns_against_cpu_port():
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-11, max_it=40, solver="chebyshev")
     ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L, spectral_radius=eig)
     t_all, w_all = kx.sample_times_weights(64, DT, RHO)
-    cols = np.arange(5, 64, 8)
+    cols = np.arange(5, 64, 16)                            # 4 columns: the widest panel that fits shared memory at ref 5
     t = np.ascontiguousarray(t_all[cols])
     x, Xall = _m1_inputs(sw, 64)
     X = Xall[cols]
