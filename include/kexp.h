@@ -213,6 +213,19 @@ int kexp_krylov_apply_batch(kexp_ctx* ctx, const double* X, int64_t ldx, int x_i
  * E = expm(A), A m x m row-major, m <= 64 */
 int kexp_dense_expm(kexp_ctx* ctx, const double* A, int m, double* E);
 
+/* ---- nonlinear slow right-hand side (the step between the two exponentials of an averaged evaluation) -------------
+ * L(U) of /root/reference/averaged_sw_explicit.py:177-213 (vector-invariant, upwinded) for B ensemble members at once:
+ * U, L are DEVICE arrays of B vectors of n = n_u + n_eta doubles in the user dof order (vector k at U + k*ldu), the
+ * tables are the device copies of krylov_exp_b200.slow_rhs.SlowTables (per-cell geometry factors at the quadrature
+ * points, basis tabulations, facet neighbours; host-side input generation like the assembled K and M).  Enqueued on
+ * `cuda_stream`; SlowSolver.solve() = M^-1 L is this followed by kexp_operator_apply_dev of a context whose K is the
+ * identity.  nq <= 36 cell points, nf <= 6 facet points. */
+int kexp_slow_form_dev(void* cuda_stream, int n_cells, int n_u, int n_eta, int nq, int nf,
+                       const double* cell, const double* fac, const double* Phi, const double* dPhi, const double* gPhi,
+                       const double* Psi, const double* gPsi, const double* PhiF, const double* PsiF, const double* qw,
+                       const double* sign, const int32_t* dofs, const int32_t* nbr_cell, const int32_t* nbr_edge, const double* b,
+                       const double* U, int64_t ldu, double* L, int64_t ldl, int B, double dT);
+
 /* ---- multi-GPU: one context per GPU/process; unique id from ncclGetUniqueId -------- */
 int kexp_comm_unique_id(void* id128);                       /* 128-byte buffer */
 int kexp_comm_init(kexp_ctx* ctx, const void* id128, int rank, int nranks);

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "kexp_krylov_apply": (C.c_int, [_p, _p, _p, C.c_double, C.c_int, C.c_int, _p, _p, _p]),
     "kexp_krylov_apply_batch": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, C.c_int, C.c_int, C.c_int]),
     "kexp_dense_expm": (C.c_int, [_p, _p, C.c_int, _p]),
+    "kexp_slow_form_dev": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [_p] * 15 + [_p, C.c_int64, _p, C.c_int64, C.c_int, C.c_double]),
     "kexp_comm_unique_id": (C.c_int, [_p]),
     "kexp_comm_init": (C.c_int, [_p, _p, C.c_int, C.c_int]),
     "kexp_allreduce_sum_dev": (C.c_int, [_p, _p, C.c_int64]),

@@ -115,6 +115,14 @@ def _eval_mono_grad(pts, exps):
     return gx, gy
 
 
+def _eval_mono_hess(pts, exps):
+    x, y = pts[:, 0], pts[:, 1]
+    hxx = np.stack([(i * (i - 1) * x ** max(i - 2, 0) if i > 1 else 0 * x) * y ** j for (i, j) in exps], axis=1)
+    hxy = np.stack([(i * x ** max(i - 1, 0) if i else 0 * x) * (j * y ** max(j - 1, 0) if j else 0 * y) for (i, j) in exps], axis=1)
+    hyy = np.stack([x ** i * (j * (j - 1) * y ** max(j - 2, 0) if j > 1 else 0 * y) for (i, j) in exps], axis=1)
+    return hxx, hxy, hyy
+
+
 def p3_nodes(variant: str = "equispaced"):
     """Reference nodes of the cubic Lagrange geometry element: 3 vertices, 2 per
     edge, centroid.  'equispaced' or 'gll' edge-node placement."""
@@ -142,6 +150,11 @@ class Lagrange:
     def tab_grad(self, pts):
         gx, gy = _eval_mono_grad(pts, self.exps)
         return gx @ self.coef, gy @ self.coef
+
+    def tab_hess(self, pts):
+        """Second reference derivatives (xx, xy, yy) of the nodal basis, each (nq, nnodes)."""
+        hxx, hxy, hyy = _eval_mono_hess(pts, self.exps)
+        return hxx @ self.coef, hxy @ self.coef, hyy @ self.coef
 
 
 _GAUSS3 = 0.5 * (roots_legendre(3)[0] + 1.0)     # edge dof points, symmetric about 1/2
@@ -176,6 +189,17 @@ class BDM2:
         V[11, nm:] = qw @ (m * qp[:, 0:1])
         self.coef = np.linalg.inv(V)         # column j = monomial coefficients of basis fn j
 
+    def tab_grad(self, pts):
+        """(nq, 12, 2, 2): [q, j, a, b] = d(component a of basis function j)/d(xi_b)."""
+        nm = len(self.exps)
+        gx, gy = _eval_mono_grad(pts, self.exps)
+        out = np.empty((pts.shape[0], 12, 2, 2))
+        out[:, :, 0, 0] = gx @ self.coef[:nm]
+        out[:, :, 0, 1] = gy @ self.coef[:nm]
+        out[:, :, 1, 0] = gx @ self.coef[nm:]
+        out[:, :, 1, 1] = gy @ self.coef[nm:]
+        return out
+
     def tab(self, pts):
         """(nq, 12, 2) values and (nq, 12) reference divergences."""
         nm = len(self.exps)
@@ -206,6 +230,8 @@ class SWOperator:
     g: float
     H: float
     radius: float
+    omega: float = OMEGA
+    p3_variant: str = "equispaced"
     Mu_elem: np.ndarray = None  # (C,12,12) signed element mass matrices
     Kuu_elem: np.ndarray = None  # (C,12,12) signed -Coriolis element matrices
     Kue_ref: np.ndarray = None  # (12,3) g * <psi_j, div v_i> (unsigned, reference)
@@ -229,21 +255,10 @@ class SWOperator:
         return fn(X[:, 0], X[:, 1], X[:, 2])
 
 
-def assemble_sw(ref_level: int, degree: int = 3, radius: float = R_EARTH,
-                g: float = GRAV, H: float = H_MEAN, omega: float = OMEGA,
-                c_scaled: bool = False, coriolis: bool = True,
-                nquad=6, p3_variant: str = "equispaced",
-                keep_elem: bool = False) -> SWOperator:
-    """Assemble K, M_u, M_eta, <div,div> for the given mesh.
-
-    c_scaled=True uses c = sqrt(gH) on both coupling terms (test_cheby.py:30,38-42).
-    """
-    if c_scaled:
-        g = H = float(np.sqrt(g * H))
+def cell_geometry(ref_level: int, degree: int = 3, radius: float = R_EARTH, p3_variant: str = "equispaced"):
+    """Vertices, cells, geometry nodes per cell X (C, nnodes, 3) and the Lagrange geometry element of the mesh
+    IcosahedralSphereMesh(radius, refinement_level, degree) stands for."""
     V, C = icosahedral_mesh(ref_level, radius)
-    nc = C.shape[0]
-
-    # geometry nodes per cell
     if degree == 1:
         geo = Lagrange(_REF_V.copy(), 1)
         X = V[C]                                             # (C,3,3)
@@ -255,6 +270,22 @@ def assemble_sw(ref_level: int, degree: int = 3, radius: float = R_EARTH,
         X *= (radius / np.linalg.norm(X, axis=2))[:, :, None]  # push out to the sphere
     else:
         raise ValueError("degree must be 1 or 3")
+    return V, C, X, geo
+
+
+def assemble_sw(ref_level: int, degree: int = 3, radius: float = R_EARTH,
+                g: float = GRAV, H: float = H_MEAN, omega: float = OMEGA,
+                c_scaled: bool = False, coriolis: bool = True,
+                nquad=6, p3_variant: str = "equispaced",
+                keep_elem: bool = False) -> SWOperator:
+    """Assemble K, M_u, M_eta, <div,div> for the given mesh.
+
+    c_scaled=True uses c = sqrt(gH) on both coupling terms (test_cheby.py:30,38-42).
+    """
+    if c_scaled:
+        g = H = float(np.sqrt(g * H))
+    V, C, X, geo = cell_geometry(ref_level, degree, radius, p3_variant)
+    nc = C.shape[0]
 
     bdm = BDM2()
     dg = Lagrange(_REF_V.copy(), 1)
@@ -345,7 +376,7 @@ def assemble_sw(ref_level: int, degree: int = 3, radius: float = R_EARTH,
     op = SWOperator(ref_level=ref_level, degree=degree, n_u=n_u, n_eta=n_eta, n_cells=nc,
                     K=K, Mu=Mu, Meta_blocks=Meta, Meta_inv_blocks=np.linalg.inv(Meta),
                     Ddiv=Ddiv, cell_u_dofs=cell_dofs, cell_u_sign=cell_sign,
-                    eta_nodes=eta_nodes, g=g, H=H, radius=radius)
+                    eta_nodes=eta_nodes, g=g, H=H, radius=radius, omega=omega, p3_variant=p3_variant)
     if keep_elem:
         op.Mu_elem = Mu_e * ss
         op.Kuu_elem = -Cor_e * ss

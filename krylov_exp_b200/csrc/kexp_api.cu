@@ -279,9 +279,10 @@ int ensure_stage(kexp_ctx* ctx, size_t bytes) {
 #define KEXP_GB 1
 #endif
 constexpr int kSpmmGB = KEXP_GB;                 // gathered blocks in flight per block row
-// Narrow panels are latency bound (one L2 round trip per gathered group): they gather four of the five blocks of a row of S at once (two round trips instead of five; five spill at 128 registers).
+// Gathered blocks per group for panels of up to 8 columns.  Measured at ref 5 x 8 columns (profiles/r02_summary.md): 1 -> 131 us,
+// 3 -> 131 us, 4 -> 149 us per mass solve -- more gathers in flight buy nothing there either (5 spill at 128 registers).
 #ifndef KEXP_GB_NARROW
-#define KEXP_GB_NARROW 4
+#define KEXP_GB_NARROW 1
 #endif
 constexpr int solve_gb(int W) { return W <= 8 ? KEXP_GB_NARROW : KEXP_GB; }
 #ifndef KEXP_GB0
@@ -2035,34 +2036,27 @@ int kexp_operator_apply_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {
     if (!in || !out || in->B != out->B) return kexp::fail(ctx, "bad batches");
     if (panels_unset(in)) return kexp::fail(ctx, "shared-input batches are only valid as the input of kexp_cheby_apply_dev / kexp_cheby_average_fused_dev");
     cudaSetDevice(ctx->device);
+    if (swap_lane(ctx, 0)) return 1;
     if (finish_upload(in)) return 1;
     if (in != out) out->order = in->order;
+    if (in->stride != out->stride || in->panelW != out->panelW) return kexp::fail(ctx, "batches have different panel layouts");
     int maxW = 0;
     for (int W : in->panelW) maxW = std::max(maxW, W);
     if (ensure_panels(ctx, maxW)) return 1;
-    for (int attempt = 0; attempt < 16; ++attempt) {
+    for (int W : in->panelW) DISPATCH_W(W, warm_occupancy<kW>(ctx));
+    // same policy as the Chebyshev applies: a solve that misses rtol makes the call repeat itself with more iterations and
+    // fail at max_it; in asynchronous mode the record is inspected by a later call
+    return run_checked(ctx, [&]() -> int {
         KEXP_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-        bool ok = true;
         for (size_t p = 0; p < in->panel.size(); ++p) {
             const int W = in->panelW[p];
             DISPATCH_W(W, launch_operator_full<kW>(ctx, in->panel[p], out->panel[p]));
-            int done = 1;          // the mass solve of this panel met rtol?
-            KEXP_CUDA(cudaMemcpyAsync(&done, &ctx->d_sc->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            KEXP_CUDA(cudaStreamSynchronize(ctx->stream));
-            ok = ok && done;
+            record_solve_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_sc);
         }
         KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
-        if (ok) break;
-        if (ctx->graph_its >= ctx->max_it) {
-            double res = 0.0;
-            KEXP_CUDA(cudaMemcpy(&res, &ctx->d_sc->max_rel_res, sizeof(double), cudaMemcpyDeviceToHost));
-            return unconverged_error(ctx, res, false);
-        }
-        raise_iterations(ctx);
-    }
-    KEXP_CUDA(cudaGetLastError());
-    if (ctx->timing) drain_events(ctx);
-    return 0;
+        KEXP_CUDA(cudaGetLastError());
+        return 0;
+    });
 }
 
 int kexp_spmm_K_dev(kexp_ctx* ctx, kexp_batch* in, kexp_batch* out) {

@@ -1099,6 +1099,14 @@ basis_combine_kernel(const double* __restrict__ basis, int ld, int nb, const dou
     }
 }
 
+// Convergence record of a mass solve that is not followed by a recurrence update (kexp_operator_apply_dev)
+static __global__ void record_solve_kernel(CgScalars* __restrict__ sc) {
+    if (!sc->done) {
+        sc->unconverged += 1;
+        sc->worst_rel_res = fmax(sc->worst_rel_res, sc->max_rel_res);
+    }
+}
+
 // Plain W = op output without recurrence (operator_apply): rows as in cheb_update, out = Wv
 template <int W, int SRC>
 __global__ void __launch_bounds__(kThreads)

@@ -200,3 +200,5 @@ class DeviceAveragedStepper(AveragedStepper):
     def synchronize(self):
         """Joins the stream and raises if a mass solve of the queued applies missed its tolerance."""
         self.op.synchronize()
+        if hasattr(self.slow, "synchronize"):
+            self.slow.synchronize()
