@@ -14,7 +14,7 @@ mesh (per-cell geometry factors of the BDM2 x DG1 pair on the cubic icosahedral 
 tabulations, facet neighbours), exactly like krylov_exp_b200.assembly is for K and M; `SlowRHS` evaluates L(U) for all
 ensemble members with the CUDA kernel `slow_form_kernel` (csrc/kexp_slow.cu, one warp = one cell x 32 members) and
 applies M^-1 with the library's batched mass solve, all on the library's stream with device-resident (B, n) arrays --
-the `slow` callback of DeviceAveragedStepper.  The NumPy restatement used as the checker is oracle/slow_rhs_ref.py.
+the `slow` callback of DeviceAveragedStepper.  The NumPy restatement used as the checker lives with the test infrastructure (slow_rhs_ref.py).
 
 Everything is evaluated in reference coordinates.  With u = J uh / detJ (contravariant Piola), G = J^T J, m = k.(J_0 x J_1),
 mu = m / detJ^2, a x b = a_0 b_1 - a_1 b_0 and uh_perp = (-uh_1, uh_0):
@@ -196,10 +196,13 @@ class SlowRHS:
         torch = self.torch
         B = F.shape[0]
         cur = torch.cuda.current_stream()
-        self.stream.wait_stream(cur)                       # F is produced on the caller's stream (device-side wait, no host join)
-        F.record_stream(self.stream)
+        # F is produced on the caller's stream and the result is consumed there: device-side waits on both sides order the two
+        # streams (no host join).  The result is allocated on the caller's stream; no tensor is tied to the library's stream,
+        # which may be destroyed (Operator.close) before the tensors are.
+        L = torch.empty((B, self.n), dtype=torch.float64, device=F.device)
+        self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
-            L = self.form(F)
+            self.form(F, out=L)
             if B not in self._batches:
                 self._batches[B] = (self.op.batch(B), self.op.batch(B))
             bi, bo = self._batches[B]
@@ -207,7 +210,6 @@ class SlowRHS:
             self.op._check(self.lib.kexp_operator_apply_dev(self.op.ctx, bi.handle, bo.handle), "kexp_operator_apply_dev")
             bo.export_dev(L)
         cur.wait_stream(self.stream)
-        L.record_stream(cur)
         return L
 
     def synchronize(self):
