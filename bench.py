@@ -325,6 +325,20 @@ def main():
     solve_path = {0: "batched PCG", 1: "Chebyshev, one kernel per iteration", 2: "Chebyshev, one cooperative kernel per solve",
                   3: "persistent narrow-panel apply kernel"}.get(int(st["solve_path"]), "?")
 
+    # ------------------------------------------------------------ where the step goes: forward / backward / average alone
+    def _timed_ms(fn, reps=3):
+        fn()
+        op.synchronize()
+        op.timer_start()
+        for _ in range(reps):
+            fn()
+        return op.timer_stop() / reps
+    ce.apply_dev(sh.f_in, sh.f_out, sh.t)
+    fwd_path = int(op.stats()["solve_path"])
+    breakdown = {"forward_ms": _timed_ms(lambda: ce.apply_dev(sh.f_in, sh.f_out, sh.t)),
+                 "backward_ms": _timed_ms(lambda: ce.apply_dev(sh.b_in, sh.b_out, -sh.t)),
+                 "average_ms": _timed_ms(lambda: sh.b_out.average_into(sh.w, sh.v.data_ptr()))}
+
     # ------------------------------------------------------------ multi-GPU numerics: the all-reduced average against
     # a single-GPU recomputation of the whole window on rank 0
     parity = None
@@ -426,6 +440,7 @@ def main():
 
     # ------------------------------------------------------------ roofline of the dominant kernel (rank 0)
     roofline, kernels = None, None
+    path_t, solve_label = -1, {}
     if not args.no_roofline and rank == 0:
         peak, peak_src = measured_peak_gbs()
         op.set_async(False)
@@ -529,7 +544,9 @@ def main():
                              "solve the 32-column panel (3 x 23.6 MB + matrix) is deliberately kept L2 resident, so the roofline "
                              "figure is effective (algorithmic) bandwidth",
                        "mass_solve": f"{'condensed ' if op.condensed else ''}block-Jacobi {'Chebyshev iteration' if args.solver == 'chebyshev' else 'PCG'} rtol {args.cg_rtol:g}, "
-                                     f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}; path: {solve_path}",
+                                     f"{cg_its_per_solve:.1f} iterations/solve, n_solve={op.n_solve}; backward batch: "
+                                     f"{solve_label.get(path_t, solve_path) if roofline else solve_path}; forward (one shared column): "
+                                     f"{'cheb_apply_narrow_kernel (persistent, one launch per apply)' if fwd_path == 3 else 'same kernels, 2-column panel'}",
                        "parallelism": f"window of {Btot} samples sharded cyclically (sample k on rank k mod N), {B}/GPU; one all-reduce of N "
                                       f"doubles per step ({'NCCL on the library stream' if lib_comm else 'torch.distributed'})",
                        "panels_per_batch": sh.b_in.num_panels,
@@ -545,7 +562,7 @@ def main():
             "parity_vs_single_gpu": parity,
             "value_independent_columns": value_indep, "value_full_series": value_full,
             "averaged_evaluation_fused": fused, "weak_scaling": weak,
-            "timing": {"device_ms": ms_dev, "host_ms": ms_host},
+            "timing": {"device_ms": ms_dev, "host_ms": ms_host, "rank0_breakdown": breakdown},
         }
         print(json.dumps(out))
     sh.close()

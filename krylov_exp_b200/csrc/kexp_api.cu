@@ -291,15 +291,17 @@ constexpr int solve_gb(int W) { return W <= 8 ? KEXP_GB_NARROW : KEXP_GB; }
 constexpr int kSpmm0GB = KEXP_GB0;               // the same for the plain product T = K~ S
 constexpr int kCptVec = 2;                  // sample columns per thread in the streaming vector kernels
 
+// fu (MODE 0 only): recurrence update to apply in the epilogue to the rows from fused_row0 on (those that need no solve)
 template <int W, int MODE>
-void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
+void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y, FusedUpd fu = FusedUpd{nullptr, nullptr, nullptr, nullptr, 0.0, 0},
+                 int fused_row0 = 0) {
     constexpr int LPR = W / 2, RPW = 32 / LPR;
     if (A.bsr()) {
         auto k = bsr3_spmm_kernel<W, MODE, (MODE == 0 ? kSpmm0GB : kSpmmGB)>;
         constexpr int per_cta = PanelCfg<W, kSpmmCpt>::BPC;
         int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
         launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, X, Y, A.nbr, A.max_bpr, ctx->T, ctx->d_Pinv,
-                 (const int*)A.rowmap, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                 (const int*)A.rowmap, ctx->d_sc, ctx->d_partials, ctx->d_counter, fu, fused_row0, (const double*)ctx->d_Dblk);
     } else {
         // MODE 1 (the CG product) always has a BSR copy: n_s is a multiple of 3 by contract
         auto k = csr_spmm_kernel<W>;
@@ -310,14 +312,21 @@ void launch_spmm(kexp_ctx* ctx, const DevCsr& A, const double* X, double* Y) {
 
 // ---- one batched application of M^-1 K on the work panels: input `in` (n x W),
 // leaves T (rows needing no solve), X (solved rows). W is a template parameter.
+// fu: recurrence update of the solved rows to fuse into the last iteration of the Chebyshev mass solve (fu.S != nullptr);
+// returns true when it was fused (the caller then skips the separate update launch for these rows).
 template <int W>
-void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
+bool enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0, FusedUpd fu = FusedUpd{nullptr, nullptr, nullptr, nullptr, 0.0, 0}) {
+    if (!ctx->use_fused_update) fu.S = nullptr;
     constexpr int LPB = PanelCfg<W, kCptVec>::LPB;
     const int ns = (int)ctx->n_s;
     const int red_grid = ctx->red_blocks_per_sm * ctx->num_sms;   // reduction kernels: few, fat blocks keep the last-block sum short
+    // rows that need no solve take their recurrence update in the epilogue of the K~ product (BSR kernel only)
+    const bool depth_fused = fu.S != nullptr && ctx->use_fused_update && ctx->Kt.bsr() && ctx->n_d > 0 && (ctx->n_s + ctx->n_b) % 3 == 0;
+    ctx->depth_rows_fused = depth_fused;
     {   // T = Kt * in
         TimedLaunch tl(ctx, KC_SPMM_K);
-        launch_spmm<W, 0>(ctx, ctx->Kt, in, ctx->T);
+        if (depth_fused) launch_spmm<W, 0>(ctx, ctx->Kt, in, ctx->T, fu, (int)(ctx->n_s + ctx->n_b));
+        else launch_spmm<W, 0>(ctx, ctx->Kt, in, ctx->T);
     }
     const int ntri = ns / 3;
     if (ctx->solver == 1) {
@@ -347,10 +356,10 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
                 attr[0].val.cooperative = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
                 cudaLaunchKernelEx(&cfg, k, (const int*)A.browptr, (const double*)A.blocks, (const double*)ctx->T, xk, xm,
-                                   (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, rtol2, A.diag_first ? 1 : 0, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                                   (const double*)ctx->d_Pinv, A.nbr, K, alpha, mu, rtol2, A.diag_first ? 1 : 0, ctx->d_sc, ctx->d_partials, ctx->d_counter, fu);
                 ctx->st_op_apps++;
                 ctx->solve_path = 2;
-                return;
+                return fu.S != nullptr;
             }
         }
         ctx->solve_path = 1;
@@ -370,18 +379,19 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
                 auto k = bsr3_cheb_iter_kernel<W, 1, solve_gb(W)>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                         omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                         omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter, fu);
             } else {
                 auto k = bsr3_cheb_iter_kernel<W, 0, solve_gb(W)>;
                 int grid = std::min(max_grid(ctx, k, kSpmmSmemBytes), std::max(1, (A.nbr + per_cta - 1) / per_cta));
                 launch_k(ctx, k, grid, kThreads, kSpmmSmemBytes, A.browptr, A.blocks, xk, xm, ctx->T, ctx->d_Pinv, A.nbr, A.max_bpr,
-                         omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter);
+                         omega, alpha, K, rtol2, ctx->d_sc, ctx->d_partials, ctx->d_counter, FusedUpd{nullptr, nullptr, nullptr, nullptr, 0.0, 0});
             }
             std::swap(xk, xm);
         }
         ctx->st_op_apps++;
-        return;
+        return fu.S != nullptr;
     }
+    fu.S = nullptr;                          // PCG: no last iteration known in advance
     ctx->solve_path = 0;
     {
         auto k = cg_init_kernel<W, kCptVec>;
@@ -402,15 +412,19 @@ void enqueue_operator(kexp_ctx* ctx, const double* in, double relax = 1.0) {
         }
     }
     ctx->st_op_apps++;
+    return false;
 }
 
 template <int W>
-void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep st) {
+void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep st, bool solved_rows_done = false) {
     constexpr int LPR = W / 2;
     const int ns = (int)ctx->n_s, nb = (int)ctx->n_b, nd = (int)ctx->n_d;
-    ChebStep st2 = st;
-    st2.check_cg = 0;
-    {
+    ChebStep st_b = st, st_d = st;             // back-substitution rows, remaining (depth) rows
+    st_b.check_cg = st_d.check_cg = 0;
+    if (solved_rows_done) {
+        // the solved rows took their update inside the mass solve; the convergence record moves to the next launch
+        if (nb > 0) st_b.check_cg = st.check_cg; else st_d.check_cg = st.check_cg;
+    } else {
         auto k = cheb_update_kernel<W, 0>;
         int grid = std::min(max_grid(ctx, k), blocks_for(ns, LPR));
         TimedLaunch tl(ctx, KC_CHEB);
@@ -421,19 +435,19 @@ void enqueue_cheb_update(kexp_ctx* ctx, double* S, const double* coef, ChebStep 
         int grid = std::min(max_grid(ctx, k), blocks_for(nb, LPR));
         const size_t o = (size_t)ns * W;
         TimedLaunch tl(ctx, KC_CHEB);
-        launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, S + o, ctx->Y + o, nb, coef, ctx->d_tscale, st2, ctx->d_sc);
+        launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, ctx->X, ctx->Rt.rowptr, ctx->Rt.col, ctx->Rt.val, nullptr, S + o, ctx->Y + o, nb, coef, ctx->d_tscale, st_b, ctx->d_sc);
     }
-    if (nd > 0) {
+    if (nd > 0 && !ctx->depth_rows_fused) {
         const size_t o = (size_t)(ns + nb) * W;
         TimedLaunch tl(ctx, KC_CHEB);
         if (ctx->d_Dblk) {
             auto k = cheb_update_kernel<W, 2>;
             int grid = std::min(max_grid(ctx, k), blocks_for(nd / 3, LPR));
-            launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
+            launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, nullptr, nullptr, nullptr, nullptr, ctx->d_Dblk, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st_d, ctx->d_sc);
         } else {
             auto k = cheb_update_kernel<W, 0>;
             int grid = std::min(max_grid(ctx, k), blocks_for(nd, LPR));
-            launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st2, ctx->d_sc);
+            launch_k(ctx, k, grid, kThreads, 0, ctx->T + o, nullptr, nullptr, nullptr, nullptr, nullptr, S + o, ctx->Y + o, nd, coef, ctx->d_tscale, st_d, ctx->d_sc);
         }
     }
 }
@@ -480,10 +494,11 @@ void enqueue_cheby(kexp_ctx* ctx, const PanelPlan& plan) {
     for (int n = 1; n <= plan.M; ++n) {
         const double* in = (n & 1) ? ctx->S0 : ctx->S1;     // S_{n-1}
         double* Sn = (n & 1) ? ctx->S1 : ctx->S0;           // holds S_{n-2}, becomes S_n
-        enqueue_operator<W>(ctx, in, (ctx->use_relax && ctx->solver == 1) ? plan.relax[n] : 1.0);
         ChebStep st;
         st.n = n; st.has_old = (n >= 2) ? 1 : 0; st.cs = (n == 1) ? 1.0 : 2.0; st.check_cg = 1;
-        enqueue_cheb_update<W>(ctx, Sn, coef, st);
+        const bool fused = enqueue_operator<W>(ctx, in, (ctx->use_relax && ctx->solver == 1) ? plan.relax[n] : 1.0,
+                                               FusedUpd{Sn, ctx->Y, coef + (size_t)n * kMaxW, ctx->d_tscale, st.cs, st.has_old});
+        enqueue_cheb_update<W>(ctx, Sn, coef, st, fused);
         if (ctx->capture_basis) {
             TimedLaunch tl(ctx, KC_MISC);
             launch_k(ctx, basis_store_kernel<W>, bgrid, kThreads, 0, Sn, (int)ctx->n, ctx->d_basis, ctx->basis_ld, n);
@@ -549,7 +564,7 @@ int run_cheby_panel(kexp_ctx* ctx, int id, int W, const PanelPlan& plan) {
     }
     KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
     ctx->st_op_apps += plan.M;
-    ctx->st_launches += 1 + (int64_t)plan.M * (2 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0))
+    ctx->st_launches += 1 + (int64_t)plan.M * (2 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) + ((ctx->solver == 1 && ctx->use_fused_update) ? 0 : 1) + (ctx->n_b > 0) + ((ctx->n_d > 0 && !ctx->depth_rows_fused) ? 1 : 0))
                         + (ctx->capture_basis ? plan.M + 1 : 0);
     return 0;
 }
@@ -680,10 +695,11 @@ void enqueue_clenshaw(kexp_ctx* ctx, const PanelPlan& plan) {
     add_z(A, plan.M);                                       // u_M = z_M
     for (int m = plan.M - 1; m >= 0; --m) {
         add_z(Bf, m);                                       // u_{m+2} + z_m
-        enqueue_operator<W>(ctx, A, (ctx->use_relax && ctx->solver == 1) ? plan.relax[m] : 1.0);
         ChebStep st;
         st.n = 0; st.has_old = 1; st.cs = (m == 0) ? 1.0 : 2.0; st.check_cg = 1;
-        enqueue_cheb_update<W>(ctx, Bf, coef, st);          // + cs * c * M^-1 K u_{m+1}
+        const bool fused = enqueue_operator<W>(ctx, A, (ctx->use_relax && ctx->solver == 1) ? plan.relax[m] : 1.0,
+                                               FusedUpd{Bf, ctx->Y, coef, ctx->d_tscale, st.cs, 1});
+        enqueue_cheb_update<W>(ctx, Bf, coef, st, fused);   // + cs * c * M^-1 K u_{m+1}
         std::swap(A, Bf);
     }
 }
@@ -783,6 +799,7 @@ int kexp_create(kexp_ctx** out, int device) {
     const char* ln = getenv("KEXP_LANES");
     if (ln && ln[0] == '1') { ctx->nlanes = 1; ctx->panel_cap = 64; }
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
+    if (const char* fz = getenv("KEXP_FUSED_UPDATE")) ctx->use_fused_update = (fz[0] != '0');
     if (const char* nw = getenv("KEXP_NARROW")) ctx->use_narrow = (nw[0] != '0');
     if (const char* nm = getenv("KEXP_NARROW_MAXW")) { const int v = atoi(nm); if (v >= 2 && v <= 16) ctx->narrow_max_w = v; }
     const char* rl = getenv("KEXP_RELAX");
@@ -1588,7 +1605,8 @@ static int run_clenshaw(kexp_ctx* ctx, int id, const PanelPlan& plan) {
     }
     KEXP_CUDA(cudaGraphLaunch(it->second, ctx->stream));
     ctx->st_op_apps += plan.M;
-    ctx->st_launches += 1 + (int64_t)plan.M * (3 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) + 1 + (ctx->n_b > 0) + (ctx->n_d > 0));
+    ctx->st_launches += 1 + (int64_t)plan.M * (3 + (ctx->solver == 1 ? (ctx->use_coop ? 0 : ctx->graph_its - 1) : 2 * ctx->graph_its) +
+                                               ((ctx->solver == 1 && ctx->use_fused_update) ? 0 : 1) + (ctx->n_b > 0) + ((ctx->n_d > 0 && !ctx->depth_rows_fused) ? 1 : 0));
     return 0;
 }
 

@@ -274,6 +274,27 @@ __device__ __forceinline__ void blk3_mul(const double* __restrict__ B, const dou
 //   instead of three.  rz itself is re-measured by that vector kernel every iteration,
 //   so the predicted value is only ever used for one beta and errors do not accumulate.
 // ------------------------------------------------------------------------------------
+// Recurrence update of the solved (edge) rows fused into the LAST iteration of the mass solve, where x_K is in registers:
+//   S_n = cs (t_k/L) x_K + S_{n-2}  (in place),  Y += a_n S_n      -- what cheb_update_kernel<W,0> does for these rows,
+// without its launch and without re-reading x_K.  S == nullptr: not fused (plain operator application).
+struct FusedUpd {
+    double* S; double* Y;
+    const double* coef_row;      // coefficient of this term per column (device)
+    const double* tscale;        // operator scale per column (device)
+    double cs; int has_old;
+};
+
+template <int W>
+__device__ __forceinline__ void fused_row_update(const FusedUpd& f, size_t o, int l, double2 xn) {
+    const double2 ts = make_double2(f.cs * __ldg(f.tscale + 2 * l), f.cs * __ldg(f.tscale + 2 * l + 1));
+    const double2 an = make_double2(__ldg(f.coef_row + 2 * l), __ldg(f.coef_row + 2 * l + 1));
+    double2 s = f.has_old ? ld2_stream(f.S + o) : make_double2(0.0, 0.0);
+    s.x = fma(ts.x, xn.x, s.x); s.y = fma(ts.y, xn.y, s.y);
+    double2 y = ld2_stream(f.Y + o);
+    y.x = fma(an.x, s.x, y.x); y.y = fma(an.y, s.y, y.y);
+    st2(f.S + o, s); st2(f.Y + o, y);
+}
+
 constexpr int kSpmmSmemBlocks = 520;      // 41 600 B of staged matrix blocks per CTA
 constexpr int kSpmmSmemRows = 128;        // block rows per staged sub-chunk (row pointers + 3x3 preconditioner blocks)
 constexpr int kSpmmSmemBytes = kSpmmSmemBlocks * 80 + kSpmmSmemRows * 72 + (kSpmmSmemRows + 4) * 4;
@@ -291,7 +312,8 @@ __global__ void __launch_bounds__(kThreads, (MODE == 0 ? KEXP_SPMM0_MINB : KEXP_
 bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                  const double* __restrict__ X, double* __restrict__ Y, int nbr, int max_bpr,
                  const double* __restrict__ R, const double* __restrict__ Pinv, const int* __restrict__ rowmap,
-                 CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
+                 CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter,
+                 const FusedUpd fu, int fused_row0, const double* __restrict__ fused_dblk) {
     using C = PanelCfg<W, kSpmmCpt>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
     extern __shared__ double2 sblk[];        // 5 double2 per staged block
@@ -360,8 +382,25 @@ bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blo
                         }
                     }
                 }
+                if (MODE == 0 && fu.S && 3 * orow >= fused_row0) {
+                    // rows that need no solve (DG1 depth): W = T (or Dblk T), so the recurrence update happens right here
+                    // and T is never written / re-read for them (MODE 0 with fu.S != nullptr: T = K~ S_{n-1} inside an apply)
+                    if (fused_dblk) {
+                        const double* D = fused_dblk + (size_t)9 * (orow - fused_row0 / 3);
+                        const double2 t0 = acc[0], t1 = acc[1], t2 = acc[2];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) st2(Y + o + (size_t)i * W, acc[i]);
+                        for (int i = 0; i < 3; ++i) {
+                            const double d0 = __ldg(D + 3 * i), d1 = __ldg(D + 3 * i + 1), d2 = __ldg(D + 3 * i + 2);
+                            acc[i].x = fma(d0, t0.x, fma(d1, t1.x, d2 * t2.x));
+                            acc[i].y = fma(d0, t0.y, fma(d1, t1.y, d2 * t2.y));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) fused_row_update<W>(fu, o + (size_t)i * W, l, acc[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) st2(Y + o + (size_t)i * W, acc[i]);
+                }
                 if (MODE == 1) {
                     const double* Pb = sP + 9 * (br - sub);
 #pragma unroll
@@ -426,7 +465,7 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
                       const double* __restrict__ Xold, double* __restrict__ Xnew, const double* __restrict__ Bv,
                       const double* __restrict__ Pinv, int nbr, int max_bpr,
                       double omega, double alpha, int iters_done, double rtol2,
-                      CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
+                      CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter, const FusedUpd fu) {
     using C = PanelCfg<W, kSpmmCpt>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
     extern __shared__ double2 sblk[];
@@ -506,6 +545,7 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
                     xn.x = fma(omega, fma(alpha, z.x, xo[i].x) - xm[i].x, xm[i].x);
                     xn.y = fma(omega, fma(alpha, z.y, xo[i].y) - xm[i].y, xm[i].y);
                     st2(Xnew + o + (size_t)i * W, xn);
+                    if (LAST && fu.S) fused_row_update<W>(fu, o + (size_t)i * W, l, xn);
                 }
             }
         }
@@ -559,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
                        const double* __restrict__ Bv, double* xk, double* xm,
                        const double* __restrict__ Pinv, int nbr, int K, double alpha, double mu, double rtol2, int diag_first,
-                       CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter) {
+                       CgScalars* __restrict__ sc, double* __restrict__ partials, unsigned* __restrict__ counter, const FusedUpd fu) {
     namespace cg = cooperative_groups;
     using C = PanelCfg<W, kSpmmCpt>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -683,6 +723,7 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                     xn.x = fma(omega, fma(alpha, z.x, xo[i].x) - xmv[i].x, xmv[i].x);
                     xn.y = fma(omega, fma(alpha, z.y, xo[i].y) - xmv[i].y, xmv[i].y);
                     st2(xm + o + (size_t)i * W, xn);
+                    if (last && fu.S) fused_row_update<W>(fu, o + (size_t)i * W, l, xn);
                 }
             }
         }

@@ -200,3 +200,22 @@ def test_series_reexpansion_against_numpy_chebyshev():
     assert reexpand_series(a, 0.0)[1] == 1 and abs(reexpand_series(a, 0.0)[0][0] - 1.0) < 1e-12   # series is 1 at A = 0
     with pytest.raises(ValueError):
         reexpand_series(a, 1.5)
+
+
+def test_checkpoint_roundtrip_and_norm_table(tmp_path, sw2):
+    """averaged_sw_explicit.py:319-326 / calculate_norm.py:66-96: store two runs, read them back, norm table = oracle norms."""
+    from krylov_exp_b200 import checkpoint
+    from oracle import norms
+    sw = sw2
+    rng = np.random.default_rng(5)
+    runs = {}
+    for name in ("avg", "std"):
+        for h in (1, 2):
+            U = rng.standard_normal(sw.n)
+            runs[(name, h)] = U
+            checkpoint.store(str(tmp_path / name), h, sw.n_u, U, time=3600.0 * h, tdump=0.5, tcheck=0.25)
+    U, attrs = checkpoint.load(str(tmp_path / "avg"), 2)
+    assert np.array_equal(U, runs[("avg", 2)]) and attrs == {"time": 7200.0, "tdump": 0.5, "tcheck": 0.25}
+    table = checkpoint.calculate_norm(sw, str(tmp_path / "avg"), str(tmp_path / "std"), (1, 2))
+    for i, h in enumerate((1, 2)):
+        assert np.allclose(table[i], norms.calculate_norm(sw, runs[("avg", h)], runs[("std", h)]), rtol=1e-13)
