@@ -140,7 +140,8 @@ struct kexp_ctx {
     bool chk_pending = false;
     int spmm_blocks_per_sm = 0;    // 0: from occupancy
     bool use_relax = true;         // relax the mass-solve tolerance of late Chebyshev terms (KEXP_RELAX=0: uniform rtol)
-    bool use_fused_update = true;  // recurrence update of the solved rows inside the last mass-solve iteration (KEXP_FUSED_UPDATE=0: separate launch)
+    bool use_fused_update = false; // KEXP_FUSED_UPDATE=1: recurrence update of the solved rows inside the last mass-solve iteration and of the
+                                   // depth rows in the K~ epilogue.  Measured neutral to slightly slower at M1 (profiles/r02_summary.md): off.
     bool depth_rows_fused = false; // set by enqueue_operator: the K~ product updated the rows that need no solve in its epilogue
     bool use_coop = true;          // whole Chebyshev mass solve as one cooperative kernel (KEXP_COOP=0: one kernel per iteration)
     int red_blocks_per_sm = 4;     // grid of the reduction kernels

@@ -1063,11 +1063,22 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
             const size_t o = (size_t)r * W + 2 * l;
             double2 wv = ld2_stream(src + o);
             if (SRC == 1) {
+                // back-substitution row: 9 entries (an interior dof against the 9 edge dofs of its cell); all gathers of a
+                // chunk are issued before the first use -- one L2 round trip per row instead of one per entry
+                constexpr int CH = 9;
                 const int k0 = __ldg(rowptr + r), k1 = __ldg(rowptr + r + 1);
-                for (int k = k0; k < k1; ++k) {
-                    const double a = __ldg(val + k);
-                    const double2 x = ld2(xs + (size_t)__ldg(col + k) * W + 2 * l);
-                    wv.x = fma(a, x.x, wv.x); wv.y = fma(a, x.y, wv.y);
+                for (int k = k0; k < k1; k += CH) {
+                    double2 x[CH];
+                    double a[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (k + j < k1) {
+                            a[j] = __ldg(val + k + j);
+                            x[j] = ld2(xs + (size_t)__ldg(col + k + j) * W + 2 * l);
+                        }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j)
+                        if (k + j < k1) { wv.x = fma(a[j], x[j].x, wv.x); wv.y = fma(a[j], x[j].y, wv.y); }
                 }
             }
             double2 s = st.has_old ? ld2_stream(S + o) : make_double2(0.0, 0.0);
