@@ -343,6 +343,8 @@ def main():
     # a single-GPU recomputation of the whole window on rank 0
     parity = None
     if world > 1:
+        sh.step_dev()                          # the all-reduced average of a complete step (the breakdown above left a local sum in v)
+        barrier()
         v_multi = sh.v.cpu().numpy().copy()
         if rank == 0:
             Xall = noisy_inputs(sw, x, range(Btot), np.empty((Btot, n)))
