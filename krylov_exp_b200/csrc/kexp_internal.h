@@ -74,6 +74,13 @@ struct GraphKey {
 
 struct KrylovState;               // kexp_krylov.cu
 
+// Device arrays of the per-CTA local problems of S (persistent narrow-panel kernel)
+struct NarrowPlanDev {
+    double* lblocks = nullptr; int* lrowptr = nullptr; int* cta_blk_ptr = nullptr; int* cta_row_ptr = nullptr;
+    int* halo_ptr = nullptr; int* halo_cols = nullptr; int* halo1_cnt = nullptr;
+    int G = 0, cap_blocks = 0, cap_rows = 0, cap_slots = 0, cap_halo = 0;
+};
+
 // Everything one in-flight panel needs: its stream, work panels, CG scalars, reduction scratch and
 // captured graphs.  The context's own fields are the ACTIVE lane; swap_lane() exchanges them with a
 // stored set, so the enqueue code is lane-agnostic (host code is single-threaded per context).
@@ -126,10 +133,13 @@ struct kexp_ctx {
     bool use_narrow = true;        // KEXP_NARROW=0: always the multi-launch path
     int narrow_max_w = 4;          // widest panel that takes it (KEXP_NARROW_MAXW; wider ones do not fit shared memory at ref 5)
     int narrow_slot = 0;           // constant-memory argument slot of this context
-    double* d_nlblocks = nullptr;  // S blocks with CTA-local column slots (kexp_narrow.cu: build_narrow_plan)
-    int* d_nhalo_ptr = nullptr;    // per CTA: range of its halo in d_nhalo_cols
-    int* d_nhalo_cols = nullptr;
-    int narrow_plan_G = 0, narrow_max_slots = 0, narrow_max_halo = 0;
+    kexp::NarrowPlanDev narrow_plan[2];   // per-CTA local problems of S: one-level / two-level (kexp_narrow.cu: build_narrow_plan)
+    int narrow_sstep = 1;          // Chebyshev iterations per grid barrier in the persistent kernel (KEXP_NARROW_SSTEP=1|2).  Two per barrier
+                                   // (redundant first halo ring) is implemented and tested but measured SLOWER at ref 5 (2.8 -> 3.5 ms for the
+                                   // single-column forward run, profiles/r02_summary.md): 1 is the default
+    int narrow_levels_used = 0;
+    int* d_nktcols = nullptr;      // block columns of K~
+    double* d_nxg = nullptr;       // four rotating publication buffers of the mass-solve iterates
     int* d_nk = nullptr;           // per-step iteration counts
     double* d_nrtol2 = nullptr;    // per-step squared tolerances
     double* d_npartials = nullptr; // per-CTA block sums

@@ -12,11 +12,14 @@
 //   * phases separated by grid-wide barriers only:   per term   A: T = K~ S_{n-1} (depth rows updated in the epilogue)
 //     | B: K-1 Chebyshev iterations of the mass solve, the edge-row recurrence update fused into the last one
 //     | C: interior rows  w_I = T_I + R w_E  and their update   -> K + 2 barriers per term;
-//   * inside the mass solve the iterate lives in SHARED memory: x_k for the CTA's own rows plus the halo rows its
-//     blocks reference (local slot numbers precomputed on the host), x_{k-1} / x_{k+1} for the own rows, and b.  Per
-//     iteration a CTA reads only its halo (each row once, coalesced, ld.global.cg) and publishes its own rows; the
-//     products read shared memory, so there is no gather latency chain, no L1 coherence question and hardly any
-//     register pressure;
+//   * inside the mass solve the iterate lives in SHARED memory: x_k on the CTA's own rows plus the halo rows its
+//     blocks reference (local slot numbers precomputed on the host), x_{k-1} / x_{k+1}, and b.  Per exchange a CTA
+//     reads only its halo (each row once, coalesced, ld.global.cg) and publishes its own rows; the products read
+//     shared memory, so there is no gather latency chain, no L1 coherence question, hardly any register pressure;
+//   * TWO Chebyshev iterations per grid barrier where shared memory allows (single-column panels at ref 5): the CTA
+//     also holds the matrix rows of its first halo ring H1 and the iterate on a second ring H2, computes x_{k+1} on
+//     own + H1 redundantly (bit-identical to what the owners compute) and then x_{k+2} on its own rows -- half the
+//     barriers and exchanges of the solve for ~45 % more local work in a latency-bound kernel;
 //   * data written by other CTAs is read with ld.global.cg (L2, the coherence point), everything else normally;
 //   * the convergence record of every mass solve (||b - S x||/||b|| per column against the relaxed tolerance of
 //     its term) is reduced in fixed order by CTA 0 behind the barrier that follows the solve.
@@ -27,6 +30,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "kexp_internal.h"
 
@@ -45,16 +49,19 @@ constexpr int kRChunk = 9;               // nonzeros of a row of R in flight (in
 struct NarrowArgs {
     // K~ (BSR 3x3, stored rows in locality order, rowmap = output block row)
     const int* kt_browptr; const double* kt_blocks; const int* kt_rowmap; int kt_nbr;
-    // S (BSR 3x3, diagonal block first), block-Jacobi inverse
-    const int* s_browptr; const double* s_blocks; const double* Pinv; int s_nbr;
-    // s_blocks here is the LOCALLY indexed copy: the 10th double of a block holds the shared-memory slot of its column
-    // (own rows first, then the CTA's halo rows); halo_ptr[c] .. halo_ptr[c+1]: global block rows of CTA c's halo
-    const int* halo_ptr; const int* halo_cols;
+    // S as per-CTA LOCAL problems (build_narrow_plan): the blocks of the rows a CTA computes -- its own rows, then (two-level
+    // plan) the rows of its first halo ring H1 -- packed per CTA with the shared-memory SLOT of each block's column in the
+    // 10th double (slots: own rows | H1 | H2); lrowptr: local row pointers; halo_cols: global block rows of H1 then H2
+    const double* lblocks; const int* lrowptr; const int* cta_blk_ptr; const int* cta_row_ptr;
+    const int* halo_ptr; const int* halo_cols; const int* halo1_cnt;
+    const double* Pinv; int s_nbr; int levels;             // levels: 1 (one iteration per barrier) or 2
+    const int* kt_cols;                                      // block columns of K~ (global copy of the 10th doubles)
     // R (CSR, n_b x n_s) or null; Dblk (n_d/3 blocks) or null
     const int* r_rowptr; const int* r_col; const double* r_val; const double* Dblk;
     int n, n_s, n_b, n_d;
     // panels [rows][W]
-    double *SA, *SB, *Y, *T, *X, *P;
+    double *SA, *SB, *Y, *T, *X;
+    double* xg[4];                       // rotating publication buffers of the mass-solve iterates (n_s x W each)
     // per-panel tables (device): tscale[W], coef[(M+1)][kMaxW]; per-term iteration counts and squared tolerances
     const double* tscale; const double* coef; const int* kterm; const double* rtol2;
     int M;                               // highest term index
@@ -64,7 +71,7 @@ struct NarrowArgs {
     CgScalars* sc; double* partials;     // [gridDim][2][W] block sums of ||r||^2, ||b||^2
     unsigned* barrier;                   // grid barrier counter (zeroed before the launch)
     // shared-memory layout (element counts, maxima over the CTAs)
-    int cap_s_blocks, cap_s_rows, cap_kt_rows, cap_kt_blocks, cap_r_rows, cap_r_nnz, cap_slots, cap_halo;
+    int cap_bpr, cap_s_rows, cap_kt_rows, cap_r_rows, cap_slots, cap_halo;     // cap_bpr: most blocks in a computed row
     int xs_offset;                       // first double of the iterate buffers in dynamic shared memory
 };
 
@@ -156,8 +163,7 @@ __device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& s
 
 // ---- phase A: T = K~ S_{n-1}; depth rows (no solve) take their recurrence update in the epilogue
 template <int W>
-KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restrict__ kptr, const int* __restrict__ kcol,
-                                         int k0r, int k1r, int kt_b0) {
+KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restrict__ kptr, int k0r, int k1r, int kt_b0) {
     const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -179,7 +185,7 @@ KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restr
 #pragma unroll
                 for (int j = 0; j < kGatherK; ++j)
                     if (q + j < q1) {
-                        const double* xr = Sin + (size_t)(3 * kcol[q + j]) * W + 2 * l;
+                        const double* xr = Sin + (size_t)(3 * __ldg(a.kt_cols + kt_b0 + q + j)) * W + 2 * l;
 #pragma unroll
                         for (int r = 0; r < 3; ++r) x[j][r] = ldcg2(xr + (size_t)r * W);
                     }
@@ -223,9 +229,15 @@ KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restr
 // Shared-memory state of the mass solve (per CTA): xa = x_k on [own rows | halo rows], xb = x_{k-1} on the own rows (it
 // becomes x_{k+1}; its halo part is filled after the next barrier), bs = b on the own rows.  Row r of a slot starts at
 // (3*slot + r) * W doubles.
-// ---- phase B, start: x_0 = 0, x_1 = alpha P^-1 b on the own rows (shared memory + published); returns ||b||^2 share
+// Shared-memory state of the mass solve (per CTA), in block-row SLOTS: own rows | first halo ring H1 | second ring H2.
+// Row r of a slot starts at (3*slot + r) * W doubles.  Two iterate arrays over all slots and b on the rows the CTA computes
+// (own rows, plus H1 in the two-level plan).
+//
+// ---- phase B, start: on the computed rows  b <- T (global), x_1 = alpha P^-1 b -> cur, x_0 = 0 -> prev; the own rows of
+// x_1 and x_0 are published (g1, g0).  x_1 on H1 is computed locally (bit-identical to the owner's).  Returns ||b||^2 (own).
 template <int W>
-KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* xg, double* xa, double* xb, double* bs, const double* __restrict__ sP, int s0, int s1) {
+KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* g1, double* g0, double* cur, double* prev, double* bs, const double* __restrict__ sP,
+                                         const int* __restrict__ hcol, int s0, int n_own, int n_rows) {
     const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -233,52 +245,59 @@ KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* xg, double* xa, doubl
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane % LPB, g = lane / LPB;
     double2 accb = make_double2(0.0, 0.0);
-    for (int base = s0; base < s1; base += BPC) {
-        const int br = base + warp * BRW + g;
-        if (br < s1) {
-            const size_t o = (size_t)(3 * br) * W + 2 * l;
-            const int ls = (3 * (br - s0)) * W + 2 * l;
+    for (int base = 0; base < n_rows; base += BPC) {
+        const int lr = base + warp * BRW + g;
+        if (lr < n_rows) {
+            const bool own = lr < n_own;
+            const int gr = own ? s0 + lr : hcol[lr - n_own];
+            const size_t o = (size_t)(3 * gr) * W + 2 * l;
+            const int ls = (3 * lr) * W + 2 * l;
             double2 bv[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 bv[i] = ldcg2(a.T + o + (size_t)i * W);
                 *reinterpret_cast<double2*>(bs + ls + i * W) = bv[i];
-                accb.x = fma(bv[i].x, bv[i].x, accb.x); accb.y = fma(bv[i].y, bv[i].y, accb.y);
+                if (own) { accb.x = fma(bv[i].x, bv[i].x, accb.x); accb.y = fma(bv[i].y, bv[i].y, accb.y); }
             }
-            const double* Pb = sP + 9 * (br - s0);
+            const double* Pb = sP + 9 * lr;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 double2 z;
                 z.x = a.alpha * fma(Pb[3 * i], bv[0].x, fma(Pb[3 * i + 1], bv[1].x, Pb[3 * i + 2] * bv[2].x));
                 z.y = a.alpha * fma(Pb[3 * i], bv[0].y, fma(Pb[3 * i + 1], bv[1].y, Pb[3 * i + 2] * bv[2].y));
-                *reinterpret_cast<double2*>(xa + ls + i * W) = z;
-                *reinterpret_cast<double2*>(xb + ls + i * W) = make_double2(0.0, 0.0);
-                *reinterpret_cast<double2*>(xg + o + (size_t)i * W) = z;
+                *reinterpret_cast<double2*>(cur + ls + i * W) = z;
+                *reinterpret_cast<double2*>(prev + ls + i * W) = make_double2(0.0, 0.0);
+                if (own) {
+                    *reinterpret_cast<double2*>(g1 + o + (size_t)i * W) = z;
+                    *reinterpret_cast<double2*>(g0 + o + (size_t)i * W) = make_double2(0.0, 0.0);
+                }
             }
         }
     }
     return accb;
 }
 
-// ---- phase B, halo: the rows of x_k this CTA's blocks reference outside its own range, global -> shared (each row once,
-// 16-byte pieces, coalesced within a row)
+// ---- phase B, halo exchange: halo slots [h_lo, h_hi) of a published iterate, global -> shared (each row once, 16-byte
+// pieces, coalesced within a row)
 template <int W>
-KEXP_PHASE_FN void narrow_load_halo(const double* xg, double* xa, const int* __restrict__ hcols, int n_own, int n_halo) {
+KEXP_PHASE_FN void narrow_load_halo(const double* xg, double* xs, const int* __restrict__ hcol, int n_own, int h_lo, int h_hi) {
     constexpr int PPR = 3 * W / 2;                     // 16-byte pieces per block row (3 rows x W doubles, contiguous)
     constexpr int NT = NarrowCfg<W>::NT;
-    for (int e = threadIdx.x; e < n_halo * PPR; e += NT) {
+    for (int e = h_lo * PPR + threadIdx.x; e < h_hi * PPR; e += NT) {
         const int h = e / PPR, p = e % PPR;
-        const double2 v = ldcg2(xg + (size_t)(3 * hcols[h]) * W + 2 * p);
-        *reinterpret_cast<double2*>(xa + (size_t)(3 * (n_own + h)) * W + 2 * p) = v;
+        const double2 v = ldcg2(xg + (size_t)(3 * hcol[h]) * W + 2 * p);
+        *reinterpret_cast<double2*>(xs + (size_t)(3 * (n_own + h)) * W + 2 * p) = v;
     }
 }
 
-// ---- phase B, one Chebyshev iteration on the own rows, everything read from shared memory: x_{k+1} overwrites x_{k-1}
-// (shared) and is published to xg_out; LAST also forms ||b - S x_k||^2 and the recurrence update of the edge rows (W = x_K)
+// ---- phase B, one Chebyshev iteration on the local rows [0, n_rows), everything read from shared memory:
+//   x_{k+1} = x_{k-1} + omega (x_k + alpha P^-1 (b - S x_k) - x_{k-1}),   x_k = cur (all slots the rows reference), x_{k-1} = prev,
+// written over prev; the own rows (lr < n_own) are published to gout (and to gout2: the final iterate also goes to a.X).
+// LAST also forms ||b - S x_k||^2 and the recurrence update of the edge rows (W = x_K).
 template <int W, bool LAST>
-KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double* xa, double* xb, const double* bs, double* xg_out, double omega,
-                                        const double2* __restrict__ sblk, const double* __restrict__ sP, const int* __restrict__ sptr,
-                                        int s0, int s1) {
+KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double* cur, double* prev, const double* bs, double* gout, double* gout2,
+                                        double omega, const double* __restrict__ sv, const int* __restrict__ ss, const double* __restrict__ sP,
+                                        const int* __restrict__ scnt, int ell_ld, int s0, int n_own, int n_rows) {
     const NarrowArgs& a = c_nargs[slot];
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
@@ -288,24 +307,32 @@ KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double
     UpdCtx u;
     if (LAST) u = make_upd<W>(a, sx, l);
     double2 accr = make_double2(0.0, 0.0);
-    for (int base = s0; base < s1; base += BPC) {
-        const int br = base + warp * BRW + g;
-        if (br < s1) {
-            const int q0 = sptr[br - s0], q1 = sptr[br - s0 + 1];
-            const int ls = (3 * (br - s0)) * W + 2 * l;
+    for (int base = 0; base < n_rows; base += BPC) {
+        const int lr = base + warp * BRW + g;
+        if (lr < n_rows) {
+            const int nq = scnt[lr];
+            const int ls = (3 * lr) * W + 2 * l;
             double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
-            for (int q = q0; q < q1; ++q) {
-                const double2* bp = sblk + 5 * q;
-                const double2 v01 = bp[0], v23 = bp[1], v45 = bp[2], v67 = bp[3], v8c = bp[4];
-                const double* xr = xa + (3 * __double2loint(v8c.y)) * W + 2 * l;
+            // the matrix is stored TRANSPOSED in shared memory (element e of block q of local row lr at sv[(9 q + e) ell_ld + lr],
+            // its column slot at ss[q ell_ld + lr]): the rows of a warp read consecutive words -- no bank conflicts, where the
+            // 80-byte blocks of one row per lane conflicted 4-way
+            for (int q = 0; q < nq; ++q) {
+                const double* vp = sv + (size_t)(9 * q) * ell_ld + lr;
+                const double* xr = cur + (3 * ss[q * ell_ld + lr]) * W + 2 * l;
                 const double2 x0 = *reinterpret_cast<const double2*>(xr), x1 = *reinterpret_cast<const double2*>(xr + W),
                               x2 = *reinterpret_cast<const double2*>(xr + 2 * W);
-                acc[0].x = fma(v01.x, x0.x, fma(v01.y, x1.x, fma(v23.x, x2.x, acc[0].x)));
-                acc[0].y = fma(v01.x, x0.y, fma(v01.y, x1.y, fma(v23.x, x2.y, acc[0].y)));
-                acc[1].x = fma(v23.y, x0.x, fma(v45.x, x1.x, fma(v45.y, x2.x, acc[1].x)));
-                acc[1].y = fma(v23.y, x0.y, fma(v45.x, x1.y, fma(v45.y, x2.y, acc[1].y)));
-                acc[2].x = fma(v67.x, x0.x, fma(v67.y, x1.x, fma(v8c.x, x2.x, acc[2].x)));
-                acc[2].y = fma(v67.x, x0.y, fma(v67.y, x1.y, fma(v8c.x, x2.y, acc[2].y)));
+                const double m00 = vp[0], m01 = vp[ell_ld], m02 = vp[2 * ell_ld], m10 = vp[3 * ell_ld], m11 = vp[4 * ell_ld], m12 = vp[5 * ell_ld],
+                             m20 = vp[6 * ell_ld], m21 = vp[7 * ell_ld], m22 = vp[8 * ell_ld];
+                // same order as the wide-panel kernels: for each block, columns r = 0, 1, 2 of the 3x3 block in turn
+                acc[0].x = fma(m00, x0.x, acc[0].x); acc[0].y = fma(m00, x0.y, acc[0].y);
+                acc[1].x = fma(m10, x0.x, acc[1].x); acc[1].y = fma(m10, x0.y, acc[1].y);
+                acc[2].x = fma(m20, x0.x, acc[2].x); acc[2].y = fma(m20, x0.y, acc[2].y);
+                acc[0].x = fma(m01, x1.x, acc[0].x); acc[0].y = fma(m01, x1.y, acc[0].y);
+                acc[1].x = fma(m11, x1.x, acc[1].x); acc[1].y = fma(m11, x1.y, acc[1].y);
+                acc[2].x = fma(m21, x1.x, acc[2].x); acc[2].y = fma(m21, x1.y, acc[2].y);
+                acc[0].x = fma(m02, x2.x, acc[0].x); acc[0].y = fma(m02, x2.y, acc[0].y);
+                acc[1].x = fma(m12, x2.x, acc[1].x); acc[1].y = fma(m12, x2.y, acc[1].y);
+                acc[2].x = fma(m22, x2.x, acc[2].x); acc[2].y = fma(m22, x2.y, acc[2].y);
             }
             double2 rv[3];
 #pragma unroll
@@ -314,20 +341,24 @@ KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double
                 rv[i].x = bv.x - acc[i].x; rv[i].y = bv.y - acc[i].y;
                 if (LAST) { accr.x = fma(rv[i].x, rv[i].x, accr.x); accr.y = fma(rv[i].y, rv[i].y, accr.y); }
             }
-            const double* Pb = sP + 9 * (br - s0);
-            const size_t o = (size_t)(3 * br) * W + 2 * l;
+            const double* Pb = sP + 9 * lr;
+            const bool own = lr < n_own;
+            const size_t o = (size_t)(3 * (s0 + lr)) * W + 2 * l;          // only meaningful for own rows
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const double2 xo = *reinterpret_cast<const double2*>(xa + ls + i * W);
-                const double2 xmv = *reinterpret_cast<const double2*>(xb + ls + i * W);
+                const double2 xo = *reinterpret_cast<const double2*>(cur + ls + i * W);
+                const double2 xmv = *reinterpret_cast<const double2*>(prev + ls + i * W);
                 double2 z, xn;
                 z.x = fma(Pb[3 * i], rv[0].x, fma(Pb[3 * i + 1], rv[1].x, Pb[3 * i + 2] * rv[2].x));
                 z.y = fma(Pb[3 * i], rv[0].y, fma(Pb[3 * i + 1], rv[1].y, Pb[3 * i + 2] * rv[2].y));
                 xn.x = fma(omega, fma(a.alpha, z.x, xo.x) - xmv.x, xmv.x);
                 xn.y = fma(omega, fma(a.alpha, z.y, xo.y) - xmv.y, xmv.y);
-                *reinterpret_cast<double2*>(xb + ls + i * W) = xn;
-                *reinterpret_cast<double2*>(xg_out + o + (size_t)i * W) = xn;
-                if (LAST) row_update(u, o + (size_t)i * W, (size_t)(3 * br + i), xn);     // edge rows: W = x_K
+                *reinterpret_cast<double2*>(prev + ls + i * W) = xn;
+                if (own) {
+                    if (gout) *reinterpret_cast<double2*>(gout + o + (size_t)i * W) = xn;
+                    if (gout2) *reinterpret_cast<double2*>(gout2 + o + (size_t)i * W) = xn;
+                    if (LAST) row_update(u, o + (size_t)i * W, (size_t)(3 * (s0 + lr) + i), xn);     // edge rows: W = x_K
+                }
             }
         }
     }
@@ -336,8 +367,7 @@ KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double
 
 // ---- phase C: interior rows  w_I = T_I + R x_K  and their recurrence update
 template <int W>
-KEXP_PHASE_FN void narrow_phase_c(int slot, const StepCtx sx, const int* __restrict__ rptr, const int* __restrict__ rcol,
-                                         int r0, int r1) {
+KEXP_PHASE_FN void narrow_phase_c(int slot, const StepCtx sx, const int* __restrict__ rptr, int r0, int r1) {
     const NarrowArgs& a = c_nargs[slot];
     constexpr int LPR = W / 2;
     constexpr int RPC = NarrowCfg<W>::NT / LPR;
@@ -355,7 +385,7 @@ KEXP_PHASE_FN void narrow_phase_c(int slot, const StepCtx sx, const int* __restr
 #pragma unroll
             for (int j = 0; j < kRChunk; ++j)
                 if (q + j < q1) {
-                    x[j] = ldcg2(a.X + (size_t)rcol[q + j] * W + 2 * lr);
+                    x[j] = ldcg2(a.X + (size_t)__ldg(a.r_col + qbase + q + j) * W + 2 * lr);
                     v[j] = __ldg(a.r_val + qbase + q + j);
                 }
 #pragma unroll
@@ -413,6 +443,7 @@ KEXP_PHASE_FN void narrow_check(int slot, double* fin, int K, double rtol2, int*
     }
 }
 
+
 template <int W>
 __global__ void __launch_bounds__(NarrowCfg<W>::NT, 1)
 cheb_apply_narrow_kernel(const int slot) {
@@ -425,16 +456,16 @@ cheb_apply_narrow_kernel(const int slot) {
     cg::grid_group grid = cg::this_grid();
 
     extern __shared__ double2 smem2[];
-    double2* sblk = smem2;                                                     // S blocks of the own rows
-    double* sP = reinterpret_cast<double*>(sblk + 5 * (size_t)a.cap_s_blocks); // block-Jacobi inverses of the own rows
+    const int ell_ld = a.cap_s_rows;                                           // leading dimension of the transposed matrix arrays
+    double* sv = reinterpret_cast<double*>(smem2);                             // S values, transposed: [9 * bpr][ell_ld]
+    double* sP = sv + (size_t)9 * a.cap_bpr * ell_ld;                          // block-Jacobi inverses of the computed rows
     double* sred = sP + 9 * (size_t)a.cap_s_rows;                              // reduction scratch: 2 x warps x W, then 2 x W x 32
-    int* sptr = reinterpret_cast<int*>(sred + 2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);
-    int* kptr = sptr + a.cap_s_rows + 1;
-    int* kcol = kptr + a.cap_kt_rows + 1;
-    int* rptr = kcol + a.cap_kt_blocks;
-    int* rcol = rptr + a.cap_r_rows + 1;
-    int* hcol = rcol + a.cap_r_nnz;
-    // mass-solve state: two iterate buffers over [own | halo] slots and b on the own rows (16-byte aligned)
+    int* ss = reinterpret_cast<int*>(sred + 2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);   // column slots, transposed: [bpr][ell_ld]
+    int* scnt = ss + (size_t)a.cap_bpr * ell_ld;                               // blocks per computed row
+    int* kptr = scnt + a.cap_s_rows;
+    int* rptr = kptr + a.cap_kt_rows + 1;
+    int* hcol = rptr + a.cap_r_rows + 1;
+    // mass-solve state: two iterate arrays over [own | H1 | H2] slots and b on the computed rows (16-byte aligned)
     double* xs0 = reinterpret_cast<double*>(smem2) + a.xs_offset;
     double* xs1 = xs0 + (size_t)3 * W * a.cap_slots;
     double* bsm = xs1 + (size_t)3 * W * a.cap_slots;
@@ -447,27 +478,39 @@ cheb_apply_narrow_kernel(const int slot) {
     cta_range(a.kt_nbr, k0r, k1r);
     cta_range(a.n_b, r0, r1);
     const int kt_b0 = __ldg(a.kt_browptr + k0r);
+    const int n_own = s1 - s0;
+    const int h0 = __ldg(a.halo_ptr + blockIdx.x), n_halo = __ldg(a.halo_ptr + blockIdx.x + 1) - h0;
+    const int n_h1 = __ldg(a.halo1_cnt + blockIdx.x);
+    const int n_rows = (a.levels == 2) ? n_own + n_h1 : n_own;                 // rows this CTA computes
 
-    // ---- stage the constant data of this CTA's row ranges
+    // ---- stage the constant data of this CTA
     {
-        const int kb0 = __ldg(a.s_browptr + s0), kb1 = __ldg(a.s_browptr + s1);
-        const double2* gsrc = reinterpret_cast<const double2*>(a.s_blocks) + (size_t)5 * kb0;
-        for (int i = threadIdx.x; i < 5 * (kb1 - kb0); i += kNT) sblk[i] = __ldg(gsrc + i);
-        for (int i = threadIdx.x; i <= s1 - s0; i += kNT) sptr[i] = __ldg(a.s_browptr + s0 + i) - kb0;
-        for (int i = threadIdx.x; i < 9 * (s1 - s0); i += kNT) sP[i] = __ldg(a.Pinv + (size_t)9 * s0 + i);
-        const int kb1k = __ldg(a.kt_browptr + k1r);
+        for (int i = threadIdx.x; i < n_halo; i += kNT) hcol[i] = __ldg(a.halo_cols + h0 + i);
+        const int b0 = __ldg(a.cta_blk_ptr + blockIdx.x);
+        const double* gsrc = a.lblocks + (size_t)10 * b0;
+        const int* lrp = a.lrowptr + __ldg(a.cta_row_ptr + blockIdx.x);
+        for (int lr = threadIdx.x; lr < n_rows; lr += kNT) {                   // one row per thread: transpose its blocks
+            const int q0 = __ldg(lrp + lr), q1 = __ldg(lrp + lr + 1);
+            scnt[lr] = q1 - q0;
+            for (int q = q0; q < q1; ++q) {
+                const double* bp = gsrc + (size_t)10 * q;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) sv[(size_t)(9 * (q - q0) + e) * ell_ld + lr] = __ldg(bp + e);
+                ss[(q - q0) * ell_ld + lr] = __double2loint(__ldg(bp + 9));
+            }
+        }
+        __syncthreads();                                                       // hcol
+        for (int i = threadIdx.x; i < 9 * n_rows; i += kNT) {
+            const int lr = i / 9, e = i % 9;
+            const int gr = lr < n_own ? s0 + lr : hcol[lr - n_own];
+            sP[i] = __ldg(a.Pinv + (size_t)9 * gr + e);
+        }
         for (int i = threadIdx.x; i <= k1r - k0r; i += kNT) kptr[i] = __ldg(a.kt_browptr + k0r + i) - kt_b0;
-        for (int i = threadIdx.x; i < kb1k - kt_b0; i += kNT)
-            kcol[i] = __double2loint(__ldg(a.kt_blocks + (size_t)10 * (kt_b0 + i) + 9));
         if (a.n_b > 0) {
-            const int q0 = __ldg(a.r_rowptr + r0), q1 = __ldg(a.r_rowptr + r1);
+            const int q0 = __ldg(a.r_rowptr + r0);
             for (int i = threadIdx.x; i <= r1 - r0; i += kNT) rptr[i] = __ldg(a.r_rowptr + r0 + i) - q0;
-            for (int i = threadIdx.x; i < q1 - q0; i += kNT) rcol[i] = __ldg(a.r_col + q0 + i);
         }
     }
-    const int h0 = __ldg(a.halo_ptr + blockIdx.x), n_halo = __ldg(a.halo_ptr + blockIdx.x + 1) - h0;
-    for (int i = threadIdx.x; i < n_halo; i += kNT) hcol[i] = __ldg(a.halo_cols + h0 + i);
-    const int n_own = s1 - s0;
     // ---- prologue on a linear slice of the rows:  mode 0: Y = a_0 S_0 (and basis[:,0]);  mode 1: SA = z_M e_0, SB = 0
     {
         int p0, p1;
@@ -500,27 +543,51 @@ cheb_apply_narrow_kernel(const int slot) {
         sx.has_old = (a.mode == 0) ? (step >= 2) : 1;
         sx.crow = a.coef + (size_t)((a.mode == 0) ? sx.term : 0) * kMaxW;
 
-        narrow_phase_a<W>(slot, sx, kptr, kcol, k0r, k1r, kt_b0);
+        narrow_phase_a<W>(slot, sx, kptr, k0r, k1r, kt_b0);
         narrow_barrier(grid, a.barrier, bar_target);
 
-        // mass solve on the own rows of S (Chebyshev semi-iteration), K - 1 iterations behind x_1
+        // ---- mass solve on the own rows of S: Chebyshev semi-iteration, K - 1 iterations behind x_1, one or two per barrier.
+        // Published iterates rotate through four global buffers: gc holds x_k, gp holds x_{k-1}, the other two are written.
         const int K = a.kterm[step];
-        double* xk = (K % 2 == 1) ? a.X : a.P;               // x_1 is published here, x_K ends up in a.X
-        double* xm = (xk == a.X) ? a.P : a.X;
-        double* xa = xs0;                                    // shared: x_k on [own | halo]
-        double* xb = xs1;                                    // shared: x_{k-1} on the own rows -> x_{k+1}
-        double2 accb = narrow_solve_start<W>(slot, xk, xa, xb, bsm, sP, s0, s1);
+        int gc = 0, gp = 1;
+        double* cur = xs0;                                   // shared: x_k on all slots the computed rows reference
+        double* prev = xs1;                                  // shared: x_{k-1} on the computed rows -> x_{k+1}
+        double2 accb = narrow_solve_start<W>(slot, a.xg[gc], a.xg[gp], cur, prev, bsm, sP, hcol, s0, n_own, n_rows);
         double2 accr = make_double2(0.0, 0.0);
         double omega = 1.0;
-        for (int it = 1; it < K; ++it) {
-            narrow_barrier(grid, a.barrier, bar_target);     // x_k of every CTA is published (and this CTA's shared copy complete)
-            narrow_load_halo<W>(xk, xa, hcol, n_own, n_halo);
+        int it = 1;                                          // next iteration to run: x_it -> x_{it+1}, it = 1 .. K-1
+        const int iters = K - 1;
+        auto next_omega = [&](int j) { omega = (j == 1) ? 1.0 / (1.0 - 0.5 * a.mu * a.mu) : 1.0 / (1.0 - 0.25 * a.mu * a.mu * omega); };
+        auto free_buf = [&](int skip) { for (int b = 0; b < 4; ++b) if (b != gc && b != gp && b != skip) return b; return 0; };
+        if (a.levels != 2 || (iters & 1)) {
+            // single iterations: all of them (one-level plan) or one to make the rest an even count
+            const int singles = (a.levels != 2) ? iters : 1;
+            for (int j = 0; j < singles; ++j, ++it) {
+                narrow_barrier(grid, a.barrier, bar_target);     // x_k of every CTA is published
+                narrow_load_halo<W>(a.xg[gc], cur, hcol, n_own, 0, n_h1);
+                __syncthreads();
+                next_omega(it);
+                const int f = free_buf(-1);
+                if (it == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, cur, prev, bsm, nullptr, a.X, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
+                else narrow_solve_iter<W, false>(slot, sx, cur, prev, bsm, a.xg[f], nullptr, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
+                gp = gc; gc = f;
+                double* tsw = cur; cur = prev; prev = tsw;
+            }
+        }
+        for (; it < K; it += 2) {
+            // two iterations per barrier: x_{k+1} on own + H1 (needs x_k on own + H1 + H2, x_{k-1} on own + H1), then x_{k+2} on own
+            narrow_barrier(grid, a.barrier, bar_target);
+            narrow_load_halo<W>(a.xg[gc], cur, hcol, n_own, 0, n_halo);
+            narrow_load_halo<W>(a.xg[gp], prev, hcol, n_own, 0, n_h1);
             __syncthreads();
-            omega = (it == 1) ? 1.0 / (1.0 - 0.5 * a.mu * a.mu) : 1.0 / (1.0 - 0.25 * a.mu * a.mu * omega);
-            if (it == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, xa, xb, bsm, xm, omega, sblk, sP, sptr, s0, s1);
-            else narrow_solve_iter<W, false>(slot, sx, xa, xb, bsm, xm, omega, sblk, sP, sptr, s0, s1);
-            double* tsw = xk; xk = xm; xm = tsw;
-            tsw = xa; xa = xb; xb = tsw;
+            const int f0 = free_buf(-1), f1 = free_buf(f0);
+            next_omega(it);
+            narrow_solve_iter<W, false>(slot, sx, cur, prev, bsm, a.xg[f0], nullptr, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_rows);
+            __syncthreads();                                     // x_{k+1} on own + H1 complete in `prev`
+            next_omega(it + 1);
+            if (it + 1 == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, prev, cur, bsm, nullptr, a.X, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
+            else narrow_solve_iter<W, false>(slot, sx, prev, cur, bsm, a.xg[f1], nullptr, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
+            gp = f0; gc = f1;                                    // cur holds x_{k+2} (own), prev x_{k+1} (own + H1): roles unchanged
         }
         // block sums of ||r||^2 and ||b||^2 per column (fixed order): shuffles over the groups of a warp, then the warps
         {
@@ -543,19 +610,19 @@ cheb_apply_narrow_kernel(const int slot) {
                 a.partials[((size_t)blockIdx.x * 2 + q) * W + c] = s;
             }
         }
-        narrow_barrier(grid, a.barrier, bar_target);                                           // x_K, the edge rows of S_n and the block sums are visible
+        narrow_barrier(grid, a.barrier, bar_target);           // x_K (in a.X), the edge rows of S_n and the block sums are visible
         if (blockIdx.x == 0) narrow_check<W>(slot, sred + 2 * kNWarpsMax * W, K, a.rtol2[step], &s_bad);
 
         if (a.n_b > 0) {
-            narrow_phase_c<W>(slot, sx, rptr, rcol, r0, r1);
-            narrow_barrier(grid, a.barrier, bar_target);                                       // S_n complete
+            narrow_phase_c<W>(slot, sx, rptr, r0, r1);
+            narrow_barrier(grid, a.barrier, bar_target);       // S_n complete
         }
         double* tsw = sx.Sin; sx.Sin = sx.Snew; sx.Snew = tsw;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct NarrowCaps { int s_blocks, s_rows, kt_rows, kt_blocks, r_rows, r_nnz, slots, halo; size_t smem; };
+struct NarrowCaps { int bpr, s_rows, kt_rows, r_rows, slots, halo; };
 
 static void range_of(int nrows, int c, int G, int& start, int& end) {
     const int per = nrows / G, rem = nrows % G;
@@ -566,9 +633,9 @@ static void range_of(int nrows, int c, int G, int& start, int& end) {
 // bytes of the constant part (matrix, index arrays, scratch), rounded to 16: the iterate buffers start there
 template <int W>
 static size_t narrow_smem_fixed(const NarrowCaps& c) {
-    size_t b = sizeof(double2) * 5 * (size_t)c.s_blocks + sizeof(double) * 9 * (size_t)c.s_rows;
+    size_t b = sizeof(double) * 9 * (size_t)c.bpr * c.s_rows + sizeof(double) * 9 * (size_t)c.s_rows;
     b += sizeof(double) * (2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);
-    b += sizeof(int) * ((size_t)c.s_rows + 1 + c.kt_rows + 1 + c.kt_blocks + c.r_rows + 1 + c.r_nnz + c.halo);
+    b += sizeof(int) * ((size_t)c.bpr * c.s_rows + c.s_rows + c.kt_rows + 1 + c.r_rows + 1 + c.halo);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -577,70 +644,105 @@ static size_t narrow_smem(const NarrowCaps& c) {
     return narrow_smem_fixed<W>(c) + sizeof(double) * 3 * W * ((size_t)2 * c.slots + c.s_rows);
 }
 
-// Shared-memory capacities for a grid of G CTAs (from the host copies of the row pointers kept at upload time).
-// Per-CTA local numbering of S for a grid of G CTAs: own rows take slots 0..n_own-1, the halo (block columns referenced
-// outside the own range, sorted) the slots behind them; the device gets a copy of the blocks with the slot in place of the
-// global block column.  Built once per operator.
-static int build_narrow_plan(kexp_ctx* ctx, int G) {
-    if (ctx->narrow_plan_G == G && ctx->d_nlblocks) return 0;
+__global__ void extract_block_cols_kernel(const double* __restrict__ blocks, int64_t nblocks, int* __restrict__ cols) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nblocks; i += (int64_t)gridDim.x * blockDim.x)
+        cols[i] = __double2loint(blocks[10 * i + 9]);
+}
+
+// Per-CTA local problems of S for a grid of G CTAs (see NarrowArgs).  levels = 1: the CTA computes its own rows, slots =
+// own | H1 (block columns referenced outside the own range, sorted).  levels = 2: it also computes the rows of H1
+// (redundantly), slots = own | H1 | H2 with H2 the columns referenced by H1 rows outside own + H1.  Built once per
+// operator and level count.
+static int build_narrow_plan(kexp_ctx* ctx, int G, int levels) {
+    NarrowPlanDev& P = ctx->narrow_plan[levels - 1];
+    if (P.G == G && P.lblocks) return 0;
     const std::vector<int>& sb = ctx->As.h_browptr;
     const std::vector<double>& blk = ctx->As.h_blocks;
     if (sb.empty() || blk.empty()) return kexp::fail(ctx, "narrow apply: host copy of S not available");
     const int nbr = (int)sb.size() - 1;
-    std::vector<double> lb(blk);
-    std::vector<int> hptr((size_t)G + 1, 0), hcols, halo;
-    int max_slots = 0, max_halo = 0;
+    auto colof = [&](int k) { int64_t bits; memcpy(&bits, &blk[(size_t)k * 10 + 9], 8); return (int)bits; };
+    std::vector<double> lb;
+    std::vector<int> lrow, cta_blk((size_t)G + 1, 0), cta_row((size_t)G + 1, 0), hptr((size_t)G + 1, 0), hcols, h1cnt((size_t)G, 0);
+    std::vector<int> h1, h2, rows;
+    NarrowCaps caps{0, 0, 0, 0, 0, 0};
     for (int c = 0; c < G; ++c) {
         int r0, r1;
         range_of(nbr, c, G, r0, r1);
-        halo.clear();
-        for (int k = sb[r0]; k < sb[r1]; ++k) {
-            int64_t bits; memcpy(&bits, &blk[(size_t)k * 10 + 9], 8);
-            const int col = (int)bits;
-            if (col < r0 || col >= r1) halo.push_back(col);
+        const int n_own = r1 - r0;
+        h1.clear(); h2.clear();
+        for (int k = sb[r0]; k < sb[r1]; ++k) { const int col = colof(k); if (col < r0 || col >= r1) h1.push_back(col); }
+        std::sort(h1.begin(), h1.end());
+        h1.erase(std::unique(h1.begin(), h1.end()), h1.end());
+        if (levels == 2) {
+            for (int r : h1)
+                for (int k = sb[r]; k < sb[r + 1]; ++k) {
+                    const int col = colof(k);
+                    if ((col < r0 || col >= r1) && !std::binary_search(h1.begin(), h1.end(), col)) h2.push_back(col);
+                }
+            std::sort(h2.begin(), h2.end());
+            h2.erase(std::unique(h2.begin(), h2.end()), h2.end());
         }
-        std::sort(halo.begin(), halo.end());
-        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
-        for (int k = sb[r0]; k < sb[r1]; ++k) {
-            int64_t bits; memcpy(&bits, &blk[(size_t)k * 10 + 9], 8);
-            const int col = (int)bits;
-            int64_t slot = (col >= r0 && col < r1) ? col - r0
-                                                   : (r1 - r0) + (int)(std::lower_bound(halo.begin(), halo.end(), col) - halo.begin());
-            memcpy(&lb[(size_t)k * 10 + 9], &slot, 8);
+        auto slot_of = [&](int col) -> int64_t {
+            if (col >= r0 && col < r1) return col - r0;
+            auto i1 = std::lower_bound(h1.begin(), h1.end(), col);
+            if (i1 != h1.end() && *i1 == col) return n_own + (i1 - h1.begin());
+            auto i2 = std::lower_bound(h2.begin(), h2.end(), col);
+            return n_own + (int64_t)h1.size() + (i2 - h2.begin());
+        };
+        rows.clear();
+        for (int r = r0; r < r1; ++r) rows.push_back(r);
+        if (levels == 2) rows.insert(rows.end(), h1.begin(), h1.end());
+        const size_t blk0 = lb.size() / 10;
+        lrow.push_back(0);
+        for (int r : rows) {
+            for (int k = sb[r]; k < sb[r + 1]; ++k) {
+                const size_t o = lb.size();
+                lb.insert(lb.end(), blk.begin() + (size_t)k * 10, blk.begin() + (size_t)k * 10 + 10);
+                const int64_t slot = slot_of(colof(k));
+                memcpy(&lb[o + 9], &slot, 8);
+            }
+            lrow.push_back((int)(lb.size() / 10 - blk0));
         }
-        hcols.insert(hcols.end(), halo.begin(), halo.end());
+        cta_blk[c + 1] = (int)(lb.size() / 10);
+        cta_row[c + 1] = (int)lrow.size();
+        hcols.insert(hcols.end(), h1.begin(), h1.end());
+        hcols.insert(hcols.end(), h2.begin(), h2.end());
         hptr[c + 1] = (int)hcols.size();
-        max_slots = std::max(max_slots, r1 - r0 + (int)halo.size());
-        max_halo = std::max(max_halo, (int)halo.size());
+        h1cnt[c] = (int)h1.size();
+        for (int r : rows) caps.bpr = std::max(caps.bpr, sb[r + 1] - sb[r]);
+        caps.s_rows = std::max(caps.s_rows, (int)rows.size());
+        caps.slots = std::max(caps.slots, n_own + (int)h1.size() + (int)h2.size());
+        caps.halo = std::max(caps.halo, (int)(h1.size() + h2.size()));
     }
-    cudaFree(ctx->d_nlblocks); cudaFree(ctx->d_nhalo_ptr); cudaFree(ctx->d_nhalo_cols);
-    ctx->d_nlblocks = nullptr; ctx->d_nhalo_ptr = ctx->d_nhalo_cols = nullptr;
-    KEXP_CUDA(cudaMalloc(&ctx->d_nlblocks, sizeof(double) * lb.size()));
-    KEXP_CUDA(cudaMalloc(&ctx->d_nhalo_ptr, sizeof(int) * hptr.size()));
-    KEXP_CUDA(cudaMalloc(&ctx->d_nhalo_cols, sizeof(int) * std::max<size_t>(hcols.size(), 1)));
-    KEXP_CUDA(cudaMemcpy(ctx->d_nlblocks, lb.data(), sizeof(double) * lb.size(), cudaMemcpyHostToDevice));
-    KEXP_CUDA(cudaMemcpy(ctx->d_nhalo_ptr, hptr.data(), sizeof(int) * hptr.size(), cudaMemcpyHostToDevice));
-    KEXP_CUDA(cudaMemcpy(ctx->d_nhalo_cols, hcols.data(), sizeof(int) * hcols.size(), cudaMemcpyHostToDevice));
-    ctx->narrow_plan_G = G; ctx->narrow_max_slots = max_slots; ctx->narrow_max_halo = max_halo;
+    cudaFree(P.lblocks); cudaFree(P.lrowptr); cudaFree(P.cta_blk_ptr); cudaFree(P.cta_row_ptr);
+    cudaFree(P.halo_ptr); cudaFree(P.halo_cols); cudaFree(P.halo1_cnt);
+    P = NarrowPlanDev();
+    auto up = [&](auto** dst, const auto& v) -> bool {
+        using T = std::remove_reference_t<decltype(**dst)>;
+        if (cudaMalloc(dst, sizeof(T) * std::max<size_t>(v.size(), 1)) != cudaSuccess) return true;
+        return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess;
+    };
+    if (up(&P.lblocks, lb) || up(&P.lrowptr, lrow) || up(&P.cta_blk_ptr, cta_blk) || up(&P.cta_row_ptr, cta_row) ||
+        up(&P.halo_ptr, hptr) || up(&P.halo_cols, hcols) || up(&P.halo1_cnt, h1cnt))
+        return kexp::fail(ctx, "out of device memory for the narrow-apply plan");
+    P.G = G; P.cap_blocks = caps.bpr; P.cap_rows = caps.s_rows; P.cap_slots = caps.slots; P.cap_halo = caps.halo;
     return 0;
 }
 
-bool narrow_caps(kexp_ctx* ctx, int G, NarrowCaps& c) {
-    const std::vector<int>& sb = ctx->As.h_browptr;
+static bool narrow_caps(kexp_ctx* ctx, int G, int levels, NarrowCaps& c) {
     const std::vector<int>& kb = ctx->Kt.h_browptr;
     const std::vector<int>& rp = ctx->Rt.h_rowptr;
-    if (sb.empty() || kb.empty()) return false;
-    if (build_narrow_plan(ctx, G)) return false;
-    c = NarrowCaps{0, 0, 0, 0, 0, 0, ctx->narrow_max_slots, ctx->narrow_max_halo, 0};
+    if (ctx->As.h_browptr.empty() || kb.empty()) return false;
+    if (build_narrow_plan(ctx, G, levels)) return false;
+    const NarrowPlanDev& P = ctx->narrow_plan[levels - 1];
+    c = NarrowCaps{P.cap_blocks, P.cap_rows, 0, 0, P.cap_slots, P.cap_halo};
     for (int i = 0; i < G; ++i) {
         int a, b;
-        range_of((int)sb.size() - 1, i, G, a, b);
-        c.s_rows = std::max(c.s_rows, b - a); c.s_blocks = std::max(c.s_blocks, sb[b] - sb[a]);
         range_of((int)kb.size() - 1, i, G, a, b);
-        c.kt_rows = std::max(c.kt_rows, b - a); c.kt_blocks = std::max(c.kt_blocks, kb[b] - kb[a]);
+        c.kt_rows = std::max(c.kt_rows, b - a);
         if (!rp.empty()) {
             range_of((int)rp.size() - 1, i, G, a, b);
-            c.r_rows = std::max(c.r_rows, b - a); c.r_nnz = std::max(c.r_nnz, rp[b] - rp[a]);
+            c.r_rows = std::max(c.r_rows, b - a);
         }
     }
     return true;
@@ -650,6 +752,7 @@ template <int W>
 static int launch_narrow_w(kexp_ctx* ctx, NarrowArgs& a, const NarrowCaps& caps) {
     auto k = cheb_apply_narrow_kernel<W>;
     const size_t smem = narrow_smem<W>(caps);
+    a.xs_offset = (int)(narrow_smem_fixed<W>(caps) / sizeof(double));
     static size_t attr_smem = 0;           // per instantiation
     if (smem > attr_smem) {
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -667,47 +770,67 @@ static int launch_narrow_w(kexp_ctx* ctx, NarrowArgs& a, const NarrowCaps& caps)
     return 0;
 }
 
-// Can a panel of width W run through the persistent kernel?  (Chebyshev mass solve, both matrices in 3x3 blocks with the
-// diagonal block present, and the CTA's share of S, index arrays and scratch within 227 KB of shared memory.)
-bool narrow_eligible(kexp_ctx* ctx, int W) {
-    if (!ctx->use_narrow || W > ctx->narrow_max_w || W > 16) return false;
-    if (ctx->solver != 1 || !ctx->Kt.bsr() || !ctx->As.bsr() || !ctx->As.diag_first) return false;
-    if (ctx->n_b > 0 && (ctx->Rt.rowptr == nullptr)) return false;
-    if (ctx->n % 3 || ctx->n_s % 3 || ctx->n_b % 3) return false;
-    NarrowCaps caps;
-    if (!narrow_caps(ctx, ctx->num_sms, caps)) return false;
-    size_t smem = 0;
+static size_t narrow_smem_for(int W, const NarrowCaps& caps) {
     switch (W) {
-        case 2: smem = narrow_smem<2>(caps); break;
-        case 4: smem = narrow_smem<4>(caps); break;
-        case 8: smem = narrow_smem<8>(caps); break;
-        case 16: smem = narrow_smem<16>(caps); break;
-        default: return false;
+        case 2: return narrow_smem<2>(caps);
+        case 4: return narrow_smem<4>(caps);
+        case 8: return narrow_smem<8>(caps);
+        case 16: return narrow_smem<16>(caps);
+        default: return (size_t)1 << 40;
     }
-    return smem <= 227u * 1024u - 1024u;
 }
+
+// How many Chebyshev iterations per barrier a panel of width W can run (0: the persistent kernel is not applicable):
+// Chebyshev mass solve, both matrices in 3x3 blocks, and the CTA's local problem + iterate buffers within the shared memory
+// an SM offers.  Two iterations per barrier when the two-level problem fits (single-column panels at ref 5), else one.
+static int narrow_levels(kexp_ctx* ctx, int W) {
+    if (!ctx->use_narrow || W > ctx->narrow_max_w || W > 16) return 0;
+    if (ctx->solver != 1 || !ctx->Kt.bsr() || !ctx->As.bsr()) return 0;
+    if (ctx->n_b > 0 && (ctx->Rt.rowptr == nullptr)) return 0;
+    if (ctx->n % 3 || ctx->n_s % 3 || ctx->n_b % 3) return 0;
+    const size_t limit = 227u * 1024u - 1024u;
+    for (int levels = std::min(2, ctx->narrow_sstep); levels >= 1; --levels) {
+        NarrowCaps caps;
+        if (!narrow_caps(ctx, ctx->num_sms, levels, caps)) return 0;
+        if (narrow_smem_for(W, caps) <= limit) return levels;
+    }
+    return 0;
+}
+
+bool narrow_eligible(kexp_ctx* ctx, int W) { return narrow_levels(ctx, W) > 0; }
 
 // Enqueue one whole apply of the panel held in ctx->S0 (mode 0: result in ctx->Y; mode 1: Clenshaw, result in the buffer
 // returned through *result).  kterm / rtol2: per-step iteration counts and squared tolerances (host, M+1 entries).
 int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm, const double* rtol2, bool with_basis, const double** result) {
+    const int levels = narrow_levels(ctx, W);
     NarrowCaps caps;
-    if (!narrow_caps(ctx, ctx->num_sms, caps)) return kexp::fail(ctx, "narrow apply: operator structure not available");
+    if (levels < 1 || !narrow_caps(ctx, ctx->num_sms, levels, caps)) return kexp::fail(ctx, "narrow apply: not applicable to this operator / width");
     if (M + 1 > kMaxTerms) return kexp::fail(ctx, "series too long");
     if (!ctx->d_nk) {
         KEXP_CUDA(cudaMalloc(&ctx->d_nk, sizeof(int) * kMaxTerms));
         KEXP_CUDA(cudaMalloc(&ctx->d_nrtol2, sizeof(double) * kMaxTerms));
         KEXP_CUDA(cudaMalloc(&ctx->d_npartials, sizeof(double) * 2 * kMaxW * (size_t)ctx->num_sms + 64));
     }
+    if (!ctx->d_nktcols) {
+        KEXP_CUDA(cudaMalloc(&ctx->d_nktcols, sizeof(int) * (size_t)std::max<int64_t>(ctx->Kt.nblocks, 1)));
+        extract_block_cols_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(ctx->Kt.blocks, ctx->Kt.nblocks, ctx->d_nktcols);
+    }
+    // rotating publication buffers of the mass-solve iterates: n_s x 16 doubles each (the widest narrow panel)
+    if (!ctx->d_nxg) KEXP_CUDA(cudaMalloc(&ctx->d_nxg, sizeof(double) * 4 * 16 * (size_t)ctx->n_s));
     // pageable sources: the driver stages them before the call returns, so the host vectors may be reused at once
     KEXP_CUDA(cudaMemcpyAsync(ctx->d_nk, kterm, sizeof(int) * (size_t)(M + 1), cudaMemcpyHostToDevice, ctx->stream));
     KEXP_CUDA(cudaMemcpyAsync(ctx->d_nrtol2, rtol2, sizeof(double) * (size_t)(M + 1), cudaMemcpyHostToDevice, ctx->stream));
+    const NarrowPlanDev& P = ctx->narrow_plan[levels - 1];
     NarrowArgs a;
     a.kt_browptr = ctx->Kt.browptr; a.kt_blocks = ctx->Kt.blocks; a.kt_rowmap = ctx->Kt.rowmap; a.kt_nbr = ctx->Kt.nbr;
-    a.s_browptr = ctx->As.browptr; a.s_blocks = ctx->d_nlblocks; a.Pinv = ctx->d_Pinv; a.s_nbr = ctx->As.nbr;
-    a.halo_ptr = ctx->d_nhalo_ptr; a.halo_cols = ctx->d_nhalo_cols;
+    a.kt_cols = ctx->d_nktcols;
+    a.lblocks = P.lblocks; a.lrowptr = P.lrowptr; a.cta_blk_ptr = P.cta_blk_ptr; a.cta_row_ptr = P.cta_row_ptr;
+    a.halo_ptr = P.halo_ptr; a.halo_cols = P.halo_cols; a.halo1_cnt = P.halo1_cnt;
+    a.Pinv = ctx->d_Pinv; a.s_nbr = ctx->As.nbr; a.levels = levels;
     a.r_rowptr = ctx->Rt.rowptr; a.r_col = ctx->Rt.col; a.r_val = ctx->Rt.val; a.Dblk = ctx->d_Dblk;
     a.n = (int)ctx->n; a.n_s = (int)ctx->n_s; a.n_b = (int)ctx->n_b; a.n_d = (int)ctx->n_d;
-    a.SA = ctx->S0; a.SB = ctx->S1; a.Y = ctx->Y; a.T = ctx->T; a.X = ctx->X; a.P = ctx->P;
+    a.SA = ctx->S0; a.SB = ctx->S1; a.Y = ctx->Y; a.T = ctx->T; a.X = ctx->X;
+    for (int b = 0; b < 4; ++b) a.xg[b] = ctx->d_nxg + (size_t)b * 16 * ctx->n_s;
     a.tscale = ctx->d_tscale; a.coef = ctx->d_tscale + kMaxW; a.kterm = ctx->d_nk; a.rtol2 = ctx->d_nrtol2;
     a.M = M; a.mode = mode;
     a.basis = (mode == 1 || with_basis) ? ctx->d_basis : nullptr; a.basis_ld = ctx->basis_ld;
@@ -716,14 +839,8 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     a.sc = ctx->d_sc; a.partials = ctx->d_npartials;
     a.barrier = reinterpret_cast<unsigned*>(ctx->d_npartials + 2 * kMaxW * (size_t)ctx->num_sms);
     KEXP_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), ctx->stream));
-    a.cap_s_blocks = caps.s_blocks; a.cap_s_rows = caps.s_rows; a.cap_kt_rows = caps.kt_rows; a.cap_kt_blocks = caps.kt_blocks;
-    a.cap_r_rows = caps.r_rows; a.cap_r_nnz = caps.r_nnz; a.cap_slots = caps.slots; a.cap_halo = caps.halo;
-    switch (W) {
-        case 2: a.xs_offset = (int)(narrow_smem_fixed<2>(caps) / sizeof(double)); break;
-        case 4: a.xs_offset = (int)(narrow_smem_fixed<4>(caps) / sizeof(double)); break;
-        case 8: a.xs_offset = (int)(narrow_smem_fixed<8>(caps) / sizeof(double)); break;
-        default: a.xs_offset = (int)(narrow_smem_fixed<16>(caps) / sizeof(double)); break;
-    }
+    a.cap_bpr = caps.bpr; a.cap_s_rows = caps.s_rows; a.cap_kt_rows = caps.kt_rows; a.cap_r_rows = caps.r_rows;
+    a.cap_slots = caps.slots; a.cap_halo = caps.halo; a.xs_offset = 0;
     int rc = 1;
     switch (W) {
         case 2: rc = launch_narrow_w<2>(ctx, a, caps); break;
@@ -735,6 +852,7 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     if (rc) return rc;
     if (result) *result = (M % 2 == 0) ? ctx->S0 : ctx->S1;       // the buffer written by the last step
     ctx->solve_path = 3;
+    ctx->narrow_levels_used = levels;
     return 0;
 }
 

@@ -353,9 +353,11 @@ def test_async_mode_defers_the_check_not_the_error(sw2):
 # ------------------------------------------------------------------------------------------------
 # persistent narrow-panel apply kernel (kexp_narrow.cu) against the multi-launch path and the oracle
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sstep", ["1", "2"])
 @pytest.mark.parametrize("B", [1, 3, 4, 7, 8])
-def test_narrow_kernel_equals_multi_launch_path(sw3, monkeypatch, B):
+def test_narrow_kernel_equals_multi_launch_path(sw3, monkeypatch, B, sstep):
     monkeypatch.setenv("KEXP_NARROW_MAXW", "8")           # ref 3: panels of up to 8 columns fit shared memory
+    monkeypatch.setenv("KEXP_NARROW_SSTEP", sstep)        # one / two Chebyshev iterations per grid barrier
     """Same rows, same order of operations: the persistent kernel must reproduce the multi-launch path to round-off
     (forward recurrence, shared-input basis run, fused Clenshaw average), with the same iteration counts."""
     import krylov_exp_b200 as kx
@@ -411,7 +413,9 @@ def test_narrow_kernel_against_oracle(sw3, condense):
     op.close()
 
 
-def test_narrow_kernel_ref5_columns_against_cpu_port():
+@pytest.mark.parametrize("sstep", ["1", "2"])
+def test_narrow_kernel_ref5_columns_against_cpu_port(monkeypatch, sstep):
+    monkeypatch.setenv("KEXP_NARROW_SSTEP", sstep)
     """A strong-scaling share of M1 (4 of the 64 samples, and the shared-input forward pass) through the persistent kernel
     at full size."""
     import krylov_exp_b200 as kx
