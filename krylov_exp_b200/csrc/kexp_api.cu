@@ -801,8 +801,7 @@ int kexp_create(kexp_ctx** out, int device) {
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
     if (const char* fz = getenv("KEXP_FUSED_UPDATE")) ctx->use_fused_update = (fz[0] != '0');
     if (const char* nw = getenv("KEXP_NARROW")) ctx->use_narrow = (nw[0] != '0');
-    if (const char* ns = getenv("KEXP_NARROW_SSTEP")) { const int v = atoi(ns); if (v == 1 || v == 2) ctx->narrow_sstep = v; }
-    if (const char* nm = getenv("KEXP_NARROW_MAXW")) { const int v = atoi(nm); if (v >= 2 && v <= 16) ctx->narrow_max_w = v; }
+    if (const char* nm = getenv("KEXP_NARROW_MAXW")) { const int v = atoi(nm); if (v >= 2 && v <= 8) ctx->narrow_max_w = v; }
     const char* rl = getenv("KEXP_RELAX");
     if (rl) ctx->use_relax = (rl[0] == '1');
     const char* co = getenv("KEXP_COOP");
@@ -848,12 +847,8 @@ int kexp_destroy(kexp_ctx* ctx) {
     for (double* b : bufs) cudaFree(b);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sc); cudaFree(ctx->d_counter);
     cudaFree(ctx->d_nk); cudaFree(ctx->d_nrtol2); cudaFree(ctx->d_npartials);
-    cudaFree(ctx->d_nktcols); cudaFree(ctx->d_nxg);
-    for (auto& P : ctx->narrow_plan) {
-        cudaFree(P.lblocks); cudaFree(P.lrowptr); cudaFree(P.cta_blk_ptr); cudaFree(P.cta_row_ptr);
-        cudaFree(P.halo_ptr); cudaFree(P.halo_cols); cudaFree(P.halo1_cnt);
-        P = kexp::NarrowPlanDev();
-    }
+    cudaFree(ctx->d_nktcols);
+    kexp::free_narrow_plan(ctx->narrow_plan);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -929,9 +924,8 @@ int kexp_set_operator_plan(kexp_ctx* ctx, int64_t n, int64_t n_s, int64_t n_b,
     invalidate_graphs(ctx);
     if (ctx->tmp_in) { kexp_batch_destroy(ctx->tmp_in); kexp_batch_destroy(ctx->tmp_out); ctx->tmp_in = ctx->tmp_out = nullptr; }
     ctx->have_op = false;
-    for (auto& P : ctx->narrow_plan) P.G = 0;      // the per-CTA local problems of S belong to the old operator
+    kexp::free_narrow_plan(ctx->narrow_plan);      // the per-CTA local problems of S belong to the old operator
     cudaFree(ctx->d_nktcols); ctx->d_nktcols = nullptr;
-    cudaFree(ctx->d_nxg); ctx->d_nxg = nullptr;
     ctx->n = n; ctx->n_s = n_s; ctx->n_b = n_b; ctx->n_d = n_d;
     ctx->curW = 0;   // panels are re-allocated for the new size
     ctx->lane_store[1 - ctx->cur_lane].curW = 0;

@@ -77,8 +77,10 @@ struct KrylovState;               // kexp_krylov.cu
 // Device arrays of the per-CTA local problems of S (persistent narrow-panel kernel)
 struct NarrowPlanDev {
     double* lblocks = nullptr; int* lrowptr = nullptr; int* cta_blk_ptr = nullptr; int* cta_row_ptr = nullptr;
-    int* halo_ptr = nullptr; int* halo_cols = nullptr; int* halo1_cnt = nullptr;
-    int G = 0, cap_blocks = 0, cap_rows = 0, cap_slots = 0, cap_halo = 0;
+    int* halo_ptr = nullptr; int* halo_cols = nullptr; int* srowptr = nullptr; int* cta_send_ptr = nullptr; int* send_dst = nullptr;
+    void* inbox = nullptr;         // flagged halo inboxes (two buffers)
+    int G = 0;                     // grid the plan was built for (< 0: built and found not applicable)
+    int cap_blocks = 0, cap_rows = 0, cap_halo = 0, cap_send = 0, inbox_slots = 0;
 };
 
 // Everything one in-flight panel needs: its stream, work panels, CG scalars, reduction scratch and
@@ -131,15 +133,11 @@ struct kexp_ctx {
     // and looked at by the next call that finds the copy finished, at the latest by kexp_synchronize / download
     // persistent narrow-panel apply kernel (kexp_narrow.cu)
     bool use_narrow = true;        // KEXP_NARROW=0: always the multi-launch path
-    int narrow_max_w = 4;          // widest panel that takes it (KEXP_NARROW_MAXW; wider ones do not fit shared memory at ref 5)
+    int narrow_max_w = 4;          // widest panel that takes it (KEXP_NARROW_MAXW, up to 8).  8-column panels: 5.5 ms against 4.2 ms for the
+                                   // multi-launch path at ref 5 (the K~ product of the persistent kernel is the slow part); 4 columns: a tie
     int narrow_slot = 0;           // constant-memory argument slot of this context
-    kexp::NarrowPlanDev narrow_plan[2];   // per-CTA local problems of S: one-level / two-level (kexp_narrow.cu: build_narrow_plan)
-    int narrow_sstep = 1;          // Chebyshev iterations per grid barrier in the persistent kernel (KEXP_NARROW_SSTEP=1|2).  Two per barrier
-                                   // (redundant first halo ring) is implemented and tested but measured SLOWER at ref 5 (2.8 -> 3.5 ms for the
-                                   // single-column forward run, profiles/r02_summary.md): 1 is the default
-    int narrow_levels_used = 0;
+    kexp::NarrowPlanDev narrow_plan;      // per-CTA local problems of S, halos and send lists (kexp_narrow.cu: build_narrow_plan)
     int* d_nktcols = nullptr;      // block columns of K~
-    double* d_nxg = nullptr;       // four rotating publication buffers of the mass-solve iterates
     int* d_nk = nullptr;           // per-step iteration counts
     double* d_nrtol2 = nullptr;    // per-step squared tolerances
     double* d_npartials = nullptr; // per-CTA block sums
@@ -251,6 +249,7 @@ int pick_W(int B);
 void krylov_free(kexp_ctx* ctx);
 // kexp_narrow.cu
 bool narrow_eligible(kexp_ctx* ctx, int W);
+void free_narrow_plan(NarrowPlanDev& P);
 int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm, const double* rtol2, bool with_basis, const double** result);
 }  // namespace kexp
 

@@ -357,6 +357,12 @@ bsr3_spmm_kernel(const int* __restrict__ browptr, const double* __restrict__ blo
                 }
                 for (int kg = k0; kg < k1; kg += GB) {
                     double2 x[GB][3];
+                    // (defined on every path: ptxas treats a conditionally defined array as live from the top of the kernel,
+                    // around all enclosing loops, and its registers are lost everywhere -- see kexp_narrow.cu, phase A)
+#pragma unroll
+                    for (int j = 0; j < GB; ++j)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) x[j][r] = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int j = 0; j < GB; ++j) {
                         if (kg + j < k1) {
@@ -504,6 +510,12 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
                 }
                 for (int kg = k0; kg < k1; kg += GB) {
                     double2 x[GB][3];
+                    // (defined on every path: ptxas treats a conditionally defined array as live from the top of the kernel,
+                    // around all enclosing loops, and its registers are lost everywhere -- see kexp_narrow.cu, phase A)
+#pragma unroll
+                    for (int j = 0; j < GB; ++j)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) x[j][r] = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int j = 0; j < GB; ++j) {
                         if (kg + j < k1) {
@@ -660,6 +672,8 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                 double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
                 double2 xo[3], bv[3], xmv[3];
 #pragma unroll
+                for (int i = 0; i < 3; ++i) xo[i] = bv[i] = xmv[i] = make_double2(0.0, 0.0);      // defined on every path
+#pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     if (!diag_first) xo[i] = ld2(xk + o + (size_t)i * W);
                     if (kPrefetch) {                       // needed only after the gather: keep the registers free
@@ -672,6 +686,12 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                 }
                 for (int kg = k0; kg < k1; kg += GB) {
                     double2 x[GB][3];
+                    // (defined on every path: ptxas treats a conditionally defined array as live from the top of the kernel,
+                    // around all enclosing loops, and its registers are lost everywhere -- see kexp_narrow.cu, phase A)
+#pragma unroll
+                    for (int j = 0; j < GB; ++j)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) x[j][r] = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int j = 0; j < GB; ++j) {
                         if (kg + j < k1) {

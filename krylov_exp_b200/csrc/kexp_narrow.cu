@@ -39,39 +39,48 @@ namespace cg = cooperative_groups;
 namespace kexp {
 
 template <int W> struct NarrowCfg {
-    static constexpr int NT = 512;                   // 1 CTA per SM, 128 registers per thread
-    static constexpr int GK = 4;                     // gathered blocks of K~ in flight per row
+    // 1 CTA per SM.  W >= 4: 256 threads, up to 255 registers each -- the mass solve keeps a whole block row (3 rows x W
+    // columns) of b, S x and the new iterate in one thread's registers.  W = 2: 384 threads (168 registers; the extra warps
+    // help the K~ product and the halo exchange, the solve itself needs one thread per block row)
+    static constexpr int NT = (W == 2) ? 384 : 256;
+    static constexpr int GK = (W == 2) ? 4 : 8;      // gathered blocks of K~ in flight per row
+    static constexpr int SS = 3 * W + (W >= 4 ? 2 : 0);   // doubles per block-row slot of the shared-memory iterates (padded: the
+                                                     // lanes of a warp read different slots; 3W doubles apart they would share banks)
 };
-constexpr int kNTmax = 512;
+constexpr int kNTmax = 384;
 constexpr int kNWarpsMax = kNTmax / 32;
+constexpr int kMaxOmega = 96;            // most Chebyshev iterations of one mass solve in the persistent kernel
 constexpr int kRChunk = 9;               // nonzeros of a row of R in flight (interior dof x the 9 edge dofs of its cell)
 
 struct NarrowArgs {
     // K~ (BSR 3x3, stored rows in locality order, rowmap = output block row)
     const int* kt_browptr; const double* kt_blocks; const int* kt_rowmap; int kt_nbr;
-    // S as per-CTA LOCAL problems (build_narrow_plan): the blocks of the rows a CTA computes -- its own rows, then (two-level
-    // plan) the rows of its first halo ring H1 -- packed per CTA with the shared-memory SLOT of each block's column in the
-    // 10th double (slots: own rows | H1 | H2); lrowptr: local row pointers; halo_cols: global block rows of H1 then H2
+    // S as per-CTA LOCAL problems (build_narrow_plan): the blocks of a CTA's own rows, packed per CTA with the SLOT of each
+    // block's column in the 10th double (slot s >= 0: own row s; s < 0: halo slot -s-1); lrowptr: local row pointers;
+    // halo_cols: global block rows of the halo (sorted); srowptr / send_dst: the CTA's send entries [cta_send_ptr[c],
+    // cta_send_ptr[c+1]): local source row and inbox slot (global numbering: halo_ptr[consumer] + its halo slot), sorted by slot
     const double* lblocks; const int* lrowptr; const int* cta_blk_ptr; const int* cta_row_ptr;
-    const int* halo_ptr; const int* halo_cols; const int* halo1_cnt;
-    const double* Pinv; int s_nbr; int levels;             // levels: 1 (one iteration per barrier) or 2
+    const int* halo_ptr; const int* halo_cols; const int* srowptr; const int* cta_send_ptr; const int* send_dst;
+    uint4* inbox; int inbox_slots;                           // two buffers of inbox_slots x 3W flagged doubles (zeroed before the launch)
+    const double* Pinv; int s_nbr;
     const int* kt_cols;                                      // block columns of K~ (global copy of the 10th doubles)
     // R (CSR, n_b x n_s) or null; Dblk (n_d/3 blocks) or null
     const int* r_rowptr; const int* r_col; const double* r_val; const double* Dblk;
     int n, n_s, n_b, n_d;
     // panels [rows][W]
     double *SA, *SB, *Y, *T, *X;
-    double* xg[4];                       // rotating publication buffers of the mass-solve iterates (n_s x W each)
     // per-panel tables (device): tscale[W], coef[(M+1)][kMaxW]; per-term iteration counts and squared tolerances
     const double* tscale; const double* coef; const int* kterm; const double* rtol2;
     int M;                               // highest term index
     int mode;                            // 0: forward recurrence y = sum a_n S_n;  1: Clenshaw (fused weighted average)
     double* basis; int basis_ld;         // mode 0: store column 0 of S_n (or null);  mode 1: z_m (required)
     double alpha, mu;                    // Chebyshev acceleration of the mass solve
+    double omega[kMaxOmega];             // omega[k]: weight of iteration k (x_k -> x_{k+1}), k = 1 .. kMaxOmega-1
     CgScalars* sc; double* partials;     // [gridDim][2][W] block sums of ||r||^2, ||b||^2
+    double* pairs;                       // convergence record handed to narrow_finish_kernel (4 doubles)
     unsigned* barrier;                   // grid barrier counter (zeroed before the launch)
     // shared-memory layout (element counts, maxima over the CTAs)
-    int cap_bpr, cap_s_rows, cap_kt_rows, cap_r_rows, cap_slots, cap_halo;     // cap_bpr: most blocks in a computed row
+    int cap_bpr, cap_s_rows, cap_kt_rows, cap_r_rows, cap_halo, cap_send;     // cap_bpr: most blocks in a row of S
     int xs_offset;                       // first double of the iterate buffers in dynamic shared memory
 };
 
@@ -92,15 +101,44 @@ __constant__ NarrowArgs c_nargs[kArgSlots];
 #define KEXP_NARROW_SYNC 1         // 0: cooperative_groups grid.sync()
 #endif
 #ifndef KEXP_NARROW_INLINE
-#define KEXP_NARROW_INLINE 0       // 1: phases inlined into one kernel body
+#define KEXP_NARROW_INLINE 1       // 1: phases inlined into one kernel body (no subroutine calls at all: see narrow_check); 0: separate functions
 #endif
 #if KEXP_NARROW_INLINE
 #define KEXP_PHASE_FN __device__ __forceinline__
 #else
 #define KEXP_PHASE_FN __device__ __noinline__
 #endif
-__device__ __forceinline__ void narrow_barrier(cg::grid_group& grid, unsigned* counter, unsigned& target) {
+#ifndef KEXP_NARROW_TIMING
+#define KEXP_NARROW_TIMING 0       // 1: thread 0 of a few CTAs accumulates clock64() per section and prints them (profiling builds only)
+#endif
+#if KEXP_NARROW_TIMING
+__device__ long long g_ntim_dummy;
+#define NTIM_DECL __shared__ long long s_tim[16]; if (threadIdx.x == 0) for (int i_ = 0; i_ < 16; ++i_) s_tim[i_] = 0;
+#define NTIM_T0 long long t0_ = clock64();
+#define NTIM_ADD(i) if (threadIdx.x == 0) { const long long t1_ = clock64(); s_tim[i] += t1_ - t0_; t0_ = t1_; }
+#else
+#define NTIM_DECL
+#define NTIM_T0
+#define NTIM_ADD(i)
+#endif
+__device__ __forceinline__ void narrow_barrier(cg::grid_group& grid, unsigned* counter, unsigned& target, long long* tim = nullptr) {
 #if KEXP_NARROW_SYNC
+#if KEXP_NARROW_TIMING
+    long long c0 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long c1 = clock64();
+        target += gridDim.x;
+        __threadfence();
+        long long c2 = clock64();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
+        long long c3 = clock64();
+        if (tim) { tim[0] += c1 - c0; tim[1] += c2 - c1; tim[2] += c3 - c2; tim[15] += 1; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && tim) tim[3] += clock64() - c0;
+#else
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
@@ -109,6 +147,7 @@ __device__ __forceinline__ void narrow_barrier(cg::grid_group& grid, unsigned* c
         while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
     }
     __syncthreads();
+#endif
 #else
     grid.sync();
 #endif
@@ -149,6 +188,19 @@ struct StepCtx {
     const double* crow;                  // coefficient row of this term
 };
 
+// S_{n-1} and S_{n-2} alternate between the two work panels; Clenshaw (mode 1) runs the terms m = M-1 ... 0
+__device__ __forceinline__ StepCtx make_step(const NarrowArgs& a, int step) {
+    StepCtx sx;
+    sx.Sin = (step & 1) ? a.SA : a.SB;              // S_{n-1}
+    sx.Snew = (step & 1) ? a.SB : a.SA;             // holds S_{n-2}, becomes S_n
+    sx.step = step;
+    sx.term = (a.mode == 0) ? step : a.M - step;
+    sx.cs = (a.mode == 0) ? (step == 1 ? 1.0 : 2.0) : (sx.term == 0 ? 1.0 : 2.0);
+    sx.has_old = (a.mode == 0) ? (step >= 2) : 1;
+    sx.crow = a.coef + (size_t)((a.mode == 0) ? sx.term : 0) * kMaxW;
+    return sx;
+}
+
 template <int W>
 __device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& sx, int lane_pair) {   // a: constant bank
     UpdCtx u;
@@ -161,10 +213,43 @@ __device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& s
     return u;
 }
 
+// Carve-up of the dynamic shared memory (every phase derives its pointers from the extern array itself, so that the
+// compiler knows they are shared-memory addresses: LDS / STS instead of generic accesses).
+struct NarrowSmem {
+    double *sv, *sP, *sred;                       // S values (transposed: [9 * bpr][ell_ld]), block-Jacobi inverses (transposed: [9][ell_ld]), reduction scratch
+    int *ss, *scnt, *sptr, *sdst, *kptr, *rptr;   // column slots ([bpr][ell_ld]), blocks per row, send entries (source row, inbox slot), row pointers of K~ and R
+    double *xo0, *xo1, *xh;                       // iterates on the own rows (two), halo of the current iterate
+    int ell_ld;
+};
+template <int W>
+__device__ __forceinline__ NarrowSmem narrow_smem_carve(const NarrowArgs& a) {
+    extern __shared__ double2 smem2[];
+    NarrowSmem m;
+    m.ell_ld = a.cap_s_rows;
+    m.sv = reinterpret_cast<double*>(smem2);
+    m.sP = m.sv + (size_t)9 * a.cap_bpr * m.ell_ld;
+    m.sred = m.sP + 9 * (size_t)a.cap_s_rows;                                  // 2 x warps x W, then 2 x W x 32 (+ 4 W)
+    m.ss = reinterpret_cast<int*>(m.sred + 2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);
+    m.scnt = m.ss + (size_t)a.cap_bpr * m.ell_ld;
+    m.sptr = m.scnt + a.cap_s_rows;
+    m.sdst = m.sptr + a.cap_send;
+    m.kptr = m.sdst + a.cap_send;
+    m.rptr = m.kptr + a.cap_kt_rows + 1;
+    m.xo0 = reinterpret_cast<double*>(smem2) + a.xs_offset;                    // 16-byte aligned
+    m.xo1 = m.xo0 + (size_t)NarrowCfg<W>::SS * a.cap_s_rows;
+    m.xh = m.xo1 + (size_t)NarrowCfg<W>::SS * a.cap_s_rows;
+    return m;
+}
+
 // ---- phase A: T = K~ S_{n-1}; depth rows (no solve) take their recurrence update in the epilogue
 template <int W>
-KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restrict__ kptr, int k0r, int k1r, int kt_b0) {
+KEXP_PHASE_FN void narrow_phase_a(int slot, int step) {
     const NarrowArgs& a = c_nargs[slot];
+    const StepCtx sx = make_step(a, step);
+    int k0r, k1r;
+    cta_range(a.kt_nbr, k0r, k1r);
+    const int kt_b0 = __ldg(a.kt_browptr + k0r);
+    const int* __restrict__ kptr = narrow_smem_carve<W>(a).kptr;
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
     constexpr int kNT = NarrowCfg<W>::NT, kNWarps = kNT / 32, kGatherK = NarrowCfg<W>::GK;
@@ -181,7 +266,13 @@ KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restr
             const int orow = a.kt_rowmap ? __ldg(a.kt_rowmap + br) : br;
             double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
             for (int q = q0; q < q1; q += kGatherK) {
+                // (every element is defined on every path: a conditionally defined array looks live from the top of the kernel
+                // to ptxas -- around the whole step loop -- and costs its registers everywhere, e.g. in the mass solve)
                 double2 x[kGatherK][3];
+#pragma unroll
+                for (int j = 0; j < kGatherK; ++j)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) x[j][r] = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int j = 0; j < kGatherK; ++j)
                     if (q + j < q1) {
@@ -226,149 +317,307 @@ KEXP_PHASE_FN void narrow_phase_a(int slot, const StepCtx sx, const int* __restr
     }
 }
 
-// Shared-memory state of the mass solve (per CTA): xa = x_k on [own rows | halo rows], xb = x_{k-1} on the own rows (it
-// becomes x_{k+1}; its halo part is filled after the next barrier), bs = b on the own rows.  Row r of a slot starts at
-// (3*slot + r) * W doubles.
-// Shared-memory state of the mass solve (per CTA), in block-row SLOTS: own rows | first halo ring H1 | second ring H2.
-// Row r of a slot starts at (3*slot + r) * W doubles.  Two iterate arrays over all slots and b on the rows the CTA computes
-// (own rows, plus H1 in the two-level plan).
+// ---- phase B: the mass solve of one term.
+// Shared-memory state (per CTA), in block-row SLOTS of 3 rows x W doubles: two iterate arrays over the OWN rows (xo0 / xo1:
+// x_k and x_{k-1}, the latter overwritten by x_{k+1}) and ONE halo array (x_k on the rows of other CTAs that the own rows
+// reference).  b (own rows) lives in REGISTERS: the row <-> thread assignment is fixed for the whole solve (NP passes of
+// NT / LPB block rows).
 //
-// ---- phase B, start: on the computed rows  b <- T (global), x_1 = alpha P^-1 b -> cur, x_0 = 0 -> prev; the own rows of
-// x_1 and x_0 are published (g1, g0).  x_1 on H1 is computed locally (bit-identical to the owner's).  Returns ||b||^2 (own).
-template <int W>
-KEXP_PHASE_FN double2 narrow_solve_start(int slot, double* g1, double* g0, double* cur, double* prev, double* bs, const double* __restrict__ sP,
-                                         const int* __restrict__ hcol, int s0, int n_own, int n_rows) {
-    const NarrowArgs& a = c_nargs[slot];
-    using C = PanelCfg<W, 2>;
-    constexpr int LPB = C::LPB, BRW = C::BRW;
-    constexpr int BPC = (NarrowCfg<W>::NT / 32) * BRW;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = lane % LPB, g = lane / LPB;
-    double2 accb = make_double2(0.0, 0.0);
-    for (int base = 0; base < n_rows; base += BPC) {
-        const int lr = base + warp * BRW + g;
-        if (lr < n_rows) {
-            const bool own = lr < n_own;
-            const int gr = own ? s0 + lr : hcol[lr - n_own];
-            const size_t o = (size_t)(3 * gr) * W + 2 * l;
-            const int ls = (3 * lr) * W + 2 * l;
-            double2 bv[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                bv[i] = ldcg2(a.T + o + (size_t)i * W);
-                *reinterpret_cast<double2*>(bs + ls + i * W) = bv[i];
-                if (own) { accb.x = fma(bv[i].x, bv[i].x, accb.x); accb.y = fma(bv[i].y, bv[i].y, accb.y); }
-            }
-            const double* Pb = sP + 9 * lr;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double2 z;
-                z.x = a.alpha * fma(Pb[3 * i], bv[0].x, fma(Pb[3 * i + 1], bv[1].x, Pb[3 * i + 2] * bv[2].x));
-                z.y = a.alpha * fma(Pb[3 * i], bv[0].y, fma(Pb[3 * i + 1], bv[1].y, Pb[3 * i + 2] * bv[2].y));
-                *reinterpret_cast<double2*>(cur + ls + i * W) = z;
-                *reinterpret_cast<double2*>(prev + ls + i * W) = make_double2(0.0, 0.0);
-                if (own) {
-                    *reinterpret_cast<double2*>(g1 + o + (size_t)i * W) = z;
-                    *reinterpret_cast<double2*>(g0 + o + (size_t)i * W) = make_double2(0.0, 0.0);
-                }
-            }
-        }
-    }
-    return accb;
+// Halo exchange WITHOUT a grid barrier ("LL" protocol: flag-in-data).  Every double travels as 16 bytes
+// {lo32, flag, hi32, flag}; 8-byte aligned words are single-copy atomic, so a reader that sees both flags equal to the
+// number of the exchange it waits for has the value -- no fence, no counter, no separate "data is there" round trip.  The
+// thread that computes x_{k+1} of a boundary row stores it straight into the inbox slot of every CTA that has that row in its
+// halo (send lists precomputed on the host); the consumer's threads poll their own inbox elements and copy them to shared
+// memory.  Two inbox buffers alternate (exchange number parity): a CTA can only be ONE exchange ahead of a neighbour,
+// because its next iterate needs that neighbour's current one (the sparsity of S is structurally symmetric; checked on the
+// host).  Exchange numbers increase monotonically through the whole launch; the inbox is zeroed before the launch.
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned flag) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 
-// ---- phase B, halo exchange: halo slots [h_lo, h_hi) of a published iterate, global -> shared (each row once, 16-byte
-// pieces, coalesced within a row)
-template <int W>
-KEXP_PHASE_FN void narrow_load_halo(const double* xg, double* xs, const int* __restrict__ hcol, int n_own, int h_lo, int h_hi) {
-    constexpr int PPR = 3 * W / 2;                     // 16-byte pieces per block row (3 rows x W doubles, contiguous)
-    constexpr int NT = NarrowCfg<W>::NT;
-    for (int e = h_lo * PPR + threadIdx.x; e < h_hi * PPR; e += NT) {
-        const int h = e / PPR, p = e % PPR;
-        const double2 v = ldcg2(xg + (size_t)(3 * hcol[h]) * W + 2 * p);
-        *reinterpret_cast<double2*>(xs + (size_t)(3 * (n_own + h)) * W + 2 * p) = v;
+// wait for exchange `flag` on the CTA's inbox elements [0, ne) and copy them to the halo array (shared memory)
+template <int NT, int RW, int SS>    // RW = 3W doubles per inbox slot, SS doubles per shared-memory slot
+__device__ __forceinline__ void ll_recv(const uint4* __restrict__ inbox, double* __restrict__ xh, int ne, unsigned flag) {
+    constexpr int U = 4;                               // elements in flight per thread
+    for (int e0 = threadIdx.x; e0 < ne; e0 += NT * U) {
+        uint4 v[U];
+        bool pending;
+        do {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (e0 + u * NT < ne) v[u] = ll_load(inbox + e0 + u * NT);
+            pending = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (e0 + u * NT < ne && (v[u].y != flag || v[u].w != flag)) pending = true;
+        } while (pending);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (e0 + u * NT < ne) { const int e = e0 + u * NT; xh[(e / RW) * SS + (e % RW)] = __hiloint2double((int)v[u].z, (int)v[u].x); }
     }
 }
 
-// ---- phase B, one Chebyshev iteration on the local rows [0, n_rows), everything read from shared memory:
-//   x_{k+1} = x_{k-1} + omega (x_k + alpha P^-1 (b - S x_k) - x_{k-1}),   x_k = cur (all slots the rows reference), x_{k-1} = prev,
-// written over prev; the own rows (lr < n_own) are published to gout (and to gout2: the final iterate also goes to a.X).
-// LAST also forms ||b - S x_k||^2 and the recurrence update of the edge rows (W = x_K).
-template <int W, bool LAST>
-KEXP_PHASE_FN double2 narrow_solve_iter(int slot, const StepCtx sx, const double* cur, double* prev, const double* bs, double* gout, double* gout2,
-                                        double omega, const double* __restrict__ sv, const int* __restrict__ ss, const double* __restrict__ sP,
-                                        const int* __restrict__ scnt, int ell_ld, int s0, int n_own, int n_rows) {
+// S x on one block row, all W columns in one thread: everything from shared memory.  The matrix is stored TRANSPOSED
+// (element e of block q of local row lr at sv[(9 q + e) ell_ld + lr], its column slot at ss[q ell_ld + lr]: the rows of a warp
+// read consecutive words -- no bank conflicts).  Slot s >= 0: own row s; s < 0: halo slot -s-1.
+// the block row of x in slot s (s >= 0: own row s; s < 0: halo slot -s-1)
+template <int W>
+__device__ __forceinline__ void narrow_load_x(int s, const double* __restrict__ xo, const double* __restrict__ xh, double2 (&x)[3][W / 2]) {
+    constexpr int NV = W / 2, SS = NarrowCfg<W>::SS;
+    const double* xr = (s >= 0 ? xo + s * SS : xh + (-s - 1) * SS);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) x[r][v] = *reinterpret_cast<const double2*>(xr + r * W + 2 * v);
+}
+// one 3x3 block (row-major m[9]) times a block row of x
+template <int W>
+__device__ __forceinline__ void narrow_block_mul(const double (&m)[9], const double2 (&x)[3][W / 2], double2 (&acc)[3][W / 2]) {
+    constexpr int NV = W / 2;
+    // same order as the wide-panel kernels: for each block, columns r = 0, 1, 2 of the 3x3 block in turn
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                acc[i][v].x = fma(m[3 * i + r], x[r][v].x, acc[i][v].x);
+                acc[i][v].y = fma(m[3 * i + r], x[r][v].y, acc[i][v].y);
+            }
+}
+template <int W>
+__device__ __forceinline__ void narrow_block_apply(const double (&m)[9], int s, const double* __restrict__ xo, const double* __restrict__ xh,
+                                                   double2 (&acc)[3][W / 2]) {
+    constexpr int NV = W / 2;
+    double2 x[3][NV];
+    narrow_load_x<W>(s, xo, xh, x);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                acc[i][v].x = fma(m[3 * i + r], x[r][v].x, acc[i][v].x);
+                acc[i][v].y = fma(m[3 * i + r], x[r][v].y, acc[i][v].y);
+            }
+}
+template <int W>
+__device__ __forceinline__ void narrow_block_fma(const double* __restrict__ sv, const int* __restrict__ ss, int ell_ld, int lr, int q,
+                                                 const double* __restrict__ xo, const double* __restrict__ xh, double2 (&acc)[3][W / 2]) {
+    const double* vp = sv + (size_t)(9 * q) * ell_ld + lr;
+    double m[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) m[e] = vp[e * ell_ld];
+    narrow_block_apply<W>(m, ss[q * ell_ld + lr], xo, xh, acc);
+}
+
+// publish the boundary rows of an iterate (in shared memory) to the CTAs that have them in their halo: the CTA's send entries
+// (source row, inbox slot of the consumer) are walked by all threads, consecutive threads -> consecutive doubles of a row,
+// so that the flagged 16-byte stores of a warp are contiguous
+template <int NT, int RW, int SS>
+__device__ __forceinline__ void narrow_send(uint4* __restrict__ inbox_par, const int* __restrict__ srow, const int* __restrict__ sdst, int nsend,
+                                            const double* __restrict__ xo, unsigned flag) {
+    for (int e = threadIdx.x; e < nsend * RW; e += NT) {
+        const int ent = e / RW, j = e % RW;
+        ll_store(inbox_par + (size_t)sdst[ent] * RW + j, xo[srow[ent] * SS + j], flag);
+    }
+}
+
+// The whole Chebyshev semi-iteration of one term on the CTA's own rows:  x_1 = alpha P^-1 b, then K - 1 iterations
+//   x_{k+1} = x_{k-1} + omega_k (x_k + alpha P^-1 (b - S x_k) - x_{k-1});
+// the last one also forms ||b - S x_{K-1}||^2, writes x_K to a.X and applies the recurrence update of the edge rows.
+// One thread per block row (NP passes of NT rows), all W columns of the row in its registers.
+// Leaves the block sums of ||r||^2 and ||b||^2 per column in a.partials.  Returns the next exchange number.
+template <int W, int NP>
+KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
+#if KEXP_NARROW_TIMING
+                                    , long long* s_tim
+#endif
+) {
     const NarrowArgs& a = c_nargs[slot];
-    using C = PanelCfg<W, 2>;
-    constexpr int LPB = C::LPB, BRW = C::BRW;
-    constexpr int BPC = (NarrowCfg<W>::NT / 32) * BRW;
+    const NarrowSmem sm = narrow_smem_carve<W>(a);
+    const StepCtx sx = make_step(a, step);
+    const int K = a.kterm[step];
+    int s0, s1;
+    cta_range(a.s_nbr, s0, s1);
+    const int n_own = s1 - s0;
+    const int h0 = __ldg(a.halo_ptr + blockIdx.x), n_h1 = __ldg(a.halo_ptr + blockIdx.x + 1) - h0;
+    const int nsend = __ldg(a.cta_send_ptr + blockIdx.x + 1) - __ldg(a.cta_send_ptr + blockIdx.x);
+    constexpr int NT = NarrowCfg<W>::NT, kNWarps = NT / 32, NV = W / 2, SS = NarrowCfg<W>::SS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = lane % LPB, g = lane / LPB;
-    UpdCtx u;
-    if (LAST) u = make_upd<W>(a, sx, l);
-    double2 accr = make_double2(0.0, 0.0);
-    for (int base = 0; base < n_rows; base += BPC) {
-        const int lr = base + warp * BRW + g;
-        if (lr < n_rows) {
-            const int nq = scnt[lr];
-            const int ls = (3 * lr) * W + 2 * l;
-            double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
-            // the matrix is stored TRANSPOSED in shared memory (element e of block q of local row lr at sv[(9 q + e) ell_ld + lr],
-            // its column slot at ss[q ell_ld + lr]): the rows of a warp read consecutive words -- no bank conflicts, where the
-            // 80-byte blocks of one row per lane conflicted 4-way
-            for (int q = 0; q < nq; ++q) {
-                const double* vp = sv + (size_t)(9 * q) * ell_ld + lr;
-                const double* xr = cur + (3 * ss[q * ell_ld + lr]) * W + 2 * l;
-                const double2 x0 = *reinterpret_cast<const double2*>(xr), x1 = *reinterpret_cast<const double2*>(xr + W),
-                              x2 = *reinterpret_cast<const double2*>(xr + 2 * W);
-                const double m00 = vp[0], m01 = vp[ell_ld], m02 = vp[2 * ell_ld], m10 = vp[3 * ell_ld], m11 = vp[4 * ell_ld], m12 = vp[5 * ell_ld],
-                             m20 = vp[6 * ell_ld], m21 = vp[7 * ell_ld], m22 = vp[8 * ell_ld];
-                // same order as the wide-panel kernels: for each block, columns r = 0, 1, 2 of the 3x3 block in turn
-                acc[0].x = fma(m00, x0.x, acc[0].x); acc[0].y = fma(m00, x0.y, acc[0].y);
-                acc[1].x = fma(m10, x0.x, acc[1].x); acc[1].y = fma(m10, x0.y, acc[1].y);
-                acc[2].x = fma(m20, x0.x, acc[2].x); acc[2].y = fma(m20, x0.y, acc[2].y);
-                acc[0].x = fma(m01, x1.x, acc[0].x); acc[0].y = fma(m01, x1.y, acc[0].y);
-                acc[1].x = fma(m11, x1.x, acc[1].x); acc[1].y = fma(m11, x1.y, acc[1].y);
-                acc[2].x = fma(m21, x1.x, acc[2].x); acc[2].y = fma(m21, x1.y, acc[2].y);
-                acc[0].x = fma(m02, x2.x, acc[0].x); acc[0].y = fma(m02, x2.y, acc[0].y);
-                acc[1].x = fma(m12, x2.x, acc[1].x); acc[1].y = fma(m12, x2.y, acc[1].y);
-                acc[2].x = fma(m22, x2.x, acc[2].x); acc[2].y = fma(m22, x2.y, acc[2].y);
-            }
-            double2 rv[3];
+    const int ell_ld = sm.ell_ld;
+    const size_t inbox_half = (size_t)a.inbox_slots * (3 * W);
+    const uint4* my_inbox = a.inbox + (size_t)h0 * (3 * W);
+    const int ne = n_h1 * 3 * W;
+    double2 bv[NP][3][NV];
+    double* cur = sm.xo0;                               // x_k on the own rows
+    double* prev = sm.xo1;                              // x_{k-1} on the own rows -> x_{k+1}
+    NTIM_T0
+    // ---- start: b <- T (global), x_1 = alpha P^-1 b, x_0 = 0
+    double accb[W];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double2 bv = *reinterpret_cast<const double2*>(bs + ls + i * W);
-                rv[i].x = bv.x - acc[i].x; rv[i].y = bv.y - acc[i].y;
-                if (LAST) { accr.x = fma(rv[i].x, rv[i].x, accr.x); accr.y = fma(rv[i].y, rv[i].y, accr.y); }
-            }
-            const double* Pb = sP + 9 * lr;
-            const bool own = lr < n_own;
-            const size_t o = (size_t)(3 * (s0 + lr)) * W + 2 * l;          // only meaningful for own rows
+    for (int c = 0; c < W; ++c) accb[c] = 0.0;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const double2 xo = *reinterpret_cast<const double2*>(cur + ls + i * W);
-                const double2 xmv = *reinterpret_cast<const double2*>(prev + ls + i * W);
-                double2 z, xn;
-                z.x = fma(Pb[3 * i], rv[0].x, fma(Pb[3 * i + 1], rv[1].x, Pb[3 * i + 2] * rv[2].x));
-                z.y = fma(Pb[3 * i], rv[0].y, fma(Pb[3 * i + 1], rv[1].y, Pb[3 * i + 2] * rv[2].y));
-                xn.x = fma(omega, fma(a.alpha, z.x, xo.x) - xmv.x, xmv.x);
-                xn.y = fma(omega, fma(a.alpha, z.y, xo.y) - xmv.y, xmv.y);
-                *reinterpret_cast<double2*>(prev + ls + i * W) = xn;
-                if (own) {
-                    if (gout) *reinterpret_cast<double2*>(gout + o + (size_t)i * W) = xn;
-                    if (gout2) *reinterpret_cast<double2*>(gout2 + o + (size_t)i * W) = xn;
-                    if (LAST) row_update(u, o + (size_t)i * W, (size_t)(3 * (s0 + lr) + i), xn);     // edge rows: W = x_K
+    for (int p = 0; p < NP; ++p) {
+        const int lr = p * NT + threadIdx.x;
+        if (lr < n_own) {
+            const size_t o = (size_t)(3 * (s0 + lr)) * W;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    bv[p][i][v] = ldcg2(a.T + o + (size_t)i * W + 2 * v);
+                    accb[2 * v] = fma(bv[p][i][v].x, bv[p][i][v].x, accb[2 * v]);
+                    accb[2 * v + 1] = fma(bv[p][i][v].y, bv[p][i][v].y, accb[2 * v + 1]);
+                }
+            double P[3][3];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = sm.sP[e * ell_ld + lr];
+            double2 z[3][NV];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    z[i][v].x = a.alpha * fma(P[i][0], bv[p][0][v].x, fma(P[i][1], bv[p][1][v].x, P[i][2] * bv[p][2][v].x));
+                    z[i][v].y = a.alpha * fma(P[i][0], bv[p][0][v].y, fma(P[i][1], bv[p][1][v].y, P[i][2] * bv[p][2][v].y));
+                    *reinterpret_cast<double2*>(cur + lr * SS + i * W + 2 * v) = z[i][v];
+                    *reinterpret_cast<double2*>(prev + lr * SS + i * W + 2 * v) = make_double2(0.0, 0.0);
+                }
+        }
+    }
+    __syncthreads();                                    // x_1 on the own rows complete
+    narrow_send<NT, 3 * W, SS>(a.inbox + (size_t)(xid & 1u) * inbox_half, sm.sptr, sm.sdst, nsend, cur, xid);
+    // warp sums of ||b||^2 per column (fixed order) -> reduction scratch
+#pragma unroll
+    for (int c = 0; c < W; ++c) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) accb[c] += __shfl_xor_sync(0xffffffffu, accb[c], off);
+        if (lane == 0) sm.sred[(1 * kNWarps + warp) * W + c] = accb[c];
+    }
+    NTIM_ADD(6)
+    for (int it = 1; it < K; ++it) {
+        // halo of x_it (exchange xid); the halo array is free: every thread has finished the previous iteration (the barrier
+        // in front of its sends)
+        ll_recv<NT, 3 * W, SS>(my_inbox + (size_t)(xid & 1u) * inbox_half, sm.xh, ne, xid);
+        __syncthreads();                                // own rows (written by the previous iteration / the start) and halo of x_it complete
+        NTIM_ADD(7)
+        ++xid;
+        const double omega = a.omega[it];
+        const bool last = (it == K - 1);
+        uint4* out_inbox = a.inbox + (size_t)(xid & 1u) * inbox_half;
+        double accr[W];                                     // ||b - S x_k||^2 per column: formed by the last iteration only
+#pragma unroll
+        for (int c = 0; c < W; ++c) accr[c] = 0.0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int lr = p * NT + threadIdx.x;
+            if (lr < n_own) {
+                const int nq = sm.scnt[lr];
+                double2 acc[3][NV];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) acc[i][v] = make_double2(0.0, 0.0);
+                if (W <= 4 && nq == 5) {                 // BDM2 edge rows: the edge and the four other edges of its two cells
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) narrow_block_fma<W>(sm.sv, sm.ss, ell_ld, lr, q, cur, sm.xh, acc);
+                } else {                                        // (8 columns: one block's 72 products at a time fill the registers)
+#pragma unroll 1
+                    for (int q = 0; q < nq; ++q) narrow_block_fma<W>(sm.sv, sm.ss, ell_ld, lr, q, cur, sm.xh, acc);
+                }
+                NTIM_ADD(1)
+                double P[3][3];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = sm.sP[e * ell_ld + lr];
+                // acc <- r = b - S x_k
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        acc[i][v].x = bv[p][i][v].x - acc[i][v].x; acc[i][v].y = bv[p][i][v].y - acc[i][v].y;
+                        if (last) {
+                            accr[2 * v] = fma(acc[i][v].x, acc[i][v].x, accr[2 * v]);
+                            accr[2 * v + 1] = fma(acc[i][v].y, acc[i][v].y, accr[2 * v + 1]);
+                        }
+                    }
+                double2 xn[3][NV];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const double2 xo = *reinterpret_cast<const double2*>(cur + lr * SS + i * W + 2 * v);
+                        const double2 xmv = *reinterpret_cast<const double2*>(prev + lr * SS + i * W + 2 * v);
+                        double2 z;
+                        z.x = fma(P[i][0], acc[0][v].x, fma(P[i][1], acc[1][v].x, P[i][2] * acc[2][v].x));
+                        z.y = fma(P[i][0], acc[0][v].y, fma(P[i][1], acc[1][v].y, P[i][2] * acc[2][v].y));
+                        xn[i][v].x = fma(omega, fma(a.alpha, z.x, xo.x) - xmv.x, xmv.x);
+                        xn[i][v].y = fma(omega, fma(a.alpha, z.y, xo.y) - xmv.y, xmv.y);
+                    }
+                NTIM_ADD(2)
+                if (!last) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) *reinterpret_cast<double2*>(prev + lr * SS + i * W + 2 * v) = xn[i][v];
+                } else {
+                    const size_t o = (size_t)(3 * (s0 + lr)) * W;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const UpdCtx u = make_upd<W>(a, sx, v);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            *reinterpret_cast<double2*>(a.X + o + (size_t)i * W + 2 * v) = xn[i][v];
+                            row_update(u, o + (size_t)i * W + 2 * v, (size_t)(3 * (s0 + lr) + i), xn[i][v]);     // edge rows: W = x_K
+                        }
+                    }
                 }
             }
         }
+        if (last) {
+#pragma unroll
+            for (int c = 0; c < W; ++c) {
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) accr[c] += __shfl_xor_sync(0xffffffffu, accr[c], off);
+                if (lane == 0) sm.sred[(0 * kNWarps + warp) * W + c] = accr[c];
+            }
+        }
+        NTIM_ADD(9)
+        if (!last) {
+            __syncthreads();                            // x_{it+1} on the own rows complete (and nobody reads the halo of x_it any more)
+            narrow_send<NT, 3 * W, SS>(out_inbox, sm.sptr, sm.sdst, nsend, prev, xid);
+        }
+        NTIM_ADD(3)
+        double* tsw = cur; cur = prev; prev = tsw;
     }
-    return accr;
+    // block sums of ||r||^2 and ||b||^2 per column (fixed order): the warp sums in turn
+    {
+        __syncthreads();
+        if (threadIdx.x < 2 * W) {
+            const int q = threadIdx.x / W, c = threadIdx.x % W;
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kNWarps; ++w) t += sm.sred[(q * kNWarps + w) * W + c];
+            a.partials[((size_t)blockIdx.x * 2 + q) * W + c] = t;
+        }
+    }
+    NTIM_ADD(10)
+    return xid;
 }
 
 // ---- phase C: interior rows  w_I = T_I + R x_K  and their recurrence update
 template <int W>
-KEXP_PHASE_FN void narrow_phase_c(int slot, const StepCtx sx, const int* __restrict__ rptr, int r0, int r1) {
+KEXP_PHASE_FN void narrow_phase_c(int slot, int step) {
     const NarrowArgs& a = c_nargs[slot];
+    const StepCtx sx = make_step(a, step);
+    int r0, r1;
+    cta_range(a.n_b, r0, r1);
+    const int* __restrict__ rptr = narrow_smem_carve<W>(a).rptr;
     constexpr int LPR = W / 2;
     constexpr int RPC = NarrowCfg<W>::NT / LPR;
     const int lr = threadIdx.x % LPR;
@@ -383,6 +632,8 @@ KEXP_PHASE_FN void narrow_phase_c(int slot, const StepCtx sx, const int* __restr
             double2 x[kRChunk];
             double v[kRChunk];
 #pragma unroll
+            for (int j = 0; j < kRChunk; ++j) { x[j] = make_double2(0.0, 0.0); v[j] = 0.0; }      // defined on every path (see phase A)
+#pragma unroll
             for (int j = 0; j < kRChunk; ++j)
                 if (q + j < q1) {
                     x[j] = ldcg2(a.X + (size_t)__ldg(a.r_col + qbase + q + j) * W + 2 * lr);
@@ -396,10 +647,18 @@ KEXP_PHASE_FN void narrow_phase_c(int slot, const StepCtx sx, const int* __restr
     }
 }
 
-// ---- convergence record of one solve (CTA 0, fixed summation order over the per-CTA block sums)
+// ---- convergence record of one solve (CTA 0, fixed summation order over the per-CTA block sums).  No division and no
+// square root in here: their slow paths are subroutine CALLs, and a kernel that contains calls gets a far worse register
+// allocation everywhere (ptxas then keeps call-free regions in the caller-saved registers only: the matrix rows of
+// narrow_solve3 were spilled with 100 registers idle).  The worst column of a solve is found by cross-multiplication;
+// pairs[0..1]: (||r||^2, ||b||^2) of the worst column of the last solve, pairs[2..3]: of the worst solve that missed its
+// tolerance -- narrow_finish_kernel turns them into relative residuals behind the launch.
 template <int W>
-KEXP_PHASE_FN void narrow_check(int slot, double* fin, int K, double rtol2, int* s_bad) {
+KEXP_PHASE_FN void narrow_check(int slot, int step, double* pairs, int* s_bad) {
     const NarrowArgs& a = c_nargs[slot];
+    double* fin = narrow_smem_carve<W>(a).sred + 2 * kNWarpsMax * W;
+    const int K = a.kterm[step];
+    const double rtol2 = a.rtol2[step];
     constexpr int kNT = NarrowCfg<W>::NT;
     constexpr int TPV = kNT / (2 * W) > 32 ? 32 : kNT / (2 * W);      // threads per value
     const int val = threadIdx.x / TPV, part = threadIdx.x % TPV;
@@ -417,79 +676,68 @@ KEXP_PHASE_FN void narrow_check(int slot, double* fin, int K, double rtol2, int*
         tot[threadIdx.x] = s;
     }
     __syncthreads();
-    double* relv = tot + 2 * W;
     if (threadIdx.x < W) {
         const double rr = tot[threadIdx.x], bb = tot[W + threadIdx.x];
-        double rel = 0.0;
-        if (bb > 0.0) {
-            rel = rr / bb;
-            if (rr > rtol2 * bb) atomicOr(s_bad, 1);
-        }
-        relv[threadIdx.x] = rel;
+        if (bb > 0.0 && rr > rtol2 * bb) atomicOr(s_bad, 1);
         a.sc->rr[threadIdx.x] = rr; a.sc->bb[threadIdx.x] = bb;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double m = 0.0;
-        for (int c = 0; c < W; ++c) m = fmax(m, relv[c]);
+        double wr = 0.0, wb = 1.0;                        // worst column: largest rr / bb
+        for (int c = 0; c < W; ++c) {
+            const double rr = tot[c], bb = tot[W + c];
+            if (bb > 0.0 && rr * wb > wr * bb) { wr = rr; wb = bb; }
+        }
+        pairs[0] = wr; pairs[1] = wb;
         CgScalars* sc = a.sc;
-        sc->max_rel_res = sqrt(m);
         sc->iters = K;
         sc->total_iters += (unsigned long long)K;
         sc->total_solves += 1ull;
         if (K > sc->max_iters) sc->max_iters = K;
         sc->done = *s_bad ? 0 : 1;
-        if (*s_bad) { sc->unconverged += 1; sc->worst_rel_res = fmax(sc->worst_rel_res, sc->max_rel_res); }
+        if (*s_bad) {
+            sc->unconverged += 1;
+            if (wr * pairs[3] > pairs[2] * wb) { pairs[2] = wr; pairs[3] = wb; }
+        }
     }
 }
 
+// relative residuals of the convergence record (one thread, behind the persistent kernel)
+__global__ void narrow_finish_kernel(const double* __restrict__ pairs, CgScalars* __restrict__ sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        sc->max_rel_res = sqrt(pairs[0] / pairs[1]);
+        if (pairs[2] > 0.0) sc->worst_rel_res = fmax(sc->worst_rel_res, sqrt(pairs[2] / pairs[3]));
+    }
+}
 
+// ---- staging of the CTA's constant data (its rows of S transposed, P^-1, send lists, row pointers of K~ and R) and the
+// prologue of the recurrence
 template <int W>
-__global__ void __launch_bounds__(NarrowCfg<W>::NT, 1)
-cheb_apply_narrow_kernel(const int slot) {
+KEXP_PHASE_FN void narrow_prologue(int slot) {
     const NarrowArgs& a = c_nargs[slot];
-    using C = PanelCfg<W, 2>;
-    constexpr int kNT = NarrowCfg<W>::NT, kNWarps = kNT / 32;
-    constexpr int LPB = C::LPB;
+    constexpr int kNT = NarrowCfg<W>::NT;
     constexpr int LPR = W / 2;                         // lanes per scalar row
     constexpr int RPC = kNT / LPR;                     // scalar rows per CTA pass
-    cg::grid_group grid = cg::this_grid();
+    const NarrowSmem sm = narrow_smem_carve<W>(a);
+    const int ell_ld = sm.ell_ld;
+    double* sv = sm.sv; double* sP = sm.sP; double* sred = sm.sred;
+    int* ss = sm.ss; int* scnt = sm.scnt; int* sptr = sm.sptr; int* sdst = sm.sdst; int* kptr = sm.kptr; int* rptr = sm.rptr;
 
-    extern __shared__ double2 smem2[];
-    const int ell_ld = a.cap_s_rows;                                           // leading dimension of the transposed matrix arrays
-    double* sv = reinterpret_cast<double*>(smem2);                             // S values, transposed: [9 * bpr][ell_ld]
-    double* sP = sv + (size_t)9 * a.cap_bpr * ell_ld;                          // block-Jacobi inverses of the computed rows
-    double* sred = sP + 9 * (size_t)a.cap_s_rows;                              // reduction scratch: 2 x warps x W, then 2 x W x 32
-    int* ss = reinterpret_cast<int*>(sred + 2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);   // column slots, transposed: [bpr][ell_ld]
-    int* scnt = ss + (size_t)a.cap_bpr * ell_ld;                               // blocks per computed row
-    int* kptr = scnt + a.cap_s_rows;
-    int* rptr = kptr + a.cap_kt_rows + 1;
-    int* hcol = rptr + a.cap_r_rows + 1;
-    // mass-solve state: two iterate arrays over [own | H1 | H2] slots and b on the computed rows (16-byte aligned)
-    double* xs0 = reinterpret_cast<double*>(smem2) + a.xs_offset;
-    double* xs1 = xs0 + (size_t)3 * W * a.cap_slots;
-    double* bsm = xs1 + (size_t)3 * W * a.cap_slots;
-    __shared__ int s_bad;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = lane % LPB;
     int s0, s1, k0r, k1r, r0, r1;
     cta_range(a.s_nbr, s0, s1);
     cta_range(a.kt_nbr, k0r, k1r);
     cta_range(a.n_b, r0, r1);
     const int kt_b0 = __ldg(a.kt_browptr + k0r);
     const int n_own = s1 - s0;
-    const int h0 = __ldg(a.halo_ptr + blockIdx.x), n_halo = __ldg(a.halo_ptr + blockIdx.x + 1) - h0;
-    const int n_h1 = __ldg(a.halo1_cnt + blockIdx.x);
-    const int n_rows = (a.levels == 2) ? n_own + n_h1 : n_own;                 // rows this CTA computes
+    const int h0 = __ldg(a.halo_ptr + blockIdx.x), n_h1 = __ldg(a.halo_ptr + blockIdx.x + 1) - h0;
 
     // ---- stage the constant data of this CTA
     {
-        for (int i = threadIdx.x; i < n_halo; i += kNT) hcol[i] = __ldg(a.halo_cols + h0 + i);
         const int b0 = __ldg(a.cta_blk_ptr + blockIdx.x);
         const double* gsrc = a.lblocks + (size_t)10 * b0;
-        const int* lrp = a.lrowptr + __ldg(a.cta_row_ptr + blockIdx.x);
-        for (int lr = threadIdx.x; lr < n_rows; lr += kNT) {                   // one row per thread: transpose its blocks
+        const int row_base = __ldg(a.cta_row_ptr + blockIdx.x);
+        const int* lrp = a.lrowptr + row_base;
+        for (int lr = threadIdx.x; lr < n_own; lr += kNT) {                    // one row per thread: transpose its blocks
             const int q0 = __ldg(lrp + lr), q1 = __ldg(lrp + lr + 1);
             scnt[lr] = q1 - q0;
             for (int q = q0; q < q1; ++q) {
@@ -499,12 +747,9 @@ cheb_apply_narrow_kernel(const int slot) {
                 ss[(q - q0) * ell_ld + lr] = __double2loint(__ldg(bp + 9));
             }
         }
-        __syncthreads();                                                       // hcol
-        for (int i = threadIdx.x; i < 9 * n_rows; i += kNT) {
-            const int lr = i / 9, e = i % 9;
-            const int gr = lr < n_own ? s0 + lr : hcol[lr - n_own];
-            sP[i] = __ldg(a.Pinv + (size_t)9 * gr + e);
-        }
+        for (int i = threadIdx.x; i < 9 * n_own; i += kNT) sP[(i % 9) * ell_ld + i / 9] = __ldg(a.Pinv + (size_t)9 * s0 + i);
+        const int sd0 = __ldg(a.cta_send_ptr + blockIdx.x), nsd = __ldg(a.cta_send_ptr + blockIdx.x + 1) - sd0;
+        for (int i = threadIdx.x; i < nsd; i += kNT) { sptr[i] = __ldg(a.srowptr + sd0 + i); sdst[i] = __ldg(a.send_dst + sd0 + i); }
         for (int i = threadIdx.x; i <= k1r - k0r; i += kNT) kptr[i] = __ldg(a.kt_browptr + k0r + i) - kt_b0;
         if (a.n_b > 0) {
             const int q0 = __ldg(a.r_rowptr + r0);
@@ -529,100 +774,64 @@ cheb_apply_narrow_kernel(const int slot) {
             }
         }
     }
+}
+
+template <int W, int NP>
+__global__ void __launch_bounds__(NarrowCfg<W>::NT, 1)
+cheb_apply_narrow_kernel(const int slot) {
+    const NarrowArgs& a = c_nargs[slot];
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_bad;
+    __shared__ double s_pairs[4];
+    if (threadIdx.x == 0) { s_pairs[0] = 0.0; s_pairs[1] = 1.0; s_pairs[2] = 0.0; s_pairs[3] = 1.0; }
+    narrow_prologue<W>(slot);
     unsigned bar_target = 0;
+    NTIM_DECL
     narrow_barrier(grid, a.barrier, bar_target);
 
-    StepCtx sx;
-    sx.Sin = a.SA;               // S_{n-1}
-    sx.Snew = a.SB;              // holds S_{n-2}, becomes S_n
+    unsigned xid = 1;                                    // number of the next halo exchange (the inbox holds zeros)
+    // Every phase is a separate, NOT inlined function that derives what it needs (row ranges, shared-memory pointers, the
+    // constants of the step) from blockIdx, the step number and the constant bank: nothing but the three counters below is
+    // live across the calls, so each phase has the whole register file to itself.
     for (int step = 1; step <= a.M; ++step) {
-        // term index / coefficient row / scale of this step (Clenshaw runs m = M-1 ... 0)
-        sx.step = step;
-        sx.term = (a.mode == 0) ? step : a.M - step;
-        sx.cs = (a.mode == 0) ? (step == 1 ? 1.0 : 2.0) : (sx.term == 0 ? 1.0 : 2.0);
-        sx.has_old = (a.mode == 0) ? (step >= 2) : 1;
-        sx.crow = a.coef + (size_t)((a.mode == 0) ? sx.term : 0) * kMaxW;
-
-        narrow_phase_a<W>(slot, sx, kptr, k0r, k1r, kt_b0);
+        NTIM_T0
+        narrow_phase_a<W>(slot, step);
+        NTIM_ADD(4)
         narrow_barrier(grid, a.barrier, bar_target);
-
-        // ---- mass solve on the own rows of S: Chebyshev semi-iteration, K - 1 iterations behind x_1, one or two per barrier.
-        // Published iterates rotate through four global buffers: gc holds x_k, gp holds x_{k-1}, the other two are written.
-        const int K = a.kterm[step];
-        int gc = 0, gp = 1;
-        double* cur = xs0;                                   // shared: x_k on all slots the computed rows reference
-        double* prev = xs1;                                  // shared: x_{k-1} on the computed rows -> x_{k+1}
-        double2 accb = narrow_solve_start<W>(slot, a.xg[gc], a.xg[gp], cur, prev, bsm, sP, hcol, s0, n_own, n_rows);
-        double2 accr = make_double2(0.0, 0.0);
-        double omega = 1.0;
-        int it = 1;                                          // next iteration to run: x_it -> x_{it+1}, it = 1 .. K-1
-        const int iters = K - 1;
-        auto next_omega = [&](int j) { omega = (j == 1) ? 1.0 / (1.0 - 0.5 * a.mu * a.mu) : 1.0 / (1.0 - 0.25 * a.mu * a.mu * omega); };
-        auto free_buf = [&](int skip) { for (int b = 0; b < 4; ++b) if (b != gc && b != gp && b != skip) return b; return 0; };
-        if (a.levels != 2 || (iters & 1)) {
-            // single iterations: all of them (one-level plan) or one to make the rest an even count
-            const int singles = (a.levels != 2) ? iters : 1;
-            for (int j = 0; j < singles; ++j, ++it) {
-                narrow_barrier(grid, a.barrier, bar_target);     // x_k of every CTA is published
-                narrow_load_halo<W>(a.xg[gc], cur, hcol, n_own, 0, n_h1);
-                __syncthreads();
-                next_omega(it);
-                const int f = free_buf(-1);
-                if (it == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, cur, prev, bsm, nullptr, a.X, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
-                else narrow_solve_iter<W, false>(slot, sx, cur, prev, bsm, a.xg[f], nullptr, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
-                gp = gc; gc = f;
-                double* tsw = cur; cur = prev; prev = tsw;
-            }
-        }
-        for (; it < K; it += 2) {
-            // two iterations per barrier: x_{k+1} on own + H1 (needs x_k on own + H1 + H2, x_{k-1} on own + H1), then x_{k+2} on own
-            narrow_barrier(grid, a.barrier, bar_target);
-            narrow_load_halo<W>(a.xg[gc], cur, hcol, n_own, 0, n_halo);
-            narrow_load_halo<W>(a.xg[gp], prev, hcol, n_own, 0, n_h1);
-            __syncthreads();
-            const int f0 = free_buf(-1), f1 = free_buf(f0);
-            next_omega(it);
-            narrow_solve_iter<W, false>(slot, sx, cur, prev, bsm, a.xg[f0], nullptr, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_rows);
-            __syncthreads();                                     // x_{k+1} on own + H1 complete in `prev`
-            next_omega(it + 1);
-            if (it + 1 == K - 1) accr = narrow_solve_iter<W, true>(slot, sx, prev, cur, bsm, nullptr, a.X, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
-            else narrow_solve_iter<W, false>(slot, sx, prev, cur, bsm, a.xg[f1], nullptr, omega, sv, ss, sP, scnt, ell_ld, s0, n_own, n_own);
-            gp = f0; gc = f1;                                    // cur holds x_{k+2} (own), prev x_{k+1} (own + H1): roles unchanged
-        }
-        // block sums of ||r||^2 and ||b||^2 per column (fixed order): shuffles over the groups of a warp, then the warps
-        {
-            double2 v[2] = {accr, accb};
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-#pragma unroll
-                for (int off = 16; off >= LPB; off >>= 1) {
-                    v[q].x += __shfl_xor_sync(0xffffffffu, v[q].x, off);
-                    v[q].y += __shfl_xor_sync(0xffffffffu, v[q].y, off);
-                }
-                if (lane < LPB) { sred[(q * kNWarps + warp) * W + 2 * l] = v[q].x; sred[(q * kNWarps + warp) * W + 2 * l + 1] = v[q].y; }
-            }
-            __syncthreads();
-            if (threadIdx.x < 2 * W) {
-                const int q = threadIdx.x / W, c = threadIdx.x % W;
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < kNWarps; ++w) s += sred[(q * kNWarps + w) * W + c];
-                a.partials[((size_t)blockIdx.x * 2 + q) * W + c] = s;
-            }
-        }
+        NTIM_ADD(5)
+        // ---- mass solve on the own rows of S: Chebyshev semi-iteration, K - 1 iterations behind x_1; halos travel through the
+        // flagged inboxes, no grid barrier inside
+#if KEXP_NARROW_TIMING
+        xid = narrow_solve<W, NP>(slot, step, xid, s_tim);
+        if (threadIdx.x == 0) s_tim[15] += a.kterm[step] - 1;
+        t0_ = clock64();
+#else
+        xid = narrow_solve<W, NP>(slot, step, xid);
+#endif
         narrow_barrier(grid, a.barrier, bar_target);           // x_K (in a.X), the edge rows of S_n and the block sums are visible
-        if (blockIdx.x == 0) narrow_check<W>(slot, sred + 2 * kNWarpsMax * W, K, a.rtol2[step], &s_bad);
-
+        NTIM_ADD(11)
+        if (blockIdx.x == 0) narrow_check<W>(slot, step, s_pairs, &s_bad);
         if (a.n_b > 0) {
-            narrow_phase_c<W>(slot, sx, rptr, r0, r1);
+            NTIM_ADD(12)
+            narrow_phase_c<W>(slot, step);
+            NTIM_ADD(13)
             narrow_barrier(grid, a.barrier, bar_target);       // S_n complete
+            NTIM_ADD(14)
         }
-        double* tsw = sx.Sin; sx.Sin = sx.Snew; sx.Snew = tsw;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {           // (CTA 0 wrote them itself: program order)
+        for (int k = 0; k < 4; ++k) a.pairs[k] = s_pairs[k];
+    }
+#if KEXP_NARROW_TIMING
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
+        printf("NTIM cta %3d W %d iters %lld | prod %lld upd %lld | A %lld barA %lld start %lld | recv %lld iter %lld | red %lld barK %lld chk %lld C %lld barC %lld | n_own %d n_h1 %d\n",
+               (int)blockIdx.x, W, s_tim[15], s_tim[1], s_tim[2], s_tim[4], s_tim[5], s_tim[6], s_tim[7], s_tim[9],
+               s_tim[10], s_tim[11], s_tim[12], s_tim[13], s_tim[14], (int)a.cap_s_rows, (int)a.cap_halo);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct NarrowCaps { int bpr, s_rows, kt_rows, r_rows, slots, halo; };
+struct NarrowCaps { int bpr, s_rows, kt_rows, r_rows, halo, send; };
 
 static void range_of(int nrows, int c, int G, int& start, int& end) {
     const int per = nrows / G, rem = nrows % G;
@@ -635,13 +844,13 @@ template <int W>
 static size_t narrow_smem_fixed(const NarrowCaps& c) {
     size_t b = sizeof(double) * 9 * (size_t)c.bpr * c.s_rows + sizeof(double) * 9 * (size_t)c.s_rows;
     b += sizeof(double) * (2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);
-    b += sizeof(int) * ((size_t)c.bpr * c.s_rows + c.s_rows + c.kt_rows + 1 + c.r_rows + 1 + c.halo);
+    b += sizeof(int) * ((size_t)c.bpr * c.s_rows + c.s_rows + 2 * (size_t)c.send + c.kt_rows + 1 + c.r_rows + 1);
     return (b + 15) & ~(size_t)15;
 }
 
 template <int W>
 static size_t narrow_smem(const NarrowCaps& c) {
-    return narrow_smem_fixed<W>(c) + sizeof(double) * 3 * W * ((size_t)2 * c.slots + c.s_rows);
+    return narrow_smem_fixed<W>(c) + sizeof(double) * NarrowCfg<W>::SS * ((size_t)2 * c.s_rows + c.halo);
 }
 
 __global__ void extract_block_cols_kernel(const double* __restrict__ blocks, int64_t nblocks, int* __restrict__ cols) {
@@ -649,93 +858,113 @@ __global__ void extract_block_cols_kernel(const double* __restrict__ blocks, int
         cols[i] = __double2loint(blocks[10 * i + 9]);
 }
 
-// Per-CTA local problems of S for a grid of G CTAs (see NarrowArgs).  levels = 1: the CTA computes its own rows, slots =
-// own | H1 (block columns referenced outside the own range, sorted).  levels = 2: it also computes the rows of H1
-// (redundantly), slots = own | H1 | H2 with H2 the columns referenced by H1 rows outside own + H1.  Built once per
-// operator and level count.
-static int build_narrow_plan(kexp_ctx* ctx, int G, int levels) {
-    NarrowPlanDev& P = ctx->narrow_plan[levels - 1];
+// Per-CTA local problems of S for a grid of G CTAs (see NarrowArgs): the CTA's own rows with shared-memory slot numbers,
+// its halo (block columns referenced outside the own range, sorted) and its send lists (which inbox slots of which CTAs
+// receive each own row).  Built once per operator.  Fails (-> multi-launch path) if the sparsity of S is not structurally
+// symmetric: the flag-in-data exchange relies on "I send to whoever sends to me".
+static int build_narrow_plan(kexp_ctx* ctx, int G) {
+    NarrowPlanDev& P = ctx->narrow_plan;
     if (P.G == G && P.lblocks) return 0;
+    if (P.G == -G) return 1;                                   // known not to be applicable
     const std::vector<int>& sb = ctx->As.h_browptr;
     const std::vector<double>& blk = ctx->As.h_blocks;
     if (sb.empty() || blk.empty()) return kexp::fail(ctx, "narrow apply: host copy of S not available");
     const int nbr = (int)sb.size() - 1;
     auto colof = [&](int k) { int64_t bits; memcpy(&bits, &blk[(size_t)k * 10 + 9], 8); return (int)bits; };
+    auto owner_of = [&](int row) {
+        const int per = nbr / G, rem = nbr % G;
+        const int cut = rem * (per + 1);
+        return row < cut ? row / (per + 1) : rem + (row - cut) / std::max(per, 1);
+    };
     std::vector<double> lb;
-    std::vector<int> lrow, cta_blk((size_t)G + 1, 0), cta_row((size_t)G + 1, 0), hptr((size_t)G + 1, 0), hcols, h1cnt((size_t)G, 0);
-    std::vector<int> h1, h2, rows;
+    std::vector<int> lrow, cta_blk((size_t)G + 1, 0), cta_row((size_t)G + 1, 0), hptr((size_t)G + 1, 0), hcols;
+    std::vector<std::vector<int>> halos((size_t)G);
     NarrowCaps caps{0, 0, 0, 0, 0, 0};
     for (int c = 0; c < G; ++c) {
         int r0, r1;
         range_of(nbr, c, G, r0, r1);
-        const int n_own = r1 - r0;
-        h1.clear(); h2.clear();
+        std::vector<int>& h1 = halos[c];
         for (int k = sb[r0]; k < sb[r1]; ++k) { const int col = colof(k); if (col < r0 || col >= r1) h1.push_back(col); }
         std::sort(h1.begin(), h1.end());
         h1.erase(std::unique(h1.begin(), h1.end()), h1.end());
-        if (levels == 2) {
-            for (int r : h1)
-                for (int k = sb[r]; k < sb[r + 1]; ++k) {
-                    const int col = colof(k);
-                    if ((col < r0 || col >= r1) && !std::binary_search(h1.begin(), h1.end(), col)) h2.push_back(col);
-                }
-            std::sort(h2.begin(), h2.end());
-            h2.erase(std::unique(h2.begin(), h2.end()), h2.end());
-        }
-        auto slot_of = [&](int col) -> int64_t {
-            if (col >= r0 && col < r1) return col - r0;
-            auto i1 = std::lower_bound(h1.begin(), h1.end(), col);
-            if (i1 != h1.end() && *i1 == col) return n_own + (i1 - h1.begin());
-            auto i2 = std::lower_bound(h2.begin(), h2.end(), col);
-            return n_own + (int64_t)h1.size() + (i2 - h2.begin());
-        };
-        rows.clear();
-        for (int r = r0; r < r1; ++r) rows.push_back(r);
-        if (levels == 2) rows.insert(rows.end(), h1.begin(), h1.end());
         const size_t blk0 = lb.size() / 10;
         lrow.push_back(0);
-        for (int r : rows) {
+        for (int r = r0; r < r1; ++r) {
             for (int k = sb[r]; k < sb[r + 1]; ++k) {
                 const size_t o = lb.size();
                 lb.insert(lb.end(), blk.begin() + (size_t)k * 10, blk.begin() + (size_t)k * 10 + 10);
-                const int64_t slot = slot_of(colof(k));
+                const int col = colof(k);
+                int64_t slot;
+                if (col >= r0 && col < r1) slot = col - r0;
+                else slot = -(int64_t)(std::lower_bound(h1.begin(), h1.end(), col) - h1.begin()) - 1;
                 memcpy(&lb[o + 9], &slot, 8);
             }
             lrow.push_back((int)(lb.size() / 10 - blk0));
+            caps.bpr = std::max(caps.bpr, sb[r + 1] - sb[r]);
         }
         cta_blk[c + 1] = (int)(lb.size() / 10);
         cta_row[c + 1] = (int)lrow.size();
         hcols.insert(hcols.end(), h1.begin(), h1.end());
-        hcols.insert(hcols.end(), h2.begin(), h2.end());
         hptr[c + 1] = (int)hcols.size();
-        h1cnt[c] = (int)h1.size();
-        for (int r : rows) caps.bpr = std::max(caps.bpr, sb[r + 1] - sb[r]);
-        caps.s_rows = std::max(caps.s_rows, (int)rows.size());
-        caps.slots = std::max(caps.slots, n_own + (int)h1.size() + (int)h2.size());
-        caps.halo = std::max(caps.halo, (int)(h1.size() + h2.size()));
+        caps.s_rows = std::max(caps.s_rows, r1 - r0);
+        caps.halo = std::max(caps.halo, (int)h1.size());
     }
-    cudaFree(P.lblocks); cudaFree(P.lrowptr); cudaFree(P.cta_blk_ptr); cudaFree(P.cta_row_ptr);
-    cudaFree(P.halo_ptr); cudaFree(P.halo_cols); cudaFree(P.halo1_cnt);
-    P = NarrowPlanDev();
+    // send lists: row `row` of CTA p goes to inbox slot hptr[c] + h of every CTA c with halos[c][h] == row
+    std::vector<std::vector<std::pair<int, int>>> sends((size_t)G);           // per producer: (local row, inbox slot)
+    std::vector<std::vector<int>> talks_to((size_t)G);
+    for (int c = 0; c < G; ++c)
+        for (size_t h = 0; h < halos[c].size(); ++h) {
+            const int row = halos[c][h], p = owner_of(row);
+            int p0, p1;
+            range_of(nbr, p, G, p0, p1);
+            if (row < p0 || row >= p1) return kexp::fail(ctx, "narrow apply: internal error (row owner)");
+            sends[p].push_back({row - p0, hptr[c] + (int)h});
+            talks_to[p].push_back(c);
+        }
+    bool symmetric = true;
+    for (int p = 0; p < G && symmetric; ++p) {
+        std::sort(talks_to[p].begin(), talks_to[p].end());
+        talks_to[p].erase(std::unique(talks_to[p].begin(), talks_to[p].end()), talks_to[p].end());
+    }
+    for (int p = 0; p < G && symmetric; ++p)
+        for (int c : talks_to[p])
+            if (!std::binary_search(talks_to[c].begin(), talks_to[c].end(), p)) { symmetric = false; break; }
+    if (!symmetric) { P.G = -G; return 1; }
+    std::vector<int> srow, cta_send((size_t)G + 1, 0), sdst;                  // per send entry: source row (local), inbox slot
+    for (int p = 0; p < G; ++p) {
+        std::sort(sends[p].begin(), sends[p].end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.second < y.second; });
+        for (const auto& e : sends[p]) { srow.push_back(e.first); sdst.push_back(e.second); }
+        cta_send[p + 1] = (int)sdst.size();
+        caps.send = std::max(caps.send, (int)sends[p].size());
+    }
+    free_narrow_plan(P);
     auto up = [&](auto** dst, const auto& v) -> bool {
         using T = std::remove_reference_t<decltype(**dst)>;
         if (cudaMalloc(dst, sizeof(T) * std::max<size_t>(v.size(), 1)) != cudaSuccess) return true;
         return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess;
     };
     if (up(&P.lblocks, lb) || up(&P.lrowptr, lrow) || up(&P.cta_blk_ptr, cta_blk) || up(&P.cta_row_ptr, cta_row) ||
-        up(&P.halo_ptr, hptr) || up(&P.halo_cols, hcols) || up(&P.halo1_cnt, h1cnt))
+        up(&P.halo_ptr, hptr) || up(&P.halo_cols, hcols) || up(&P.srowptr, srow) || up(&P.cta_send_ptr, cta_send) || up(&P.send_dst, sdst))
         return kexp::fail(ctx, "out of device memory for the narrow-apply plan");
-    P.G = G; P.cap_blocks = caps.bpr; P.cap_rows = caps.s_rows; P.cap_slots = caps.slots; P.cap_halo = caps.halo;
+    P.G = G; P.cap_blocks = caps.bpr; P.cap_rows = caps.s_rows; P.cap_halo = caps.halo; P.cap_send = caps.send;
+    P.inbox_slots = (int)hcols.size();
     return 0;
 }
 
-static bool narrow_caps(kexp_ctx* ctx, int G, int levels, NarrowCaps& c) {
+void free_narrow_plan(NarrowPlanDev& P) {
+    cudaFree(P.lblocks); cudaFree(P.lrowptr); cudaFree(P.cta_blk_ptr); cudaFree(P.cta_row_ptr);
+    cudaFree(P.halo_ptr); cudaFree(P.halo_cols); cudaFree(P.srowptr); cudaFree(P.cta_send_ptr); cudaFree(P.send_dst);
+    cudaFree(P.inbox);
+    P = NarrowPlanDev();
+}
+
+static bool narrow_caps(kexp_ctx* ctx, int G, NarrowCaps& c) {
     const std::vector<int>& kb = ctx->Kt.h_browptr;
     const std::vector<int>& rp = ctx->Rt.h_rowptr;
     if (ctx->As.h_browptr.empty() || kb.empty()) return false;
-    if (build_narrow_plan(ctx, G, levels)) return false;
-    const NarrowPlanDev& P = ctx->narrow_plan[levels - 1];
-    c = NarrowCaps{P.cap_blocks, P.cap_rows, 0, 0, P.cap_slots, P.cap_halo};
+    if (build_narrow_plan(ctx, G)) return false;
+    const NarrowPlanDev& P = ctx->narrow_plan;
+    c = NarrowCaps{P.cap_blocks, P.cap_rows, 0, 0, P.cap_halo, P.cap_send};
     for (int i = 0; i < G; ++i) {
         int a, b;
         range_of((int)kb.size() - 1, i, G, a, b);
@@ -748,9 +977,16 @@ static bool narrow_caps(kexp_ctx* ctx, int G, int levels, NarrowCaps& c) {
     return true;
 }
 
-template <int W>
+static int narrow_threads(int W) { return W == 2 ? NarrowCfg<2>::NT : NarrowCfg<4>::NT; }
+// passes of NT block rows a CTA needs for its own rows (one thread per block row; b of every pass lives in registers: 1 or 2)
+static int narrow_passes(int W, const NarrowCaps& c) {
+    const int nt = narrow_threads(W);
+    return (c.s_rows + nt - 1) / nt;
+}
+
+template <int W, int NP>
 static int launch_narrow_w(kexp_ctx* ctx, NarrowArgs& a, const NarrowCaps& caps) {
-    auto k = cheb_apply_narrow_kernel<W>;
+    auto k = cheb_apply_narrow_kernel<W, NP>;
     const size_t smem = narrow_smem<W>(caps);
     a.xs_offset = (int)(narrow_smem_fixed<W>(caps) / sizeof(double));
     static size_t attr_smem = 0;           // per instantiation
@@ -775,36 +1011,29 @@ static size_t narrow_smem_for(int W, const NarrowCaps& caps) {
         case 2: return narrow_smem<2>(caps);
         case 4: return narrow_smem<4>(caps);
         case 8: return narrow_smem<8>(caps);
-        case 16: return narrow_smem<16>(caps);
         default: return (size_t)1 << 40;
     }
 }
 
-// How many Chebyshev iterations per barrier a panel of width W can run (0: the persistent kernel is not applicable):
-// Chebyshev mass solve, both matrices in 3x3 blocks, and the CTA's local problem + iterate buffers within the shared memory
-// an SM offers.  Two iterations per barrier when the two-level problem fits (single-column panels at ref 5), else one.
-static int narrow_levels(kexp_ctx* ctx, int W) {
-    if (!ctx->use_narrow || W > ctx->narrow_max_w || W > 16) return 0;
-    if (ctx->solver != 1 || !ctx->Kt.bsr() || !ctx->As.bsr()) return 0;
-    if (ctx->n_b > 0 && (ctx->Rt.rowptr == nullptr)) return 0;
-    if (ctx->n % 3 || ctx->n_s % 3 || ctx->n_b % 3) return 0;
+// Is the persistent kernel applicable to a panel of width W?  Chebyshev mass solve, both matrices in 3x3 blocks, S
+// structurally symmetric, the CTA's local problem + iterate buffers within the shared memory an SM offers, at most two
+// passes over the own rows.
+bool narrow_eligible(kexp_ctx* ctx, int W) {
+    if (!ctx->use_narrow || W > ctx->narrow_max_w || W > 8) return false;
+    if (ctx->solver != 1 || !ctx->Kt.bsr() || !ctx->As.bsr()) return false;
+    if (ctx->n_b > 0 && (ctx->Rt.rowptr == nullptr)) return false;
+    if (ctx->n % 3 || ctx->n_s % 3 || ctx->n_b % 3) return false;
     const size_t limit = 227u * 1024u - 1024u;
-    for (int levels = std::min(2, ctx->narrow_sstep); levels >= 1; --levels) {
-        NarrowCaps caps;
-        if (!narrow_caps(ctx, ctx->num_sms, levels, caps)) return 0;
-        if (narrow_smem_for(W, caps) <= limit) return levels;
-    }
-    return 0;
+    NarrowCaps caps;
+    if (!narrow_caps(ctx, ctx->num_sms, caps)) return false;
+    return narrow_smem_for(W, caps) <= limit && narrow_passes(W, caps) <= 2;
 }
-
-bool narrow_eligible(kexp_ctx* ctx, int W) { return narrow_levels(ctx, W) > 0; }
 
 // Enqueue one whole apply of the panel held in ctx->S0 (mode 0: result in ctx->Y; mode 1: Clenshaw, result in the buffer
 // returned through *result).  kterm / rtol2: per-step iteration counts and squared tolerances (host, M+1 entries).
 int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm, const double* rtol2, bool with_basis, const double** result) {
-    const int levels = narrow_levels(ctx, W);
     NarrowCaps caps;
-    if (levels < 1 || !narrow_caps(ctx, ctx->num_sms, levels, caps)) return kexp::fail(ctx, "narrow apply: not applicable to this operator / width");
+    if (!narrow_eligible(ctx, W) || !narrow_caps(ctx, ctx->num_sms, caps)) return kexp::fail(ctx, "narrow apply: not applicable to this operator / width");
     if (M + 1 > kMaxTerms) return kexp::fail(ctx, "series too long");
     if (!ctx->d_nk) {
         KEXP_CUDA(cudaMalloc(&ctx->d_nk, sizeof(int) * kMaxTerms));
@@ -815,44 +1044,53 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
         KEXP_CUDA(cudaMalloc(&ctx->d_nktcols, sizeof(int) * (size_t)std::max<int64_t>(ctx->Kt.nblocks, 1)));
         extract_block_cols_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(ctx->Kt.blocks, ctx->Kt.nblocks, ctx->d_nktcols);
     }
-    // rotating publication buffers of the mass-solve iterates: n_s x 16 doubles each (the widest narrow panel)
-    if (!ctx->d_nxg) KEXP_CUDA(cudaMalloc(&ctx->d_nxg, sizeof(double) * 4 * 16 * (size_t)ctx->n_s));
+    NarrowPlanDev& P = ctx->narrow_plan;
+    // halo inboxes: two buffers of (all halo slots) x 3 x 8 flagged doubles (sized for the widest narrow panel), zeroed per launch
+    const size_t inbox_bytes = sizeof(uint4) * 2 * (size_t)std::max(P.inbox_slots, 1) * 3 * 8;
+    if (!P.inbox) KEXP_CUDA(cudaMalloc(&P.inbox, inbox_bytes));
+    KEXP_CUDA(cudaMemsetAsync(P.inbox, 0, sizeof(uint4) * 2 * (size_t)std::max(P.inbox_slots, 1) * 3 * W, ctx->stream));
     // pageable sources: the driver stages them before the call returns, so the host vectors may be reused at once
     KEXP_CUDA(cudaMemcpyAsync(ctx->d_nk, kterm, sizeof(int) * (size_t)(M + 1), cudaMemcpyHostToDevice, ctx->stream));
     KEXP_CUDA(cudaMemcpyAsync(ctx->d_nrtol2, rtol2, sizeof(double) * (size_t)(M + 1), cudaMemcpyHostToDevice, ctx->stream));
-    const NarrowPlanDev& P = ctx->narrow_plan[levels - 1];
     NarrowArgs a;
     a.kt_browptr = ctx->Kt.browptr; a.kt_blocks = ctx->Kt.blocks; a.kt_rowmap = ctx->Kt.rowmap; a.kt_nbr = ctx->Kt.nbr;
     a.kt_cols = ctx->d_nktcols;
     a.lblocks = P.lblocks; a.lrowptr = P.lrowptr; a.cta_blk_ptr = P.cta_blk_ptr; a.cta_row_ptr = P.cta_row_ptr;
-    a.halo_ptr = P.halo_ptr; a.halo_cols = P.halo_cols; a.halo1_cnt = P.halo1_cnt;
-    a.Pinv = ctx->d_Pinv; a.s_nbr = ctx->As.nbr; a.levels = levels;
+    a.halo_ptr = P.halo_ptr; a.halo_cols = P.halo_cols; a.srowptr = P.srowptr; a.cta_send_ptr = P.cta_send_ptr; a.send_dst = P.send_dst;
+    a.inbox = reinterpret_cast<uint4*>(P.inbox); a.inbox_slots = P.inbox_slots;
+    a.Pinv = ctx->d_Pinv; a.s_nbr = ctx->As.nbr;
     a.r_rowptr = ctx->Rt.rowptr; a.r_col = ctx->Rt.col; a.r_val = ctx->Rt.val; a.Dblk = ctx->d_Dblk;
     a.n = (int)ctx->n; a.n_s = (int)ctx->n_s; a.n_b = (int)ctx->n_b; a.n_d = (int)ctx->n_d;
     a.SA = ctx->S0; a.SB = ctx->S1; a.Y = ctx->Y; a.T = ctx->T; a.X = ctx->X;
-    for (int b = 0; b < 4; ++b) a.xg[b] = ctx->d_nxg + (size_t)b * 16 * ctx->n_s;
     a.tscale = ctx->d_tscale; a.coef = ctx->d_tscale + kMaxW; a.kterm = ctx->d_nk; a.rtol2 = ctx->d_nrtol2;
     a.M = M; a.mode = mode;
     a.basis = (mode == 1 || with_basis) ? ctx->d_basis : nullptr; a.basis_ld = ctx->basis_ld;
     a.alpha = 2.0 / (ctx->cheb_hi + ctx->cheb_lo);
     a.mu = (ctx->cheb_hi - ctx->cheb_lo) / (ctx->cheb_hi + ctx->cheb_lo);
+    a.omega[0] = 1.0;
+    for (int k = 1; k < kMaxOmega; ++k) a.omega[k] = (k == 1) ? 1.0 / (1.0 - 0.5 * a.mu * a.mu) : 1.0 / (1.0 - 0.25 * a.mu * a.mu * a.omega[k - 1]);
+    for (int n = 1; n <= M; ++n)
+        if (kterm[n] > kMaxOmega) return kexp::fail(ctx, "narrow apply: too many mass-solve iterations");
     a.sc = ctx->d_sc; a.partials = ctx->d_npartials;
     a.barrier = reinterpret_cast<unsigned*>(ctx->d_npartials + 2 * kMaxW * (size_t)ctx->num_sms);
+    a.pairs = ctx->d_npartials + 2 * kMaxW * (size_t)ctx->num_sms + 2;
     KEXP_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), ctx->stream));
     a.cap_bpr = caps.bpr; a.cap_s_rows = caps.s_rows; a.cap_kt_rows = caps.kt_rows; a.cap_r_rows = caps.r_rows;
-    a.cap_slots = caps.slots; a.cap_halo = caps.halo; a.xs_offset = 0;
+    a.cap_halo = caps.halo; a.cap_send = caps.send; a.xs_offset = 0;
+    const int np = narrow_passes(W, caps);
     int rc = 1;
-    switch (W) {
-        case 2: rc = launch_narrow_w<2>(ctx, a, caps); break;
-        case 4: rc = launch_narrow_w<4>(ctx, a, caps); break;
-        case 8: rc = launch_narrow_w<8>(ctx, a, caps); break;
-        case 16: rc = launch_narrow_w<16>(ctx, a, caps); break;
+    switch (W * 10 + np) {
+        case 21: rc = launch_narrow_w<2, 1>(ctx, a, caps); break;
+        case 22: rc = launch_narrow_w<2, 2>(ctx, a, caps); break;
+        case 41: rc = launch_narrow_w<4, 1>(ctx, a, caps); break;
+        case 42: rc = launch_narrow_w<4, 2>(ctx, a, caps); break;
+        case 81: rc = launch_narrow_w<8, 1>(ctx, a, caps); break;
         default: return kexp::fail(ctx, "narrow apply: unsupported panel width");
     }
     if (rc) return rc;
+    narrow_finish_kernel<<<1, 32, 0, ctx->stream>>>(a.pairs, ctx->d_sc);
     if (result) *result = (M % 2 == 0) ? ctx->S0 : ctx->S1;       // the buffer written by the last step
     ctx->solve_path = 3;
-    ctx->narrow_levels_used = levels;
     return 0;
 }
 

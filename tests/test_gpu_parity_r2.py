@@ -353,13 +353,12 @@ def test_async_mode_defers_the_check_not_the_error(sw2):
 # ------------------------------------------------------------------------------------------------
 # persistent narrow-panel apply kernel (kexp_narrow.cu) against the multi-launch path and the oracle
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("sstep", ["1", "2"])
 @pytest.mark.parametrize("B", [1, 3, 4, 7, 8])
-def test_narrow_kernel_equals_multi_launch_path(sw3, monkeypatch, B, sstep):
-    monkeypatch.setenv("KEXP_NARROW_MAXW", "8")           # ref 3: panels of up to 8 columns fit shared memory
-    monkeypatch.setenv("KEXP_NARROW_SSTEP", sstep)        # one / two Chebyshev iterations per grid barrier
-    """Same rows, same order of operations: the persistent kernel must reproduce the multi-launch path to round-off
-    (forward recurrence, shared-input basis run, fused Clenshaw average), with the same iteration counts."""
+def test_narrow_kernel_equals_multi_launch_path(sw3, monkeypatch, B):
+    monkeypatch.setenv("KEXP_NARROW_MAXW", "8")           # default: up to 4 columns (8 is slower than the multi-launch path at ref 5)
+    """Same rows, same order of operations: the persistent kernel (halo exchange through flagged inboxes instead of grid
+    barriers) must reproduce the multi-launch path to round-off (forward recurrence, shared-input basis run, fused Clenshaw
+    average), with the same iteration counts."""
     import krylov_exp_b200 as kx
     sw = sw3
     dt, rho = 3600.0, 1.0
@@ -413,11 +412,11 @@ def test_narrow_kernel_against_oracle(sw3, condense):
     op.close()
 
 
-@pytest.mark.parametrize("sstep", ["1", "2"])
-def test_narrow_kernel_ref5_columns_against_cpu_port(monkeypatch, sstep):
-    monkeypatch.setenv("KEXP_NARROW_SSTEP", sstep)
-    """A strong-scaling share of M1 (4 of the 64 samples, and the shared-input forward pass) through the persistent kernel
-    at full size."""
+@pytest.mark.parametrize("ncols", [4, 8])
+def test_narrow_kernel_ref5_columns_against_cpu_port(monkeypatch, ncols):
+    monkeypatch.setenv("KEXP_NARROW_MAXW", "8")
+    """A strong-scaling share of M1 (4 or 8 of the 64 samples, and the shared-input forward pass) through the persistent
+    kernel at full size."""
     import krylov_exp_b200 as kx
     from oracle import coeffs, norms
     from oracle.cpu_port import CpuCheby
@@ -428,7 +427,7 @@ def test_narrow_kernel_ref5_columns_against_cpu_port(monkeypatch, sstep):
     op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-11, max_it=40, solver="chebyshev")
     ce = kx.cheby_exp(op, None, None, 10000, 1e-8, L, spectral_radius=eig)
     t_all, w_all = kx.sample_times_weights(64, DT, RHO)
-    cols = np.arange(5, 64, 16)                            # 4 columns: the widest panel that fits shared memory at ref 5
+    cols = np.arange(5, 64, 64 // ncols)
     t = np.ascontiguousarray(t_all[cols])
     x, Xall = _m1_inputs(sw, 64)
     X = Xall[cols]
