@@ -720,7 +720,7 @@ KEXP_PHASE_FN void narrow_prologue(int slot) {
     constexpr int RPC = kNT / LPR;                     // scalar rows per CTA pass
     const NarrowSmem sm = narrow_smem_carve<W>(a);
     const int ell_ld = sm.ell_ld;
-    double* sv = sm.sv; double* sP = sm.sP; double* sred = sm.sred;
+    double* sv = sm.sv; double* sP = sm.sP;
     int* ss = sm.ss; int* scnt = sm.scnt; int* sptr = sm.sptr; int* sdst = sm.sdst; int* kptr = sm.kptr; int* rptr = sm.rptr;
 
     int s0, s1, k0r, k1r, r0, r1;
