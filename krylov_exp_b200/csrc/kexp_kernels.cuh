@@ -1091,6 +1091,8 @@ cheb_update_kernel(const double* __restrict__ src, const double* __restrict__ xs
                     double2 x[CH];
                     double a[CH];
 #pragma unroll
+                    for (int j = 0; j < CH; ++j) { x[j] = make_double2(0.0, 0.0); a[j] = 0.0; }      // defined on every path
+#pragma unroll
                     for (int j = 0; j < CH; ++j)
                         if (k + j < k1) {
                             a[j] = __ldg(val + k + j);
