@@ -270,6 +270,27 @@ int ensure_stage(kexp_ctx* ctx, size_t bytes) {
     return 0;
 }
 
+// staging buffer of the host uploads: used on the copy stream only, so that an upload never waits for work of the compute stream
+static int ensure_stage_up(kexp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->stage_up_bytes) return 0;
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->d_stage_up);
+    ctx->d_stage_up = nullptr; ctx->stage_up_bytes = 0;
+    KEXP_CUDA(cudaMalloc(&ctx->d_stage_up, bytes));
+    ctx->stage_up_bytes = bytes;
+    return 0;
+}
+
+// The scratch input batch of the host-pointer entry points is read by the apply / fused-average implementations only: they
+// record this event behind their last read, and the next upload into the batch waits for it instead of for everything the
+// compute stream holds (e.g. the forward half of an averaged evaluation, under which the backward inputs can then cross PCIe).
+static int mark_consumed(kexp_ctx* ctx, kexp_batch* in) {
+    if (in != ctx->tmp_in) return 0;
+    if (!in->ev_consumed) KEXP_CUDA(cudaEventCreateWithFlags(&in->ev_consumed, cudaEventDisableTiming));
+    KEXP_CUDA(cudaEventRecord(in->ev_consumed, ctx->stream));
+    return 0;
+}
+
 // Y = A X (MODE 0) or the CG product q = A p with the fused p.q reduction (MODE 1); BSR(3x3)
 // kernel when the matrix has that structure, generic CSR kernel otherwise.
 // Measured on the bench step (profiles/r01e_summary.md): 1 -> 5990, 2 -> 5810, 3 -> 5930, 4 -> 5590, 5 -> 5380 applications/s.
@@ -843,7 +864,7 @@ int kexp_destroy(kexp_ctx* ctx) {
     }
     free_csr(ctx->Kt); free_csr(ctx->As); free_csr(ctx->Rt);
     double* bufs[] = {ctx->S0, ctx->S1, ctx->Y, ctx->T, ctx->X, ctx->P, ctx->Q, ctx->d_Dblk, ctx->d_Pinv,
-                      ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_v, ctx->d_basis, ctx->d_D};
+                      ctx->d_partials, ctx->d_tscale, ctx->d_w, ctx->d_stage, ctx->d_stage_up, ctx->d_v, ctx->d_basis, ctx->d_D};
     for (double* b : bufs) cudaFree(b);
     cudaFree(ctx->d_perm); cudaFree(ctx->d_sc); cudaFree(ctx->d_counter);
     cudaFree(ctx->d_nk); cudaFree(ctx->d_nrtol2); cudaFree(ctx->d_npartials);
@@ -1096,6 +1117,7 @@ int kexp_batch_destroy(kexp_batch* b) {
     if (b->pending && b->ctx->copy_stream) cudaStreamSynchronize(b->ctx->copy_stream);
     for (double* p : b->panel) cudaFree(p);
     for (cudaEvent_t e : b->ready) cudaEventDestroy(e);
+    if (b->ev_consumed) cudaEventDestroy(b->ev_consumed);
     cudaFree(b->shared_vec);
     delete b;
     return 0;
@@ -1121,7 +1143,7 @@ static int batch_upload_impl(kexp_batch* b, const double* X, int64_t ldx, int x_
     const int nvec = x_is_shared ? 1 : b->B;
     if (!x_is_shared && ldx < ctx->n) return kexp::fail(ctx, "ldx < n");
     ctx->st_h2d_bytes += (int64_t)sizeof(double) * ctx->n * nvec;
-    if (ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * nvec)) return 1;
+    if (x_is_shared ? ensure_stage(ctx, sizeof(double) * (size_t)ctx->n * nvec) : ensure_stage_up(ctx, sizeof(double) * (size_t)ctx->n * nvec)) return 1;
     b->is_shared = x_is_shared != 0;
     if (finish_upload(b)) return 1;
     if (b->is_shared) {
@@ -1147,9 +1169,14 @@ static int batch_upload_impl(kexp_batch* b, const double* X, int64_t ldx, int x_
         KEXP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         b->ready.push_back(e);
     }
-    // the copy stream starts after whatever the compute stream still does with the staging buffer / the panels
-    KEXP_CUDA(cudaEventRecord(ctx->ev_prev, ctx->stream));
-    KEXP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prev, 0));
+    // the copy stream starts after whatever the compute stream still does with the panels: for the scratch batch of the
+    // host-pointer entry points that is its last apply (mark_consumed), for any other batch everything queued so far
+    if (b == ctx->tmp_in && b->ev_consumed) {
+        KEXP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, b->ev_consumed, 0));
+    } else {
+        KEXP_CUDA(cudaEventRecord(ctx->ev_prev, ctx->stream));
+        KEXP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prev, 0));
+    }
     cudaStream_t compute = ctx->stream;
     ctx->stream = ctx->copy_stream;                  // pack kernels of this upload run behind their copy
     int rc = 0;
@@ -1158,14 +1185,14 @@ static int batch_upload_impl(kexp_batch* b, const double* X, int64_t ldx, int x_
         const int ncols = std::min(b->panelW[p], b->B - col0);
         cudaError_t e = cudaSuccess;
         if (b->order.empty())
-            e = cudaMemcpy2DAsync(ctx->d_stage + (size_t)col0 * ctx->n, sizeof(double) * ctx->n, X + (size_t)col0 * ldx,
+            e = cudaMemcpy2DAsync(ctx->d_stage_up + (size_t)col0 * ctx->n, sizeof(double) * ctx->n, X + (size_t)col0 * ldx,
                                   sizeof(double) * ldx, sizeof(double) * ctx->n, ncols, cudaMemcpyHostToDevice, ctx->copy_stream);
         else
             for (int c = 0; c < ncols && e == cudaSuccess; ++c)
-                e = cudaMemcpyAsync(ctx->d_stage + (size_t)(col0 + c) * ctx->n, X + (size_t)b->order[col0 + c] * ldx,
+                e = cudaMemcpyAsync(ctx->d_stage_up + (size_t)(col0 + c) * ctx->n, X + (size_t)b->order[col0 + c] * ldx,
                                     sizeof(double) * ctx->n, cudaMemcpyHostToDevice, ctx->copy_stream);
         if (e != cudaSuccess) { rc = kexp::fail(ctx, cudaGetErrorString(e)); break; }
-        rc = pack_panel(ctx, ctx->d_stage, ctx->n, 0, b->B, col0, b->panelW[p], b->panel[p]);
+        rc = pack_panel(ctx, ctx->d_stage_up, ctx->n, 0, b->B, col0, b->panelW[p], b->panel[p]);
         if (!rc && cudaEventRecord(b->ready[p], ctx->copy_stream) != cudaSuccess) rc = kexp::fail(ctx, "event record failed");
     }
     ctx->stream = compute;
@@ -1711,7 +1738,7 @@ static int cheby_average_fused_impl(kexp_ctx* ctx, int id, kexp_batch* in, const
     if (colsum_panel(ctx, res, one, 0, 2, 2, v_dev, 0)) return 1;
     KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
     KEXP_CUDA(cudaGetLastError());
-    return 0;
+    return mark_consumed(ctx, in);
 }
 
 static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batch* out, const double* t, bool time_it) {
@@ -1758,7 +1785,7 @@ static int cheby_apply_dev_impl(kexp_ctx* ctx, int id, kexp_batch* in, kexp_batc
     if (swap_lane(ctx, 0)) return 1;
     if (time_it) KEXP_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
     (void)maxW;
-    return 0;
+    return mark_consumed(ctx, in);
 }
 
 // The CG loop inside the graph has a fixed number of early-exit iterations.  After the

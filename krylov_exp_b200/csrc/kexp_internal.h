@@ -209,6 +209,8 @@ struct kexp_ctx {
     int panel_cap = 64;            // widest panel a new batch gets (32 with two lanes)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prev = nullptr;
     cudaStream_t copy_stream = nullptr;   // host->device uploads overlap the compute of the previous panel
+    double* d_stage_up = nullptr;         // landing area of host->device uploads (copy stream only; d_stage belongs to the compute stream)
+    size_t stage_up_bytes = 0;
     // asynchronous downloads (kexp_batch_download_async): own staging buffer and stream
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t ev_unpacked = nullptr, ev_d2h_done = nullptr;
@@ -235,6 +237,7 @@ struct kexp_batch {
     bool is_shared = false;
     std::vector<cudaEvent_t> ready;   // per panel: upload + pack finished (copy stream)
     bool pending = false;          // an asynchronous upload may still be in flight
+    cudaEvent_t ev_consumed = nullptr;   // scratch input batch of the host-pointer entry points: the last apply has read the panels
     // stored column j holds the caller's column order[j] (empty = identity).  Sorting the columns by |t_k|
     // groups sample times of similar economised series length into the same panel.
     std::vector<int> order;
