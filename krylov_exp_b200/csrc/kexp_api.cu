@@ -822,6 +822,7 @@ int kexp_create(kexp_ctx** out, int device) {
     if (ln && ln[0] == '2') { ctx->nlanes = 2; ctx->panel_cap = 32; }
     if (const char* fz = getenv("KEXP_FUSED_UPDATE")) ctx->use_fused_update = (fz[0] != '0');
     if (const char* nw = getenv("KEXP_NARROW")) ctx->use_narrow = (nw[0] != '0');
+    if (const char* nr = getenv("KEXP_NARROW_MREG")) ctx->narrow_mreg = (nr[0] != '0');
     if (const char* nm = getenv("KEXP_NARROW_MAXW")) { const int v = atoi(nm); if (v >= 2 && v <= 8) ctx->narrow_max_w = v; }
     const char* rl = getenv("KEXP_RELAX");
     if (rl) ctx->use_relax = (rl[0] == '1');

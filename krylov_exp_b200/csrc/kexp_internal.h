@@ -135,6 +135,7 @@ struct kexp_ctx {
     bool use_narrow = true;        // KEXP_NARROW=0: always the multi-launch path
     int narrow_max_w = 4;          // widest panel that takes it (KEXP_NARROW_MAXW, up to 8).  8-column panels: 5.5 ms against 4.2 ms for the
                                    // multi-launch path at ref 5 (the K~ product of the persistent kernel is the slow part); 4 columns: a tie
+    bool narrow_mreg = true;       // panels of up to 4 columns keep their rows of S in registers (KEXP_NARROW_MREG=0: shared memory)
     int narrow_slot = 0;           // constant-memory argument slot of this context
     kexp::NarrowPlanDev narrow_plan;      // per-CTA local problems of S, halos and send lists (kexp_narrow.cu: build_narrow_plan)
     int* d_nktcols = nullptr;      // block columns of K~

@@ -39,15 +39,14 @@ namespace cg = cooperative_groups;
 namespace kexp {
 
 template <int W> struct NarrowCfg {
-    // 1 CTA per SM.  W >= 4: 256 threads, up to 255 registers each -- the mass solve keeps a whole block row (3 rows x W
-    // columns) of b, S x and the new iterate in one thread's registers.  W = 2: 384 threads (168 registers; the extra warps
-    // help the K~ product and the halo exchange, the solve itself needs one thread per block row)
-    static constexpr int NT = (W == 2) ? 384 : 256;
+    // 1 CTA per SM, 256 threads, up to 255 registers each -- the mass solve keeps a whole block row (3 rows x W columns) of
+    // b, S x and the new iterate in one thread's registers, for W <= 4 also the row of the matrix
+    static constexpr int NT = 256;
     static constexpr int GK = (W == 2) ? 4 : 8;      // gathered blocks of K~ in flight per row
     static constexpr int SS = 3 * W + (W >= 4 ? 2 : 0);   // doubles per block-row slot of the shared-memory iterates (padded: the
                                                      // lanes of a warp read different slots; 3W doubles apart they would share banks)
 };
-constexpr int kNTmax = 384;
+constexpr int kNTmax = 256;
 constexpr int kNWarpsMax = kNTmax / 32;
 constexpr int kMaxOmega = 96;            // most Chebyshev iterations of one mass solve in the persistent kernel
 constexpr int kRChunk = 9;               // nonzeros of a row of R in flight (interior dof x the 9 edge dofs of its cell)
@@ -432,9 +431,12 @@ __device__ __forceinline__ void narrow_send(uint4* __restrict__ inbox_par, const
 // The whole Chebyshev semi-iteration of one term on the CTA's own rows:  x_1 = alpha P^-1 b, then K - 1 iterations
 //   x_{k+1} = x_{k-1} + omega_k (x_k + alpha P^-1 (b - S x_k) - x_{k-1});
 // the last one also forms ||b - S x_{K-1}||^2, writes x_K to a.X and applies the recurrence update of the edge rows.
-// One thread per block row (NP passes of NT rows), all W columns of the row in its registers.
+// One thread per block row (NP passes of NT rows), all W columns of the row in its registers.  MREG (one pass, at most 5
+// blocks per row, W <= 4): the thread's matrix row -- 5 blocks of S and its block of P^-1, 54 doubles -- stays in registers
+// for the whole solve as well: at W = 2 the matrix is 60 % of the shared-memory wavefronts of an iteration (75 KB per CTA
+// at ref 5 against 50 KB of x), and the iteration is bound by exactly those.
 // Leaves the block sums of ||r||^2 and ||b||^2 per column in a.partials.  Returns the next exchange number.
-template <int W, int NP>
+template <int W, int NP, bool MREG>
 KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
 #if KEXP_NARROW_TIMING
                                     , long long* s_tim
@@ -458,6 +460,30 @@ KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
     double2 bv[NP][3][NV];
     double* cur = sm.xo0;                               // x_k on the own rows
     double* prev = sm.xo1;                              // x_{k-1} on the own rows -> x_{k+1}
+    constexpr int kRegBlocks = MREG ? 5 : 1;
+    double mreg[kRegBlocks][9], preg[9];
+    int sreg[kRegBlocks];
+#pragma unroll
+    for (int q = 0; q < kRegBlocks; ++q) {              // (defined on every path)
+        sreg[q] = 0;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) mreg[q][e] = 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) preg[e] = 0.0;
+    if (MREG && (int)threadIdx.x < n_own) {
+        const int lr = threadIdx.x;
+        const int nq = sm.scnt[lr];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const bool have = q < nq;                    // shorter rows: zero blocks on the row's own slot
+            sreg[q] = have ? sm.ss[q * ell_ld + lr] : lr;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) mreg[q][e] = have ? sm.sv[(size_t)(9 * q + e) * ell_ld + lr] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 9; ++e) preg[e] = sm.sP[e * ell_ld + lr];
+    }
     NTIM_T0
     // ---- start: b <- T (global), x_1 = alpha P^-1 b, x_0 = 0
     double accb[W];
@@ -478,7 +504,7 @@ KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
                 }
             double P[3][3];
 #pragma unroll
-            for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = sm.sP[e * ell_ld + lr];
+            for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = MREG ? preg[e] : sm.sP[e * ell_ld + lr];
             double2 z[3][NV];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -518,13 +544,16 @@ KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
         for (int p = 0; p < NP; ++p) {
             const int lr = p * NT + threadIdx.x;
             if (lr < n_own) {
-                const int nq = sm.scnt[lr];
+                const int nq = MREG ? 5 : sm.scnt[lr];
                 double2 acc[3][NV];
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
                     for (int v = 0; v < NV; ++v) acc[i][v] = make_double2(0.0, 0.0);
-                if (W <= 4 && nq == 5) {                 // BDM2 edge rows: the edge and the four other edges of its two cells
+                if (MREG) {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) narrow_block_apply<W>(mreg[q], sreg[q], cur, sm.xh, acc);
+                } else if (W <= 4 && nq == 5) {          // BDM2 edge rows: the edge and the four other edges of its two cells
 #pragma unroll
                     for (int q = 0; q < 5; ++q) narrow_block_fma<W>(sm.sv, sm.ss, ell_ld, lr, q, cur, sm.xh, acc);
                 } else {                                        // (8 columns: one block's 72 products at a time fill the registers)
@@ -534,7 +563,7 @@ KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
                 NTIM_ADD(1)
                 double P[3][3];
 #pragma unroll
-                for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = sm.sP[e * ell_ld + lr];
+                for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = MREG ? preg[e] : sm.sP[e * ell_ld + lr];
                 // acc <- r = b - S x_k
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
@@ -776,7 +805,7 @@ KEXP_PHASE_FN void narrow_prologue(int slot) {
     }
 }
 
-template <int W, int NP>
+template <int W, int NP, bool MREG>
 __global__ void __launch_bounds__(NarrowCfg<W>::NT, 1)
 cheb_apply_narrow_kernel(const int slot) {
     const NarrowArgs& a = c_nargs[slot];
@@ -802,11 +831,11 @@ cheb_apply_narrow_kernel(const int slot) {
         // ---- mass solve on the own rows of S: Chebyshev semi-iteration, K - 1 iterations behind x_1; halos travel through the
         // flagged inboxes, no grid barrier inside
 #if KEXP_NARROW_TIMING
-        xid = narrow_solve<W, NP>(slot, step, xid, s_tim);
+        xid = narrow_solve<W, NP, MREG>(slot, step, xid, s_tim);
         if (threadIdx.x == 0) s_tim[15] += a.kterm[step] - 1;
         t0_ = clock64();
 #else
-        xid = narrow_solve<W, NP>(slot, step, xid);
+        xid = narrow_solve<W, NP, MREG>(slot, step, xid);
 #endif
         narrow_barrier(grid, a.barrier, bar_target);           // x_K (in a.X), the edge rows of S_n and the block sums are visible
         NTIM_ADD(11)
@@ -984,9 +1013,9 @@ static int narrow_passes(int W, const NarrowCaps& c) {
     return (c.s_rows + nt - 1) / nt;
 }
 
-template <int W, int NP>
+template <int W, int NP, bool MREG>
 static int launch_narrow_w(kexp_ctx* ctx, NarrowArgs& a, const NarrowCaps& caps) {
-    auto k = cheb_apply_narrow_kernel<W, NP>;
+    auto k = cheb_apply_narrow_kernel<W, NP, MREG>;
     const size_t smem = narrow_smem<W>(caps);
     a.xs_offset = (int)(narrow_smem_fixed<W>(caps) / sizeof(double));
     static size_t attr_smem = 0;           // per instantiation
@@ -1078,13 +1107,16 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     a.cap_bpr = caps.bpr; a.cap_s_rows = caps.s_rows; a.cap_kt_rows = caps.kt_rows; a.cap_r_rows = caps.r_rows;
     a.cap_halo = caps.halo; a.cap_send = caps.send; a.xs_offset = 0;
     const int np = narrow_passes(W, caps);
+    const bool mreg = ctx->narrow_mreg && np == 1 && caps.bpr <= 5 && W <= 4;      // matrix rows in registers
     int rc = 1;
-    switch (W * 10 + np) {
-        case 21: rc = launch_narrow_w<2, 1>(ctx, a, caps); break;
-        case 22: rc = launch_narrow_w<2, 2>(ctx, a, caps); break;
-        case 41: rc = launch_narrow_w<4, 1>(ctx, a, caps); break;
-        case 42: rc = launch_narrow_w<4, 2>(ctx, a, caps); break;
-        case 81: rc = launch_narrow_w<8, 1>(ctx, a, caps); break;
+    switch (W * 100 + np * 10 + (mreg ? 1 : 0)) {
+        case 211: rc = launch_narrow_w<2, 1, true>(ctx, a, caps); break;
+        case 210: rc = launch_narrow_w<2, 1, false>(ctx, a, caps); break;
+        case 220: rc = launch_narrow_w<2, 2, false>(ctx, a, caps); break;
+        case 411: rc = launch_narrow_w<4, 1, true>(ctx, a, caps); break;
+        case 410: rc = launch_narrow_w<4, 1, false>(ctx, a, caps); break;
+        case 420: rc = launch_narrow_w<4, 2, false>(ctx, a, caps); break;
+        case 810: rc = launch_narrow_w<8, 1, false>(ctx, a, caps); break;
         default: return kexp::fail(ctx, "narrow apply: unsupported panel width");
     }
     if (rc) return rc;
