@@ -42,14 +42,14 @@ def _m1_inputs(sw, B, seed=1234):
 # (a) per-iteration mass-solve path and the other environment-switched variants
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env,path", [({"KEXP_COOP": "0", "KEXP_NARROW": "0"}, 1), ({"KEXP_COOP": "0", "KEXP_NO_GRAPH": "1", "KEXP_NARROW": "0"}, 1),
-                                      ({"KEXP_NARROW": "0"}, 2), ({"KEXP_NARROW_MAXW": "8"}, 3),
+                                      ({"KEXP_NARROW": "0"}, 2), ({"KEXP_NARROW_MAXW": "8"}, 3), ({"KEXP_NARROW_MREG": "0"}, 3), ({"KEXP_NARROW_MAXW": "2"}, 3),
                                       ({"KEXP_FUSED_UPDATE": "1", "KEXP_NARROW": "0"}, 2), ({"KEXP_FUSED_UPDATE": "1", "KEXP_COOP": "0", "KEXP_NARROW": "0"}, 1),
                                       ({"KEXP_LANES": "2"}, None), ({"KEXP_PANEL_CAP": "16"}, None),
                                       ({"KEXP_RELAX": "0", "KEXP_PDL": "0"}, None)])
 def test_switched_variants_ref3_against_oracle(sw3, monkeypatch, env, path):
     import krylov_exp_b200 as kx
     from oracle import coeffs, cheby_ref
-    for k in ("KEXP_COOP", "KEXP_NO_GRAPH", "KEXP_LANES", "KEXP_PANEL_CAP", "KEXP_RELAX", "KEXP_PDL", "KEXP_NARROW", "KEXP_NARROW_MAXW",
+    for k in ("KEXP_COOP", "KEXP_NO_GRAPH", "KEXP_LANES", "KEXP_PANEL_CAP", "KEXP_RELAX", "KEXP_PDL", "KEXP_NARROW", "KEXP_NARROW_MAXW", "KEXP_NARROW_MREG",
               "KEXP_FUSED_UPDATE"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
