@@ -78,6 +78,7 @@ struct KrylovState;               // kexp_krylov.cu
 struct NarrowPlanDev {
     double* lblocks = nullptr; int* lrowptr = nullptr; int* cta_blk_ptr = nullptr; int* cta_row_ptr = nullptr;
     int* halo_ptr = nullptr; int* halo_cols = nullptr; int* srowptr = nullptr; int* cta_send_ptr = nullptr; int* send_dst = nullptr;
+    int* grow = nullptr; int* cta_nb = nullptr;    // local row order of every CTA (rows that reference halo slots first)
     void* inbox = nullptr;         // flagged halo inboxes (two buffers)
     int G = 0;                     // grid the plan was built for (< 0: built and found not applicable)
     int cap_blocks = 0, cap_rows = 0, cap_halo = 0, cap_send = 0, inbox_slots = 0;

@@ -60,6 +60,9 @@ struct NarrowArgs {
     // cta_send_ptr[c+1]): local source row and inbox slot (global numbering: halo_ptr[consumer] + its halo slot), sorted by slot
     const double* lblocks; const int* lrowptr; const int* cta_blk_ptr; const int* cta_row_ptr;
     const int* halo_ptr; const int* halo_cols; const int* srowptr; const int* cta_send_ptr; const int* send_dst;
+    // local row order of a CTA: the rows that reference a halo slot first (cta_nb[c] of them), then the rows that need only
+    // the CTA's own x; grow[s0 + lr] = global block row of local row lr (a permutation inside the CTA's range)
+    const int* grow; const int* cta_nb;
     uint4* inbox; int inbox_slots;                           // two buffers of inbox_slots x 3W flagged doubles (zeroed before the launch)
     const double* Pinv; int s_nbr;
     const int* kt_cols;                                      // block columns of K~ (global copy of the 10th doubles)
@@ -217,6 +220,7 @@ __device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& s
 struct NarrowSmem {
     double *sv, *sP, *sred;                       // S values (transposed: [9 * bpr][ell_ld]), block-Jacobi inverses (transposed: [9][ell_ld]), reduction scratch
     int *ss, *scnt, *sptr, *sdst, *kptr, *rptr;   // column slots ([bpr][ell_ld]), blocks per row, send entries (source row, inbox slot), row pointers of K~ and R
+    int *sgrow;                                   // global block row of every local row
     double *xo0, *xo1, *xh;                       // iterates on the own rows (two), halo of the current iterate
     int ell_ld;
 };
@@ -234,6 +238,7 @@ __device__ __forceinline__ NarrowSmem narrow_smem_carve(const NarrowArgs& a) {
     m.sdst = m.sptr + a.cap_send;
     m.kptr = m.sdst + a.cap_send;
     m.rptr = m.kptr + a.cap_kt_rows + 1;
+    m.sgrow = m.rptr + a.cap_r_rows + 1;
     m.xo0 = reinterpret_cast<double*>(smem2) + a.xs_offset;                    // 16-byte aligned
     m.xo1 = m.xo0 + (size_t)NarrowCfg<W>::SS * a.cap_s_rows;
     m.xh = m.xo1 + (size_t)NarrowCfg<W>::SS * a.cap_s_rows;
@@ -493,7 +498,7 @@ KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
     for (int p = 0; p < NP; ++p) {
         const int lr = p * NT + threadIdx.x;
         if (lr < n_own) {
-            const size_t o = (size_t)(3 * (s0 + lr)) * W;
+            const size_t o = (size_t)(3 * sm.sgrow[lr]) * W;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -527,87 +532,100 @@ KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
         if (lane == 0) sm.sred[(1 * kNWarps + warp) * W + c] = accb[c];
     }
     NTIM_ADD(6)
+    // The rows of the CTA are ordered: the nb rows that reference a halo slot first, then the rows that need only the CTA's
+    // own x_k.  For W = 2 the latter are computed BEFORE the halo of x_k is waited for: their work (1.2 k cycles) hides in the
+    // latency of the exchange (the neighbours' values were sent one __syncthreads ago and need ~1.9 k cycles to be seen).
+    // Wider panels keep the plain order: their own-row work is longer than the latency and would only delay the threads'
+    // share of the polling (measured at W = 4: 2.78 against 2.60 ms per apply).
+    constexpr bool kOverlap = (W == 2);
+    const int nb = __ldg(a.cta_nb + blockIdx.x);
     for (int it = 1; it < K; ++it) {
-        // halo of x_it (exchange xid); the halo array is free: every thread has finished the previous iteration (the barrier
-        // in front of its sends)
-        ll_recv<NT, 3 * W, SS>(my_inbox + (size_t)(xid & 1u) * inbox_half, sm.xh, ne, xid);
-        __syncthreads();                                // own rows (written by the previous iteration / the start) and halo of x_it complete
-        NTIM_ADD(7)
-        ++xid;
         const double omega = a.omega[it];
         const bool last = (it == K - 1);
-        uint4* out_inbox = a.inbox + (size_t)(xid & 1u) * inbox_half;
         double accr[W];                                     // ||b - S x_k||^2 per column: formed by the last iteration only
 #pragma unroll
         for (int c = 0; c < W; ++c) accr[c] = 0.0;
+        // x_{it+1} on the rows of one class (halo_rows: the rows that reference halo slots / the others)
+        auto rows = [&](const bool halo_rows) {
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            const int lr = p * NT + threadIdx.x;
-            if (lr < n_own) {
-                const int nq = MREG ? 5 : sm.scnt[lr];
-                double2 acc[3][NV];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) acc[i][v] = make_double2(0.0, 0.0);
-                if (MREG) {
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) narrow_block_apply<W>(mreg[q], sreg[q], cur, sm.xh, acc);
-                } else if (W <= 4 && nq == 5) {          // BDM2 edge rows: the edge and the four other edges of its two cells
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) narrow_block_fma<W>(sm.sv, sm.ss, ell_ld, lr, q, cur, sm.xh, acc);
-                } else {                                        // (8 columns: one block's 72 products at a time fill the registers)
-#pragma unroll 1
-                    for (int q = 0; q < nq; ++q) narrow_block_fma<W>(sm.sv, sm.ss, ell_ld, lr, q, cur, sm.xh, acc);
-                }
-                NTIM_ADD(1)
-                double P[3][3];
-#pragma unroll
-                for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = MREG ? preg[e] : sm.sP[e * ell_ld + lr];
-                // acc <- r = b - S x_k
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        acc[i][v].x = bv[p][i][v].x - acc[i][v].x; acc[i][v].y = bv[p][i][v].y - acc[i][v].y;
-                        if (last) {
-                            accr[2 * v] = fma(acc[i][v].x, acc[i][v].x, accr[2 * v]);
-                            accr[2 * v + 1] = fma(acc[i][v].y, acc[i][v].y, accr[2 * v + 1]);
-                        }
-                    }
-                double2 xn[3][NV];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        const double2 xo = *reinterpret_cast<const double2*>(cur + lr * SS + i * W + 2 * v);
-                        const double2 xmv = *reinterpret_cast<const double2*>(prev + lr * SS + i * W + 2 * v);
-                        double2 z;
-                        z.x = fma(P[i][0], acc[0][v].x, fma(P[i][1], acc[1][v].x, P[i][2] * acc[2][v].x));
-                        z.y = fma(P[i][0], acc[0][v].y, fma(P[i][1], acc[1][v].y, P[i][2] * acc[2][v].y));
-                        xn[i][v].x = fma(omega, fma(a.alpha, z.x, xo.x) - xmv.x, xmv.x);
-                        xn[i][v].y = fma(omega, fma(a.alpha, z.y, xo.y) - xmv.y, xmv.y);
-                    }
-                NTIM_ADD(2)
-                if (!last) {
+            for (int p = 0; p < NP; ++p) {
+                const int lr = p * NT + threadIdx.x;
+                if (lr < n_own && (lr < nb) == halo_rows) {
+                    const int nq = MREG ? 5 : sm.scnt[lr];
+                    double2 acc[3][NV];
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) *reinterpret_cast<double2*>(prev + lr * SS + i * W + 2 * v) = xn[i][v];
-                } else {
-                    const size_t o = (size_t)(3 * (s0 + lr)) * W;
+                        for (int v = 0; v < NV; ++v) acc[i][v] = make_double2(0.0, 0.0);
+                    if (MREG) {
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        const UpdCtx u = make_upd<W>(a, sx, v);
+                        for (int q = 0; q < 5; ++q) narrow_block_apply<W>(mreg[q], sreg[q], cur, sm.xh, acc);
+                    } else if (W <= 4 && nq == 5) {          // BDM2 edge rows: the edge and the four other edges of its two cells
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            *reinterpret_cast<double2*>(a.X + o + (size_t)i * W + 2 * v) = xn[i][v];
-                            row_update(u, o + (size_t)i * W + 2 * v, (size_t)(3 * (s0 + lr) + i), xn[i][v]);     // edge rows: W = x_K
+                        for (int q = 0; q < 5; ++q) narrow_block_fma<W>(sm.sv, sm.ss, ell_ld, lr, q, cur, sm.xh, acc);
+                    } else {                                 // (8 columns: one block's 72 products at a time fill the registers)
+#pragma unroll 1
+                        for (int q = 0; q < nq; ++q) narrow_block_fma<W>(sm.sv, sm.ss, ell_ld, lr, q, cur, sm.xh, acc);
+                    }
+                    double P[3][3];
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) P[e / 3][e % 3] = MREG ? preg[e] : sm.sP[e * ell_ld + lr];
+                    // acc <- r = b - S x_k
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            acc[i][v].x = bv[p][i][v].x - acc[i][v].x; acc[i][v].y = bv[p][i][v].y - acc[i][v].y;
+                            if (last) {
+                                accr[2 * v] = fma(acc[i][v].x, acc[i][v].x, accr[2 * v]);
+                                accr[2 * v + 1] = fma(acc[i][v].y, acc[i][v].y, accr[2 * v + 1]);
+                            }
+                        }
+                    double2 xn[3][NV];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const double2 xo = *reinterpret_cast<const double2*>(cur + lr * SS + i * W + 2 * v);
+                            const double2 xmv = *reinterpret_cast<const double2*>(prev + lr * SS + i * W + 2 * v);
+                            double2 z;
+                            z.x = fma(P[i][0], acc[0][v].x, fma(P[i][1], acc[1][v].x, P[i][2] * acc[2][v].x));
+                            z.y = fma(P[i][0], acc[0][v].y, fma(P[i][1], acc[1][v].y, P[i][2] * acc[2][v].y));
+                            xn[i][v].x = fma(omega, fma(a.alpha, z.x, xo.x) - xmv.x, xmv.x);
+                            xn[i][v].y = fma(omega, fma(a.alpha, z.y, xo.y) - xmv.y, xmv.y);
+                        }
+                    if (!last) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) *reinterpret_cast<double2*>(prev + lr * SS + i * W + 2 * v) = xn[i][v];
+                    } else {
+                        const int gr = sm.sgrow[lr];
+                        const size_t o = (size_t)(3 * gr) * W;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const UpdCtx u = make_upd<W>(a, sx, v);
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                *reinterpret_cast<double2*>(a.X + o + (size_t)i * W + 2 * v) = xn[i][v];
+                                row_update(u, o + (size_t)i * W + 2 * v, (size_t)(3 * gr + i), xn[i][v]);     // edge rows: W = x_K
+                            }
                         }
                     }
                 }
             }
-        }
+        };
+        if (kOverlap) rows(false);                      // needs the own rows of x_it only (complete: barrier of the last send)
+        NTIM_ADD(1)
+        // halo of x_it (exchange xid); the halo array is free: every thread has finished the halo rows of the previous
+        // iteration (the barrier in front of its sends)
+        ll_recv<NT, 3 * W, SS>(my_inbox + (size_t)(xid & 1u) * inbox_half, sm.xh, ne, xid);
+        __syncthreads();
+        NTIM_ADD(7)
+        ++xid;
+        rows(true);
+        if (!kOverlap) rows(false);
+        NTIM_ADD(2)
         if (last) {
 #pragma unroll
             for (int c = 0; c < W; ++c) {
@@ -619,7 +637,7 @@ KEXP_PHASE_FN unsigned narrow_solve(int slot, int step, unsigned xid
         NTIM_ADD(9)
         if (!last) {
             __syncthreads();                            // x_{it+1} on the own rows complete (and nobody reads the halo of x_it any more)
-            narrow_send<NT, 3 * W, SS>(out_inbox, sm.sptr, sm.sdst, nsend, prev, xid);
+            narrow_send<NT, 3 * W, SS>(a.inbox + (size_t)(xid & 1u) * inbox_half, sm.sptr, sm.sdst, nsend, prev, xid);
         }
         NTIM_ADD(3)
         double* tsw = cur; cur = prev; prev = tsw;
@@ -776,7 +794,9 @@ KEXP_PHASE_FN void narrow_prologue(int slot) {
                 ss[(q - q0) * ell_ld + lr] = __double2loint(__ldg(bp + 9));
             }
         }
-        for (int i = threadIdx.x; i < 9 * n_own; i += kNT) sP[(i % 9) * ell_ld + i / 9] = __ldg(a.Pinv + (size_t)9 * s0 + i);
+        for (int i = threadIdx.x; i < n_own; i += kNT) sm.sgrow[i] = __ldg(a.grow + s0 + i);
+        for (int i = threadIdx.x; i < 9 * n_own; i += kNT)
+            sP[(i % 9) * ell_ld + i / 9] = __ldg(a.Pinv + (size_t)9 * __ldg(a.grow + s0 + i / 9) + i % 9);
         const int sd0 = __ldg(a.cta_send_ptr + blockIdx.x), nsd = __ldg(a.cta_send_ptr + blockIdx.x + 1) - sd0;
         for (int i = threadIdx.x; i < nsd; i += kNT) { sptr[i] = __ldg(a.srowptr + sd0 + i); sdst[i] = __ldg(a.send_dst + sd0 + i); }
         for (int i = threadIdx.x; i <= k1r - k0r; i += kNT) kptr[i] = __ldg(a.kt_browptr + k0r + i) - kt_b0;
@@ -853,7 +873,7 @@ cheb_apply_narrow_kernel(const int slot) {
     }
 #if KEXP_NARROW_TIMING
     if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
-        printf("NTIM cta %3d W %d iters %lld | prod %lld upd %lld | A %lld barA %lld start %lld | recv %lld iter %lld | red %lld barK %lld chk %lld C %lld barC %lld | n_own %d n_h1 %d\n",
+        printf("NTIM cta %3d W %d iters %lld | rows(own) %lld rows(halo) %lld | A %lld barA %lld start %lld | recv %lld iter %lld | red %lld barK %lld chk %lld C %lld barC %lld | n_own %d n_h1 %d\n",
                (int)blockIdx.x, W, s_tim[15], s_tim[1], s_tim[2], s_tim[4], s_tim[5], s_tim[6], s_tim[7], s_tim[9],
                s_tim[10], s_tim[11], s_tim[12], s_tim[13], s_tim[14], (int)a.cap_s_rows, (int)a.cap_halo);
 #endif
@@ -873,7 +893,7 @@ template <int W>
 static size_t narrow_smem_fixed(const NarrowCaps& c) {
     size_t b = sizeof(double) * 9 * (size_t)c.bpr * c.s_rows + sizeof(double) * 9 * (size_t)c.s_rows;
     b += sizeof(double) * (2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);
-    b += sizeof(int) * ((size_t)c.bpr * c.s_rows + c.s_rows + 2 * (size_t)c.send + c.kt_rows + 1 + c.r_rows + 1);
+    b += sizeof(int) * ((size_t)c.bpr * c.s_rows + 2 * (size_t)c.s_rows + 2 * (size_t)c.send + c.kt_rows + 1 + c.r_rows + 1);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -908,6 +928,7 @@ static int build_narrow_plan(kexp_ctx* ctx, int G) {
     std::vector<double> lb;
     std::vector<int> lrow, cta_blk((size_t)G + 1, 0), cta_row((size_t)G + 1, 0), hptr((size_t)G + 1, 0), hcols;
     std::vector<std::vector<int>> halos((size_t)G);
+    std::vector<int> grow((size_t)nbr, 0), lpos((size_t)nbr, 0), cta_nb((size_t)G, 0);     // local row order (see NarrowArgs)
     NarrowCaps caps{0, 0, 0, 0, 0, 0};
     for (int c = 0; c < G; ++c) {
         int r0, r1;
@@ -916,15 +937,27 @@ static int build_narrow_plan(kexp_ctx* ctx, int G) {
         for (int k = sb[r0]; k < sb[r1]; ++k) { const int col = colof(k); if (col < r0 || col >= r1) h1.push_back(col); }
         std::sort(h1.begin(), h1.end());
         h1.erase(std::unique(h1.begin(), h1.end()), h1.end());
+        // local order: the rows that reference a halo column first, then the rows that need only the CTA's own rows
+        {
+            int nbc = 0;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int r = r0; r < r1; ++r) {
+                    bool needs = false;
+                    for (int k = sb[r]; k < sb[r + 1] && !needs; ++k) { const int col = colof(k); needs = (col < r0 || col >= r1); }
+                    if (needs == (pass == 0)) { lpos[r] = nbc; grow[(size_t)r0 + nbc] = r; ++nbc; }
+                    if (pass == 0 && r == r1 - 1) cta_nb[c] = nbc;
+                }
+        }
         const size_t blk0 = lb.size() / 10;
         lrow.push_back(0);
-        for (int r = r0; r < r1; ++r) {
+        for (int lr = 0; lr < r1 - r0; ++lr) {
+            const int r = grow[(size_t)r0 + lr];
             for (int k = sb[r]; k < sb[r + 1]; ++k) {
                 const size_t o = lb.size();
                 lb.insert(lb.end(), blk.begin() + (size_t)k * 10, blk.begin() + (size_t)k * 10 + 10);
                 const int col = colof(k);
                 int64_t slot;
-                if (col >= r0 && col < r1) slot = col - r0;
+                if (col >= r0 && col < r1) slot = lpos[col];
                 else slot = -(int64_t)(std::lower_bound(h1.begin(), h1.end(), col) - h1.begin()) - 1;
                 memcpy(&lb[o + 9], &slot, 8);
             }
@@ -947,7 +980,7 @@ static int build_narrow_plan(kexp_ctx* ctx, int G) {
             int p0, p1;
             range_of(nbr, p, G, p0, p1);
             if (row < p0 || row >= p1) return kexp::fail(ctx, "narrow apply: internal error (row owner)");
-            sends[p].push_back({row - p0, hptr[c] + (int)h});
+            sends[p].push_back({lpos[row], hptr[c] + (int)h});
             talks_to[p].push_back(c);
         }
     bool symmetric = true;
@@ -973,7 +1006,8 @@ static int build_narrow_plan(kexp_ctx* ctx, int G) {
         return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess;
     };
     if (up(&P.lblocks, lb) || up(&P.lrowptr, lrow) || up(&P.cta_blk_ptr, cta_blk) || up(&P.cta_row_ptr, cta_row) ||
-        up(&P.halo_ptr, hptr) || up(&P.halo_cols, hcols) || up(&P.srowptr, srow) || up(&P.cta_send_ptr, cta_send) || up(&P.send_dst, sdst))
+        up(&P.halo_ptr, hptr) || up(&P.halo_cols, hcols) || up(&P.srowptr, srow) || up(&P.cta_send_ptr, cta_send) || up(&P.send_dst, sdst) ||
+        up(&P.grow, grow) || up(&P.cta_nb, cta_nb))
         return kexp::fail(ctx, "out of device memory for the narrow-apply plan");
     P.G = G; P.cap_blocks = caps.bpr; P.cap_rows = caps.s_rows; P.cap_halo = caps.halo; P.cap_send = caps.send;
     P.inbox_slots = (int)hcols.size();
@@ -983,6 +1017,7 @@ static int build_narrow_plan(kexp_ctx* ctx, int G) {
 void free_narrow_plan(NarrowPlanDev& P) {
     cudaFree(P.lblocks); cudaFree(P.lrowptr); cudaFree(P.cta_blk_ptr); cudaFree(P.cta_row_ptr);
     cudaFree(P.halo_ptr); cudaFree(P.halo_cols); cudaFree(P.srowptr); cudaFree(P.cta_send_ptr); cudaFree(P.send_dst);
+    cudaFree(P.grow); cudaFree(P.cta_nb);
     cudaFree(P.inbox);
     P = NarrowPlanDev();
 }
@@ -1086,6 +1121,7 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     a.kt_cols = ctx->d_nktcols;
     a.lblocks = P.lblocks; a.lrowptr = P.lrowptr; a.cta_blk_ptr = P.cta_blk_ptr; a.cta_row_ptr = P.cta_row_ptr;
     a.halo_ptr = P.halo_ptr; a.halo_cols = P.halo_cols; a.srowptr = P.srowptr; a.cta_send_ptr = P.cta_send_ptr; a.send_dst = P.send_dst;
+    a.grow = P.grow; a.cta_nb = P.cta_nb;
     a.inbox = reinterpret_cast<uint4*>(P.inbox); a.inbox_slots = P.inbox_slots;
     a.Pinv = ctx->d_Pinv; a.s_nbr = ctx->As.nbr;
     a.r_rowptr = ctx->Rt.rowptr; a.r_col = ctx->Rt.col; a.r_val = ctx->Rt.val; a.Dblk = ctx->d_Dblk;
