@@ -305,7 +305,10 @@ constexpr int kSpmmGB = KEXP_GB;                 // gathered blocks in flight pe
 #ifndef KEXP_GB_NARROW
 #define KEXP_GB_NARROW 1
 #endif
-constexpr int solve_gb(int W) { return W <= 8 ? KEXP_GB_NARROW : KEXP_GB; }
+#ifndef KEXP_GB_NARROW_MAXW
+#define KEXP_GB_NARROW_MAXW 8
+#endif
+constexpr int solve_gb(int W) { return W <= KEXP_GB_NARROW_MAXW ? KEXP_GB_NARROW : KEXP_GB; }
 #ifndef KEXP_GB0
 #define KEXP_GB0 3
 #endif

@@ -444,3 +444,30 @@ def test_narrow_kernel_ref5_columns_against_cpu_port(monkeypatch, ncols):
         assert max(norms.calculate_norm(sw, F[k], reff[k])) < TOL, k
     assert op.stats()["unconverged_solves"] == 0
     op.close()
+
+
+@pytest.mark.parametrize("B", [1, 4])
+def test_narrow_kernel_repeats_bit_identically(B):
+    """The halo exchange of the persistent kernel has no barrier: a value read before its flag, a slot overwritten too early or a
+    stale halo would show up as run-to-run differences.  60 applies of the same inputs at ref 5 (every CTA has ~7 neighbours and
+    ~500 exchanges per apply) must agree bit for bit, forward recurrence and fused Clenshaw average."""
+    import krylov_exp_b200 as kx
+    sw = get_sw(5)
+    DT, RHO = 900.0, 1.0
+    eig = kx.EIGS[2]
+    op = kx.Operator(sw.K, sw.Mu, sw.Meta_inv_blocks, rtol=1e-11, max_it=40, solver="chebyshev")
+    ce = kx.cheby_exp(op, None, None, 10000, 1e-8, eig * DT * RHO, spectral_radius=eig)
+    t_all, w_all = kx.sample_times_weights(64, DT, RHO)
+    cols = np.arange(3, 64, 64 // B)[:B]
+    t = np.ascontiguousarray(t_all[cols]); w = np.ascontiguousarray(w_all[cols])
+    x, Xall = _m1_inputs(sw, 64)
+    X = np.ascontiguousarray(Xall[cols])
+    Y0 = ce.apply_batch(X, -t).copy()
+    assert op.stats()["solve_path"] == 3
+    v0 = ce.apply_average(X, -t, w, fused=True).copy()
+    for _ in range(60):
+        assert np.array_equal(ce.apply_batch(X, -t), Y0)
+    for _ in range(20):
+        assert np.array_equal(ce.apply_average(X, -t, w, fused=True), v0)
+    assert op.stats()["unconverged_solves"] == 0
+    op.close()
