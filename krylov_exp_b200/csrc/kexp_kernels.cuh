@@ -606,6 +606,16 @@ bsr3_cheb_iter_kernel(const int* __restrict__ browptr, const double* __restrict_
 // iteration still hits L1.  Needs (rows per CTA) <= kSpmmSmemRows and their blocks <= kSpmmSmemBlocks
 // (checked on the host; otherwise one kernel per iteration, bsr3_cheb_iter_kernel).
 // ------------------------------------------------------------------------------------
+// b and x_{k-1} of the own rows are touched once per iteration (L1 is invalidated by every grid barrier): KEXP_COOP_STREAM=1
+// loads them evict-first so that they do not displace the gathered rows of x_k in L1
+#ifndef KEXP_COOP_STREAM
+#define KEXP_COOP_STREAM 0
+#endif
+#if KEXP_COOP_STREAM
+#define KEXP_COOP_LD ld2_stream
+#else
+#define KEXP_COOP_LD ld2
+#endif
 template <int W, int GB>
 __global__ void __launch_bounds__(kThreads, KEXP_SPMM_MINB)
 cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict__ blocks,
@@ -680,8 +690,8 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                         prefetch_l1(Bv + o + (size_t)i * W);
                         prefetch_l1(xm + o + (size_t)i * W);
                     } else {
-                        bv[i] = ld2(Bv + o + (size_t)i * W);
-                        xmv[i] = ld2(xm + o + (size_t)i * W);
+                        bv[i] = KEXP_COOP_LD(Bv + o + (size_t)i * W);
+                        xmv[i] = KEXP_COOP_LD(xm + o + (size_t)i * W);
                     }
                 }
                 for (int kg = k0; kg < k1; kg += GB) {
@@ -724,8 +734,8 @@ cheb_solve_coop_kernel(const int* __restrict__ browptr, const double* __restrict
                 if (kPrefetch) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        bv[i] = ld2(Bv + o + (size_t)i * W);
-                        xmv[i] = ld2(xm + o + (size_t)i * W);
+                        bv[i] = KEXP_COOP_LD(Bv + o + (size_t)i * W);
+                        xmv[i] = KEXP_COOP_LD(xm + o + (size_t)i * W);
                     }
                 }
                 double2 rv[3];
