@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--ref-level", type=int, default=5)
     ap.add_argument("--samples", type=int, default=64, help="averaging samples of the window (whole job); per GPU with --weak")
     ap.add_argument("--weak", action="store_true", help="weak scaling: --samples per GPU, window of samples*N")
+    ap.add_argument("--partition", default="balanced", choices=["balanced", "cyclic"],
+                    help="how the window is split over N > 1 GPUs: cost-balanced unequal shares sorted by |t_k| "
+                         "(ensemble.balanced_partition) or sample k on rank k mod N")
     ap.add_argument("--cg-rtol", type=float, default=1e-11,
                     help="relative residual of the batched mass solve; 1e-11 gives <= 3.2e-12 parity error at ref 5 "
                          "(tests/test_gpu_parity_r2.py::test_M1_exact_bench_settings_all_columns)")
@@ -240,14 +243,20 @@ def main():
         return float(tt.item())
 
     class Shard:
-        """One rank's share of a window: cyclic sample partition (every rank holds the same mix of |t_k|, i.e. of
-        economised series lengths), pinned host buffers for the e2e path, device batches for `value`."""
+        """One rank's share of a window, pinned host buffers for the e2e path, device batches for `value`.  Partition: "cyclic"
+        (sample k on rank k mod N: every rank holds the same mix of |t_k|, i.e. of economised series lengths) or "balanced"
+        (ensemble.balanced_partition: |t_k|-sorted groups of unequal size -- the step of a rank is decided by its longest
+        series, so the rank that holds the longest ones gets fewer samples)."""
 
-        def __init__(self, Bwin):
+        def __init__(self, Bwin, partition="cyclic"):
             self.Bwin = Bwin
-            self.cols = np.arange(rank, Bwin, world)
-            self.B = len(self.cols)
             tw, ww = kx.sample_times_weights(Bwin, DT, RHO)
+            if partition == "balanced" and world > 1:
+                self.groups = kx.balanced_partition(ce.series_terms(tw), world)
+            else:
+                self.groups = [np.arange(r, Bwin, world) for r in range(world)]
+            self.cols = self.groups[rank]
+            self.B = len(self.cols)
             self.t = np.ascontiguousarray(tw[self.cols])
             self.w = np.ascontiguousarray(ww[self.cols])
             self.hX = torch.empty((self.B, n), dtype=torch.float64).pin_memory().numpy()
@@ -299,7 +308,7 @@ def main():
             for b_ in (self.f_in, self.f_out, self.b_in, self.b_out):
                 b_.close()
 
-    sh = Shard(Btot)
+    sh = Shard(Btot, args.partition)
     B = sh.B
     for _ in range(max(args.warmup, 3)):
         sh.step_dev()
@@ -422,7 +431,7 @@ def main():
         _, e_host = sh.timed(sh.step_host, ksteps)
         e_ms = e_host / ksteps
         e2e = {"value": apps_per_step / (e_ms * 1e-3), "unit": "applications/s",
-               "h2d_bytes_per_step": int(8 * n * (B + 1)) * world, "d2h_bytes_per_step": int(8 * n * (B + 1)) * world,
+               "h2d_bytes_per_step": int(8 * n * (Btot + world)), "d2h_bytes_per_step": int(8 * n * (Btot + world)),
                "ms_per_step": e_ms,
                "timing": "host clock around the host-pointer C-ABI calls (pinned buffers; the D2H of the forward results overlaps "
                          "the backward half; all-reduce on the device), barrier + synchronize on both sides, max over ranks"}
@@ -541,7 +550,8 @@ def main():
             "scaling": "weak" if args.weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name, "ncheb": int(ce.ncheb), "L": L, "N": int(n), "applications_per_step": apps_per_step,
-                       "window_samples": Btot, "samples_per_gpu": B,
+                       "window_samples": Btot, "samples_per_gpu": [int(len(g)) for g in sh.groups] if world > 1 else B,
+                       "partition": (args.partition if world > 1 else "single GPU"),
                        "l2": "inputs/outputs of a step ~0.9 GB at 64 samples per GPU (>> 126 MB L2), no explicit flush; inside one mass "
                              "solve the 32-column panel (3 x 23.6 MB + matrix) is deliberately kept L2 resident, so the roofline "
                              "figure is effective (algorithmic) bandwidth",

@@ -12,8 +12,8 @@ from .cheby import cheby_exp, chebyshev_coefficients, real_table
 from .krylov import krylov_exp, ShiftedOperator
 from .function import MixedVector
 from .samples import sample_times_weights, natural_Mbar, EIGS
-from .ensemble import SampleEnsemble, block_partition
+from .ensemble import SampleEnsemble, block_partition, balanced_partition, partition_cost
 
 __all__ = ["cheby_exp", "krylov_exp", "Operator", "DeviceBatch", "CondensedPlan", "MixedVector",
            "ShiftedOperator", "chebyshev_coefficients", "real_table", "sample_times_weights",
-           "natural_Mbar", "EIGS", "SampleEnsemble", "block_partition", "KexpError", "load_library", "LIB_PATH", "detect_interior_dofs"]
+           "natural_Mbar", "EIGS", "SampleEnsemble", "block_partition", "balanced_partition", "partition_cost", "KexpError", "load_library", "LIB_PATH", "detect_interior_dofs"]

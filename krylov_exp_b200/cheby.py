@@ -107,6 +107,18 @@ class cheby_exp(object):
         self.t_valid = float(self.L) / float(eig) if eig else 0.0
         self.op._check(self.op.lib.kexp_set_cheby_time_range(self.op.ctx, self.id, self.t_valid), "kexp_set_cheby_time_range")
 
+    def series_terms(self, t):
+        """Operator applications (Chebyshev terms) the apply spends on each sample time: the length of the economised series
+        when a spectral radius is set, ncheb otherwise.  Host only (kexp_series_reexpand); used to balance samples over GPUs."""
+        t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        if not self.t_valid:
+            return np.full(t.shape, int(self.ncheb), dtype=np.int64)
+        out = np.empty(t.shape, dtype=np.int64)
+        for k, tk in enumerate(t):
+            s = abs(float(tk)) * 1.01 / self.t_valid
+            out[k] = int(self.ncheb) if s > 1.0 else max(reexpand_series(self.a, s)[1] - 1, 1)
+        return out
+
     # ---- the reference interface -------------------------------------------------
     def apply(self, x, y, t):
         """y <- exp(t M^-1 K) x   (cheby_exp.py:110-165).  x is left unchanged, x is not y."""

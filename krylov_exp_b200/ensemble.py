@@ -20,6 +20,82 @@ def block_partition(Mbar, world):
     return np.concatenate([[0], np.cumsum(sizes)]).astype(int)
 
 
+def _panel_widths(k, cap=32):
+    """Panel widths the library gives a batch of k columns: full panels of `cap`, the rest padded to a power of two >= 2."""
+    out = [cap] * (k // cap)
+    r = k % cap
+    if r:
+        w = 2
+        while w < r:
+            w *= 2
+        out.append(w)
+    return out
+
+
+def balanced_partition(terms, world, latency_columns=6.4, forward_columns=6.8, cap=32):
+    """Unequal, cost-balanced shares of the averaging samples for `world` GPUs.
+
+    terms[k]: Chebyshev terms of sample k (cheby_exp.series_terms).  The samples are sorted by series length (= by |t_k|) and cut
+    into `world` contiguous groups; a group costs  max(terms) * forward_columns  for the shared-input forward run plus, per
+    backward panel (sorted, at most `cap` columns),  max(terms of the panel) * (latency_columns + panel width):  a panel's time
+    per term is a latency floor plus a part proportional to its width (measured at ref 5: 70 + 11 W us per term, forward run
+    75 us per term; profiles/r02_summary.md section 2).  The cut minimising the most expensive group is found by dynamic
+    programming.  Returns a list of `world` index arrays (every sample exactly once).  With few samples per GPU the long
+    series decide the step: the rank that holds them gets fewer samples, the ranks with short series more."""
+    terms = np.asarray(terms, dtype=np.float64)
+    B = len(terms)
+    world = int(world)
+    if world < 1 or B < world:
+        raise ValueError("need at least one sample per rank")
+    order = np.argsort(terms, kind="stable")
+    ts = terms[order]
+
+    def cost(i, j):                      # samples i..j-1 of the sorted order
+        c = ts[j - 1] * forward_columns
+        lo = i
+        for w in _panel_widths(j - i, cap):
+            hi = min(lo + min(w, cap), j)
+            c += ts[hi - 1] * (latency_columns + w)
+            lo = hi
+        return c
+    INF = float("inf")
+    best = np.full((world + 1, B + 1), INF)
+    arg = np.zeros((world + 1, B + 1), dtype=np.int64)
+    best[0, 0] = 0.0
+    for g in range(1, world + 1):
+        for j in range(g, B - (world - g) + 1):
+            for i in range(g - 1, j):
+                if best[g - 1, i] == INF:
+                    continue
+                c = max(best[g - 1, i], cost(i, j))
+                if c < best[g, j]:
+                    best[g, j] = c
+                    arg[g, j] = i
+    cuts = [B]
+    j = B
+    for g in range(world, 0, -1):
+        j = int(arg[g, j])
+        cuts.append(j)
+    cuts = cuts[::-1]
+    return [np.sort(order[cuts[g]:cuts[g + 1]]) for g in range(world)]
+
+
+def partition_cost(terms, groups, latency_columns=6.4, forward_columns=6.8, cap=32):
+    """Model cost (in units of one column-term) of the most expensive group of a partition; see balanced_partition."""
+    terms = np.asarray(terms, dtype=np.float64)
+    worst = 0.0
+    for g in groups:
+        ts = np.sort(terms[np.asarray(g)])
+        c = ts[-1] * forward_columns
+        lo = 0
+        for w in _panel_widths(len(ts), cap):
+            hi = min(lo + min(w, cap), len(ts))
+            c += ts[hi - 1] * (latency_columns + w)
+            lo = hi
+        worst = max(worst, c)
+    return worst
+
+
 class SampleEnsemble:
     def __init__(self, Mbar, rank=None, world=None, partition="block"):
         """partition: "block" (contiguous sample blocks per rank) or "cyclic" (sample k on rank k mod world).

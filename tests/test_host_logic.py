@@ -219,3 +219,25 @@ def test_checkpoint_roundtrip_and_norm_table(tmp_path, sw2):
     table = checkpoint.calculate_norm(sw, str(tmp_path / "avg"), str(tmp_path / "std"), (1, 2))
     for i, h in enumerate((1, 2)):
         assert np.allclose(table[i], norms.calculate_norm(sw, runs[("avg", h)], runs[("std", h)]), rtol=1e-13)
+
+
+def test_balanced_partition_covers_every_sample_and_beats_cyclic():
+    """Unequal |t|-sorted shares for the strong-scaling split of an averaging window (ensemble.balanced_partition): every sample
+    exactly once, no empty rank, and under its own cost model never worse than the cyclic split; with the M1 series lengths the
+    rank that holds the longest series gets the fewest samples."""
+    from krylov_exp_b200.ensemble import balanced_partition, partition_cost
+    # series lengths of the 64 M1 sample times (economised, ref 5, dt = 900 s): cheby_exp.series_terms
+    half = [7, 9, 10, 11, 12, 13, 13, 14, 15, 15, 16, 16, 17, 17, 18, 18, 19, 19, 20, 20, 21, 21, 21, 22, 22, 23, 23, 23, 24, 24, 25, 25]
+    terms = np.array(half[::-1] + half)
+    for world in (1, 2, 3, 4, 8, 16):
+        groups = balanced_partition(terms, world)
+        assert len(groups) == world and all(len(g) > 0 for g in groups)
+        assert sorted(np.concatenate(groups).tolist()) == list(range(64))
+        cyc = [np.arange(r, 64, world) for r in range(world)]
+        assert partition_cost(terms, groups) <= partition_cost(terms, cyc) * (1 + 1e-12)
+    g8 = balanced_partition(terms, 8)
+    longest = [g for g in g8 if terms[g].max() == 25][0]
+    assert len(longest) == min(len(g) for g in g8)
+    assert partition_cost(terms, g8) < 0.95 * partition_cost(terms, [np.arange(r, 64, 8) for r in range(8)])
+    with pytest.raises(ValueError):
+        balanced_partition(terms[:3], 4)
