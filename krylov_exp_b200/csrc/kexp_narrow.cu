@@ -1,28 +1,27 @@
-// kexp_narrow.cu -- the whole cheby_exp.apply (cheby_exp.py:110-165) of a NARROW panel (2..16 sample columns) as ONE
+// kexp_narrow.cu -- the whole cheby_exp.apply (cheby_exp.py:110-165) of a NARROW panel (2, 4 or 8 sample columns) as ONE
 // persistent cooperative kernel.
 //
-// Why: with few columns per GPU -- the strong-scaling regime (64 samples over 8 GPUs = 8 columns each), the
-// single-column recurrences of the shared-input forward pass and of the fused Clenshaw average, and the reference's
-// own un-batched apply(x, y, t) -- an apply is a chain of ~25 terms x ~22 sparse products with a grid-wide dependency
-// after each one, and its cost is LATENCY (L2 round trip of the gather + barrier), not bandwidth.  Five kernel
-// launches per term (K~ product, mass solve, three row ranges of the recurrence update) each pay a launch boundary,
-// re-stage the mass matrix in shared memory and serialise the gathers of a block row.  Here:
-//   * one launch per apply: 1 CTA per SM, 512 threads, matrix S (+ the index arrays of K~ and R) of the CTA's row
-//     ranges resident in shared memory for ALL terms and iterations;
-//   * phases separated by grid-wide barriers only:   per term   A: T = K~ S_{n-1} (depth rows updated in the epilogue)
-//     | B: K-1 Chebyshev iterations of the mass solve, the edge-row recurrence update fused into the last one
-//     | C: interior rows  w_I = T_I + R w_E  and their update   -> K + 2 barriers per term;
-//   * inside the mass solve the iterate lives in SHARED memory: x_k on the CTA's own rows plus the halo rows its
-//     blocks reference (local slot numbers precomputed on the host), x_{k-1} / x_{k+1}, and b.  Per exchange a CTA
-//     reads only its halo (each row once, coalesced, ld.global.cg) and publishes its own rows; the products read
-//     shared memory, so there is no gather latency chain, no L1 coherence question, hardly any register pressure;
-//   * TWO Chebyshev iterations per grid barrier where shared memory allows (single-column panels at ref 5): the CTA
-//     also holds the matrix rows of its first halo ring H1 and the iterate on a second ring H2, computes x_{k+1} on
-//     own + H1 redundantly (bit-identical to what the owners compute) and then x_{k+2} on its own rows -- half the
-//     barriers and exchanges of the solve for ~45 % more local work in a latency-bound kernel;
-//   * data written by other CTAs is read with ld.global.cg (L2, the coherence point), everything else normally;
-//   * the convergence record of every mass solve (||b - S x||/||b|| per column against the relaxed tolerance of
-//     its term) is reduced in fixed order by CTA 0 behind the barrier that follows the solve.
+// Why: with few columns per GPU -- the per-GPU share of an averaging window split over many GPUs, the single-column
+// recurrences of the shared-input forward pass and of the fused Clenshaw average, and the reference's own un-batched
+// apply(x, y, t) -- an apply is a chain of ~25 terms x ~22 sparse products with a dependency on the neighbours after each
+// one, and its cost is LATENCY, not bandwidth.  Five kernel launches per term (K~ product, mass solve, three row ranges of
+// the recurrence update) each pay a launch boundary, re-stage the mass matrix in shared memory and serialise the gathers of
+// a block row.  Here:
+//   * one launch per apply: 1 CTA per SM, 256 threads with up to 255 registers; the CTA's rows of S (transposed), P^-1,
+//     the index arrays of K~ and R and its send lists stay in shared memory for ALL terms and iterations;
+//   * per term three phases separated by grid-wide barriers:  A: T = K~ S_{n-1} (depth rows updated in the epilogue)
+//     | B: the mass solve, K-1 Chebyshev iterations, the edge-row recurrence update fused into the last one
+//     | C: interior rows  w_I = T_I + R w_E  and their update;
+//   * INSIDE the mass solve there is no grid barrier: the iterate lives in shared memory (own rows, two generations, plus
+//     the halo rows the own rows reference), b and -- for up to 4 columns -- the thread's row of S and P^-1 in registers,
+//     one thread per block row; the boundary rows of every new iterate travel to the neighbours' inboxes as flagged values
+//     (flag-in-data, see the comment in front of ll_store), and a CTA waits only for the values it needs;
+//   * data written by other CTAs is read with ld.global.cg / relaxed gpu-scope loads (L2, the coherence point), everything
+//     else normally;
+//   * the convergence record of every mass solve (||b - S x||/||b|| per column against the relaxed tolerance of its term) is
+//     reduced in fixed order by CTA 0 behind the barrier that follows the solve;
+//   * the kernel contains no CALL and no conditionally defined local array: both cost registers everywhere (comments at
+//     narrow_check and in phase A; measurements in profiles/r02_summary.md section 3).
 // The arithmetic per row is the same as in the wide-panel kernels (kexp_kernels.cuh): same three-term Chebyshev
 // acceleration, same recurrence, same order of operations inside a row.
 #include <cooperative_groups.h>
@@ -86,10 +85,10 @@ struct NarrowArgs {
     int xs_offset;                       // first double of the iterate buffers in dynamic shared memory
 };
 
-// The arguments live in constant memory (one slot per context, round-robin): the phases below are separate, NOT
-// inlined functions -- each gets its own register allocation instead of one body that keeps the loop invariants of all
-// phases alive and spills -- and read their arguments from the constant bank.  (Passing the ADDRESS of a by-value
-// kernel parameter to out-of-line functions makes the compiler keep a per-thread copy in local memory: every pointer
+// The arguments live in constant memory (one slot per context, round-robin): every phase derives what it needs -- row
+// ranges, shared-memory pointers, the constants of the step -- from blockIdx, the step number and this bank, so that
+// nothing but three counters is live between the phases and each phase has the register file to itself.  (Passing the
+// ADDRESS of a by-value kernel parameter around makes the compiler keep a per-thread copy in local memory: every pointer
 // load of the hot loops became a dependent L1/L2 access, measured 4x slower.)
 constexpr int kArgSlots = 8;
 __constant__ NarrowArgs c_nargs[kArgSlots];
@@ -839,9 +838,8 @@ cheb_apply_narrow_kernel(const int slot) {
     narrow_barrier(grid, a.barrier, bar_target);
 
     unsigned xid = 1;                                    // number of the next halo exchange (the inbox holds zeros)
-    // Every phase is a separate, NOT inlined function that derives what it needs (row ranges, shared-memory pointers, the
-    // constants of the step) from blockIdx, the step number and the constant bank: nothing but the three counters below is
-    // live across the calls, so each phase has the whole register file to itself.
+    // Every phase derives what it needs (row ranges, shared-memory pointers, the constants of the step) from blockIdx, the
+    // step number and the constant bank: nothing but the three counters below is live between them.
     for (int step = 1; step <= a.M; ++step) {
         NTIM_T0
         narrow_phase_a<W>(slot, step);
