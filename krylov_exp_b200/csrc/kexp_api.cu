@@ -108,6 +108,7 @@ static int build_bsr3(kexp_ctx* ctx, DevCsr& d, int nrows, int ncols, const int3
     }
     d.nbr = nbr; d.nblocks = nblocks; d.max_bpr = max_bpr;
     d.h_browptr = browptr;
+    d.h_rowmap = rowmap;
     if (force && nrows == ncols) d.h_blocks = blocks;
     d.diag_first = force && nrows == ncols && all_diag;
     if (max_bpr > kSpmmSmemBlocks) { cudaFree(d.browptr); cudaFree(d.blocks); d.browptr = nullptr; d.blocks = nullptr; d.h_browptr.clear(); }

@@ -27,6 +27,7 @@ struct DevCsr {
     bool diag_first = false;       // every block row starts with its diagonal block
     int64_t nblocks = 0;
     std::vector<int> h_browptr;    // host copy of browptr (stored row order): shared-memory budgeting of the persistent kernels
+    std::vector<int> h_rowmap;     // host copy of rowmap (empty: identity)
     std::vector<int> h_rowptr;     // host copy of rowptr
     std::vector<double> h_blocks;  // host copy of the blocks (square matrices only: S)
     bool bsr() const { return blocks != nullptr; }
@@ -79,6 +80,11 @@ struct NarrowPlanDev {
     double* lblocks = nullptr; int* lrowptr = nullptr; int* cta_blk_ptr = nullptr; int* cta_row_ptr = nullptr;
     int* halo_ptr = nullptr; int* halo_cols = nullptr; int* srowptr = nullptr; int* cta_send_ptr = nullptr; int* send_dst = nullptr;
     int* grow = nullptr; int* cta_nb = nullptr;    // local row order of every CTA (rows that reference halo slots first)
+    // K~ for the product of the persistent kernel: per CTA the rows sorted by block count, in groups of 32 rows whose blocks
+    // are stored transposed ([block slot][16-byte part][row of the group]) so that a warp's loads are contiguous
+    double* kt2 = nullptr; int* kt2_cnt = nullptr; int* kt2_orow = nullptr; int* kt2_gbase = nullptr; int* kt2_grp_ptr = nullptr;
+    int* kt2_cta_ptr = nullptr;    // rows of K~ per CTA, cut by block count
+    int cap_kt_groups = 0, cap_kt_rows = 0;
     void* inbox = nullptr;         // flagged halo inboxes (two buffers)
     int G = 0;                     // grid the plan was built for (< 0: built and found not applicable)
     int cap_blocks = 0, cap_rows = 0, cap_halo = 0, cap_send = 0, inbox_slots = 0;

@@ -64,7 +64,11 @@ struct NarrowArgs {
     const int* grow; const int* cta_nb;
     uint4* inbox; int inbox_slots;                           // two buffers of inbox_slots x 3W flagged doubles (zeroed before the launch)
     const double* Pinv; int s_nbr;
-    const int* kt_cols;                                      // block columns of K~ (global copy of the 10th doubles)
+    // K~ re-laid out for coalesced loads (build_narrow_kt): the CTA's rows sorted by block count; kt2_cnt / kt2_orow: blocks and
+    // output block row of every row in that order; groups of 32 rows, group g of CTA c starts at double2 index
+    // kt2_gbase[kt2_grp_ptr[c] + g]; part p (0..4) of block slot q of row r of the group at  base + (5 q + p) 32 + r
+    const double2* kt2; const int* kt2_cnt; const int* kt2_orow; const int* kt2_gbase; const int* kt2_grp_ptr;
+    const int* kt2_cta_ptr;                                  // the CTA's rows of K~: [kt2_cta_ptr[c], kt2_cta_ptr[c+1]), cut by BLOCK count
     // R (CSR, n_b x n_s) or null; Dblk (n_d/3 blocks) or null
     const int* r_rowptr; const int* r_col; const double* r_val; const double* Dblk;
     int n, n_s, n_b, n_d;
@@ -82,6 +86,7 @@ struct NarrowArgs {
     unsigned* barrier;                   // grid barrier counter (zeroed before the launch)
     // shared-memory layout (element counts, maxima over the CTAs)
     int cap_bpr, cap_s_rows, cap_kt_rows, cap_r_rows, cap_halo, cap_send;     // cap_bpr: most blocks in a row of S
+    int cap_kt_groups;                   // most 32-row groups of K~ in a CTA
     int xs_offset;                       // first double of the iterate buffers in dynamic shared memory
 };
 
@@ -218,7 +223,8 @@ __device__ __forceinline__ UpdCtx make_upd(const NarrowArgs& a, const StepCtx& s
 // compiler knows they are shared-memory addresses: LDS / STS instead of generic accesses).
 struct NarrowSmem {
     double *sv, *sP, *sred;                       // S values (transposed: [9 * bpr][ell_ld]), block-Jacobi inverses (transposed: [9][ell_ld]), reduction scratch
-    int *ss, *scnt, *sptr, *sdst, *kptr, *rptr;   // column slots ([bpr][ell_ld]), blocks per row, send entries (source row, inbox slot), row pointers of K~ and R
+    int *ss, *scnt, *sptr, *sdst, *kptr, *rptr;   // column slots ([bpr][ell_ld]), blocks per row, send entries (source row, inbox slot), K~: blocks per row (sorted order), row pointers of R
+    int *korow, *kgb;                             // K~: output block row of every row (sorted order), base of every 32-row group
     int *sgrow;                                   // global block row of every local row
     double *xo0, *xo1, *xh;                       // iterates on the own rows (two), halo of the current iterate
     int ell_ld;
@@ -238,21 +244,28 @@ __device__ __forceinline__ NarrowSmem narrow_smem_carve(const NarrowArgs& a) {
     m.kptr = m.sdst + a.cap_send;
     m.rptr = m.kptr + a.cap_kt_rows + 1;
     m.sgrow = m.rptr + a.cap_r_rows + 1;
+    m.korow = m.sgrow + a.cap_s_rows;
+    m.kgb = m.korow + a.cap_kt_rows;
     m.xo0 = reinterpret_cast<double*>(smem2) + a.xs_offset;                    // 16-byte aligned
     m.xo1 = m.xo0 + (size_t)NarrowCfg<W>::SS * a.cap_s_rows;
     m.xh = m.xo1 + (size_t)NarrowCfg<W>::SS * a.cap_s_rows;
     return m;
 }
 
-// ---- phase A: T = K~ S_{n-1}; depth rows (no solve) take their recurrence update in the epilogue
+// ---- phase A: T = K~ S_{n-1}; depth rows (no solve) take their recurrence update in the epilogue.
+// K~ is streamed from L2 / HBM once per term (37 MB at ref 5) and the rows of a warp are different rows: with the plain
+// 80-byte blocks every 16-byte load of a warp touched 32 different lines and the phase was bound by the LSU request rate
+// (30 k cycles per term at W = 2).  The copy used here stores, per group of 32 rows of similar length, part p of block
+// slot q of all 32 rows side by side: the loads of a warp are contiguous.
 template <int W>
 KEXP_PHASE_FN void narrow_phase_a(int slot, int step) {
     const NarrowArgs& a = c_nargs[slot];
     const StepCtx sx = make_step(a, step);
-    int k0r, k1r;
-    cta_range(a.kt_nbr, k0r, k1r);
-    const int kt_b0 = __ldg(a.kt_browptr + k0r);
-    const int* __restrict__ kptr = narrow_smem_carve<W>(a).kptr;
+    const int k0r = __ldg(a.kt2_cta_ptr + blockIdx.x), k1r = __ldg(a.kt2_cta_ptr + blockIdx.x + 1);
+    const NarrowSmem smA = narrow_smem_carve<W>(a);
+    const int* __restrict__ kcnt = smA.kptr;
+    const int* __restrict__ korow = smA.korow;
+    const int* __restrict__ kgb = smA.kgb;
     using C = PanelCfg<W, 2>;
     constexpr int LPB = C::LPB, BRW = C::BRW;
     constexpr int kNT = NarrowCfg<W>::NT, kNWarps = kNT / 32, kGatherK = NarrowCfg<W>::GK;
@@ -262,33 +275,40 @@ KEXP_PHASE_FN void narrow_phase_a(int slot, int step) {
     const UpdCtx u = make_upd<W>(a, sx, l);
     const double* Sin = sx.Sin;
     const int row_eta = a.n_s + a.n_b;
-    for (int base = k0r; base < k1r; base += BPC) {
-        const int br = base + warp * BRW + g;
-        if (br < k1r) {
-            const int q0 = kptr[br - k0r], q1 = kptr[br - k0r + 1];
-            const int orow = a.kt_rowmap ? __ldg(a.kt_rowmap + br) : br;
+    const int nrows = k1r - k0r;
+    for (int base = 0; base < nrows; base += BPC) {
+        const int lr = base + warp * BRW + g;
+        if (lr < nrows) {
+            const int nq = kcnt[lr];
+            const int orow = korow[lr];
+            const double2* gp = a.kt2 + kgb[lr >> 5] + (lr & 31);
             double2 acc[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
-            for (int q = q0; q < q1; q += kGatherK) {
+            for (int q = 0; q < nq; q += kGatherK) {
                 // (every element is defined on every path: a conditionally defined array looks live from the top of the kernel
                 // to ptxas -- around the whole step loop -- and costs its registers everywhere, e.g. in the mass solve)
-                double2 x[kGatherK][3];
+                double2 x[kGatherK][3], v8c[kGatherK];
 #pragma unroll
-                for (int j = 0; j < kGatherK; ++j)
+                for (int j = 0; j < kGatherK; ++j) {
+                    v8c[j] = make_double2(0.0, 0.0);
 #pragma unroll
                     for (int r = 0; r < 3; ++r) x[j][r] = make_double2(0.0, 0.0);
+                }
 #pragma unroll
                 for (int j = 0; j < kGatherK; ++j)
-                    if (q + j < q1) {
-                        const double* xr = Sin + (size_t)(3 * __ldg(a.kt_cols + kt_b0 + q + j)) * W + 2 * l;
+                    if (q + j < nq) v8c[j] = __ldg(gp + (5 * (q + j) + 4) * 32);          // m22 and the block column
+#pragma unroll
+                for (int j = 0; j < kGatherK; ++j)
+                    if (q + j < nq) {
+                        const double* xr = Sin + (size_t)(3 * __double2loint(v8c[j].y)) * W + 2 * l;
 #pragma unroll
                         for (int r = 0; r < 3; ++r) x[j][r] = ldcg2(xr + (size_t)r * W);
                     }
 #pragma unroll
                 for (int j = 0; j < kGatherK; ++j)
-                    if (q + j < q1) {
-                        const double2* bp = reinterpret_cast<const double2*>(a.kt_blocks) + (size_t)5 * (kt_b0 + q + j);
-                        const double2 v01 = __ldg(bp), v23 = __ldg(bp + 1), v45 = __ldg(bp + 2), v67 = __ldg(bp + 3), v8c = __ldg(bp + 4);
-                        const double m[3][3] = {{v01.x, v01.y, v23.x}, {v23.y, v45.x, v45.y}, {v67.x, v67.y, v8c.x}};
+                    if (q + j < nq) {
+                        const double2* bp = gp + (5 * (q + j)) * 32;
+                        const double2 v01 = __ldg(bp), v23 = __ldg(bp + 32), v45 = __ldg(bp + 64), v67 = __ldg(bp + 96);
+                        const double m[3][3] = {{v01.x, v01.y, v23.x}, {v23.y, v45.x, v45.y}, {v67.x, v67.y, v8c[j].x}};
 #pragma unroll
                         for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -769,11 +789,10 @@ KEXP_PHASE_FN void narrow_prologue(int slot) {
     double* sv = sm.sv; double* sP = sm.sP;
     int* ss = sm.ss; int* scnt = sm.scnt; int* sptr = sm.sptr; int* sdst = sm.sdst; int* kptr = sm.kptr; int* rptr = sm.rptr;
 
-    int s0, s1, k0r, k1r, r0, r1;
+    int s0, s1, r0, r1;
     cta_range(a.s_nbr, s0, s1);
-    cta_range(a.kt_nbr, k0r, k1r);
+    const int k0r = __ldg(a.kt2_cta_ptr + blockIdx.x), k1r = __ldg(a.kt2_cta_ptr + blockIdx.x + 1);
     cta_range(a.n_b, r0, r1);
-    const int kt_b0 = __ldg(a.kt_browptr + k0r);
     const int n_own = s1 - s0;
     const int h0 = __ldg(a.halo_ptr + blockIdx.x), n_h1 = __ldg(a.halo_ptr + blockIdx.x + 1) - h0;
 
@@ -798,7 +817,11 @@ KEXP_PHASE_FN void narrow_prologue(int slot) {
             sP[(i % 9) * ell_ld + i / 9] = __ldg(a.Pinv + (size_t)9 * __ldg(a.grow + s0 + i / 9) + i % 9);
         const int sd0 = __ldg(a.cta_send_ptr + blockIdx.x), nsd = __ldg(a.cta_send_ptr + blockIdx.x + 1) - sd0;
         for (int i = threadIdx.x; i < nsd; i += kNT) { sptr[i] = __ldg(a.srowptr + sd0 + i); sdst[i] = __ldg(a.send_dst + sd0 + i); }
-        for (int i = threadIdx.x; i <= k1r - k0r; i += kNT) kptr[i] = __ldg(a.kt_browptr + k0r + i) - kt_b0;
+        for (int i = threadIdx.x; i < k1r - k0r; i += kNT) { kptr[i] = __ldg(a.kt2_cnt + k0r + i); sm.korow[i] = __ldg(a.kt2_orow + k0r + i); }
+        {
+            const int g0 = __ldg(a.kt2_grp_ptr + blockIdx.x), ng = __ldg(a.kt2_grp_ptr + blockIdx.x + 1) - g0;
+            for (int i = threadIdx.x; i < ng; i += kNT) sm.kgb[i] = __ldg(a.kt2_gbase + g0 + i);
+        }
         if (a.n_b > 0) {
             const int q0 = __ldg(a.r_rowptr + r0);
             for (int i = threadIdx.x; i <= r1 - r0; i += kNT) rptr[i] = __ldg(a.r_rowptr + r0 + i) - q0;
@@ -878,7 +901,7 @@ cheb_apply_narrow_kernel(const int slot) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct NarrowCaps { int bpr, s_rows, kt_rows, r_rows, halo, send; };
+struct NarrowCaps { int bpr, s_rows, kt_rows, r_rows, halo, send, kt_groups; };
 
 static void range_of(int nrows, int c, int G, int& start, int& end) {
     const int per = nrows / G, rem = nrows % G;
@@ -891,7 +914,7 @@ template <int W>
 static size_t narrow_smem_fixed(const NarrowCaps& c) {
     size_t b = sizeof(double) * 9 * (size_t)c.bpr * c.s_rows + sizeof(double) * 9 * (size_t)c.s_rows;
     b += sizeof(double) * (2 * kNWarpsMax * W + 2 * W * 32 + 4 * W);
-    b += sizeof(int) * ((size_t)c.bpr * c.s_rows + 2 * (size_t)c.s_rows + 2 * (size_t)c.send + c.kt_rows + 1 + c.r_rows + 1);
+    b += sizeof(int) * ((size_t)c.bpr * c.s_rows + 2 * (size_t)c.s_rows + 2 * (size_t)c.send + 2 * (size_t)c.kt_rows + 1 + c.r_rows + 1 + c.kt_groups);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -900,9 +923,79 @@ static size_t narrow_smem(const NarrowCaps& c) {
     return narrow_smem_fixed<W>(c) + sizeof(double) * NarrowCfg<W>::SS * ((size_t)2 * c.s_rows + c.halo);
 }
 
-__global__ void extract_block_cols_kernel(const double* __restrict__ blocks, int64_t nblocks, int* __restrict__ cols) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nblocks; i += (int64_t)gridDim.x * blockDim.x)
-        cols[i] = __double2loint(blocks[10 * i + 9]);
+// gather kernel of build_narrow_kt: one thread per (row in the sorted order, block slot, 16-byte part)
+__global__ void kt_transpose_kernel(const double2* __restrict__ blocks, const int* __restrict__ browptr, const int* __restrict__ srow,
+                                    const int* __restrict__ cnt, const int* __restrict__ rbase, int nbr, int max_cnt, double2* __restrict__ out) {
+    const int64_t total = (int64_t)nbr * max_cnt * 5;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / (max_cnt * 5)), rem = (int)(i % (max_cnt * 5)), q = rem / 5, p = rem % 5;
+        if (q < cnt[row]) out[(size_t)rbase[row] + (size_t)(5 * q + p) * 32] = blocks[(size_t)5 * (browptr[srow[row]] + q) + p];
+    }
+}
+
+// K~ for phase A of the persistent kernel (see NarrowArgs): per CTA the rows of its range sorted by block count (a warp then
+// holds rows of equal length), cut into groups of 32 rows, every group stored transposed and padded to its longest row.
+// The index arrays are built on the host from the row pointers, the blocks are moved by kt_transpose_kernel.
+static int build_narrow_kt(kexp_ctx* ctx, int G) {
+    NarrowPlanDev& P = ctx->narrow_plan;
+    if (P.kt2) return 0;
+    const std::vector<int>& kb = ctx->Kt.h_browptr;
+    if (kb.empty()) return kexp::fail(ctx, "narrow apply: host copy of the row pointers of K~ not available");
+    const int nbr = (int)kb.size() - 1;
+    std::vector<int> srow((size_t)nbr), cnt((size_t)nbr), orow((size_t)nbr), rbase((size_t)nbr), gbase, grp_ptr((size_t)G + 1, 0);
+    // the CTAs' row ranges: cut by block count (a warp holds rows of equal length, so a CTA's time follows its blocks)
+    std::vector<int> cta_ptr((size_t)G + 1, 0);
+    for (int c = 1; c < G; ++c) {
+        const int64_t want = (int64_t)kb[nbr] * c / G;
+        cta_ptr[c] = (int)(std::lower_bound(kb.begin(), kb.end(), (int)want) - kb.begin());
+        cta_ptr[c] = std::min(std::max(cta_ptr[c], cta_ptr[c - 1]), nbr);
+    }
+    cta_ptr[G] = nbr;
+    size_t total = 0;                                  // double2 elements of the transposed copy
+    int max_cnt = 1, cap_groups = 0, cap_rows = 0;
+    for (int c = 0; c < G; ++c) {
+        const int r0 = cta_ptr[c], r1 = cta_ptr[c + 1];
+        cap_rows = std::max(cap_rows, r1 - r0);
+        std::vector<int> idx;
+        for (int r = r0; r < r1; ++r) idx.push_back(r);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return kb[x + 1] - kb[x] > kb[y + 1] - kb[y]; });
+        for (int i = 0; i < r1 - r0; ++i) {
+            const int r = idx[i];
+            srow[(size_t)r0 + i] = r;
+            cnt[(size_t)r0 + i] = kb[r + 1] - kb[r];
+            orow[(size_t)r0 + i] = ctx->Kt.h_rowmap.empty() ? r : ctx->Kt.h_rowmap[r];
+            max_cnt = std::max(max_cnt, cnt[(size_t)r0 + i]);
+        }
+        const int ng = (r1 - r0 + 31) / 32;
+        for (int g = 0; g < ng; ++g) {
+            const int gmax = cnt[(size_t)r0 + 32 * g];  // sorted: the first row of the group is its longest
+            gbase.push_back((int)total);
+            for (int i = 32 * g; i < std::min(32 * g + 32, r1 - r0); ++i) rbase[(size_t)r0 + i] = (int)total + (i - 32 * g);
+            total += (size_t)gmax * 5 * 32;
+        }
+        grp_ptr[c + 1] = (int)gbase.size();
+        cap_groups = std::max(cap_groups, ng);
+    }
+    if (total >= ((size_t)1 << 31)) return kexp::fail(ctx, "narrow apply: K~ too large for the persistent kernel");
+    int* d_srow = nullptr; int* d_rbase = nullptr;
+    auto up = [&](int** dst, const std::vector<int>& v) -> bool {
+        if (cudaMalloc(dst, sizeof(int) * std::max<size_t>(v.size(), 1)) != cudaSuccess) return true;
+        return cudaMemcpy(*dst, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess;
+    };
+    if (up(&P.kt2_cnt, cnt) || up(&P.kt2_orow, orow) || up(&P.kt2_gbase, gbase) || up(&P.kt2_grp_ptr, grp_ptr) || up(&P.kt2_cta_ptr, cta_ptr) ||
+        up(&d_srow, srow) || up(&d_rbase, rbase) ||
+        cudaMalloc(&P.kt2, sizeof(double2) * std::max<size_t>(total, 1)) != cudaSuccess) {
+        cudaFree(d_srow); cudaFree(d_rbase);
+        return kexp::fail(ctx, "out of device memory for the narrow-apply copy of K~");
+    }
+    cudaMemsetAsync(P.kt2, 0, sizeof(double2) * std::max<size_t>(total, 1), ctx->stream);
+    kt_transpose_kernel<<<8 * ctx->num_sms, 256, 0, ctx->stream>>>(reinterpret_cast<const double2*>(ctx->Kt.blocks), ctx->Kt.browptr, d_srow, P.kt2_cnt,
+                                                                   d_rbase, nbr, max_cnt, reinterpret_cast<double2*>(P.kt2));
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_srow); cudaFree(d_rbase);
+    if (e != cudaSuccess) return kexp::fail(ctx, std::string("narrow apply: transposing K~ failed: ") + cudaGetErrorString(e));
+    P.cap_kt_groups = cap_groups; P.cap_kt_rows = cap_rows;
+    return 0;
 }
 
 // Per-CTA local problems of S for a grid of G CTAs (see NarrowArgs): the CTA's own rows with shared-memory slot numbers,
@@ -927,7 +1020,7 @@ static int build_narrow_plan(kexp_ctx* ctx, int G) {
     std::vector<int> lrow, cta_blk((size_t)G + 1, 0), cta_row((size_t)G + 1, 0), hptr((size_t)G + 1, 0), hcols;
     std::vector<std::vector<int>> halos((size_t)G);
     std::vector<int> grow((size_t)nbr, 0), lpos((size_t)nbr, 0), cta_nb((size_t)G, 0);     // local row order (see NarrowArgs)
-    NarrowCaps caps{0, 0, 0, 0, 0, 0};
+    NarrowCaps caps{0, 0, 0, 0, 0, 0, 0};
     for (int c = 0; c < G; ++c) {
         int r0, r1;
         range_of(nbr, c, G, r0, r1);
@@ -1016,6 +1109,7 @@ void free_narrow_plan(NarrowPlanDev& P) {
     cudaFree(P.lblocks); cudaFree(P.lrowptr); cudaFree(P.cta_blk_ptr); cudaFree(P.cta_row_ptr);
     cudaFree(P.halo_ptr); cudaFree(P.halo_cols); cudaFree(P.srowptr); cudaFree(P.cta_send_ptr); cudaFree(P.send_dst);
     cudaFree(P.grow); cudaFree(P.cta_nb);
+    cudaFree(P.kt2); cudaFree(P.kt2_cnt); cudaFree(P.kt2_orow); cudaFree(P.kt2_gbase); cudaFree(P.kt2_grp_ptr); cudaFree(P.kt2_cta_ptr);
     cudaFree(P.inbox);
     P = NarrowPlanDev();
 }
@@ -1024,13 +1118,11 @@ static bool narrow_caps(kexp_ctx* ctx, int G, NarrowCaps& c) {
     const std::vector<int>& kb = ctx->Kt.h_browptr;
     const std::vector<int>& rp = ctx->Rt.h_rowptr;
     if (ctx->As.h_browptr.empty() || kb.empty()) return false;
-    if (build_narrow_plan(ctx, G)) return false;
+    if (build_narrow_plan(ctx, G) || build_narrow_kt(ctx, G)) return false;
     const NarrowPlanDev& P = ctx->narrow_plan;
-    c = NarrowCaps{P.cap_blocks, P.cap_rows, 0, 0, P.cap_halo, P.cap_send};
+    c = NarrowCaps{P.cap_blocks, P.cap_rows, P.cap_kt_rows, 0, P.cap_halo, P.cap_send, P.cap_kt_groups};
     for (int i = 0; i < G; ++i) {
         int a, b;
-        range_of((int)kb.size() - 1, i, G, a, b);
-        c.kt_rows = std::max(c.kt_rows, b - a);
         if (!rp.empty()) {
             range_of((int)rp.size() - 1, i, G, a, b);
             c.r_rows = std::max(c.r_rows, b - a);
@@ -1102,10 +1194,6 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
         KEXP_CUDA(cudaMalloc(&ctx->d_nrtol2, sizeof(double) * kMaxTerms));
         KEXP_CUDA(cudaMalloc(&ctx->d_npartials, sizeof(double) * 2 * kMaxW * (size_t)ctx->num_sms + 64));
     }
-    if (!ctx->d_nktcols) {
-        KEXP_CUDA(cudaMalloc(&ctx->d_nktcols, sizeof(int) * (size_t)std::max<int64_t>(ctx->Kt.nblocks, 1)));
-        extract_block_cols_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(ctx->Kt.blocks, ctx->Kt.nblocks, ctx->d_nktcols);
-    }
     NarrowPlanDev& P = ctx->narrow_plan;
     // halo inboxes: two buffers of (all halo slots) x 3 x 8 flagged doubles (sized for the widest narrow panel), zeroed per launch
     const size_t inbox_bytes = sizeof(uint4) * 2 * (size_t)std::max(P.inbox_slots, 1) * 3 * 8;
@@ -1116,7 +1204,8 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     KEXP_CUDA(cudaMemcpyAsync(ctx->d_nrtol2, rtol2, sizeof(double) * (size_t)(M + 1), cudaMemcpyHostToDevice, ctx->stream));
     NarrowArgs a;
     a.kt_browptr = ctx->Kt.browptr; a.kt_blocks = ctx->Kt.blocks; a.kt_rowmap = ctx->Kt.rowmap; a.kt_nbr = ctx->Kt.nbr;
-    a.kt_cols = ctx->d_nktcols;
+    a.kt2 = reinterpret_cast<const double2*>(P.kt2); a.kt2_cnt = P.kt2_cnt; a.kt2_orow = P.kt2_orow; a.kt2_gbase = P.kt2_gbase;
+    a.kt2_grp_ptr = P.kt2_grp_ptr; a.kt2_cta_ptr = P.kt2_cta_ptr;
     a.lblocks = P.lblocks; a.lrowptr = P.lrowptr; a.cta_blk_ptr = P.cta_blk_ptr; a.cta_row_ptr = P.cta_row_ptr;
     a.halo_ptr = P.halo_ptr; a.halo_cols = P.halo_cols; a.srowptr = P.srowptr; a.cta_send_ptr = P.cta_send_ptr; a.send_dst = P.send_dst;
     a.grow = P.grow; a.cta_nb = P.cta_nb;
@@ -1139,7 +1228,7 @@ int launch_narrow_apply(kexp_ctx* ctx, int W, int M, int mode, const int* kterm,
     a.pairs = ctx->d_npartials + 2 * kMaxW * (size_t)ctx->num_sms + 2;
     KEXP_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), ctx->stream));
     a.cap_bpr = caps.bpr; a.cap_s_rows = caps.s_rows; a.cap_kt_rows = caps.kt_rows; a.cap_r_rows = caps.r_rows;
-    a.cap_halo = caps.halo; a.cap_send = caps.send; a.xs_offset = 0;
+    a.cap_halo = caps.halo; a.cap_send = caps.send; a.cap_kt_groups = caps.kt_groups; a.xs_offset = 0;
     const int np = narrow_passes(W, caps);
     const bool mreg = ctx->narrow_mreg && np == 1 && caps.bpr <= 5 && W <= 4;      // matrix rows in registers
     int rc = 1;
