@@ -84,7 +84,13 @@ class krylov_exp(object):
         self.u = None
 
     def apply(self, x, y, t, its=-999, residuals=True):
-        """y <- exp(-t M^-1 K) x by SAI-Arnoldi (krylov_exp.py:50-109; note the sign, :89,96)."""
+        """y <- exp(-t M^-1 K) x by SAI-Arnoldi (krylov_exp.py:50-109; note the sign, :89,96).
+
+        `self.residuals` holds the reference's residual estimates (krylov_exp.py:95-101).  Deviation: the constant C of
+        the estimate is ||M^-1 K w|| from THIS context's operator; the reference applies whatever `operator_solver` it was
+        constructed with (its docstring and test_krylov.py pass the operator of the shifted problem there), so the printed
+        estimates agree with the reference only when that argument is an M^-1 K solver, as in the golden vectors.  The
+        result y does not depend on it."""
         if its < 0:
             its = self.kdim                                          # krylov_exp.py:66-67
         assert its <= self.kdim                                      # krylov_exp.py:68
