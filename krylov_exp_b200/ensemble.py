@@ -97,10 +97,12 @@ def partition_cost(terms, groups, latency_columns=6.4, forward_columns=6.8, cap=
 
 
 class SampleEnsemble:
-    def __init__(self, Mbar, rank=None, world=None, partition="block"):
-        """partition: "block" (contiguous sample blocks per rank) or "cyclic" (sample k on rank k mod world).
-        With the economised series the cost of a sample grows with |t_k|, and the sample times are ordered, so
-        "cyclic" gives every rank the same mix of short and long series (balanced max-over-ranks time)."""
+    def __init__(self, Mbar, rank=None, world=None, partition="block", terms=None):
+        """partition: "block" (contiguous sample blocks per rank), "cyclic" (sample k on rank k mod world) or "balanced"
+        (unequal shares by cost, balanced_partition; needs terms = cheby_exp.series_terms(t), the series length of every
+        sample).  With the economised series the cost of a sample grows with |t_k|, and the sample times are ordered, so
+        "cyclic" gives every rank the same mix of short and long series; "balanced" gives the rank with the longest series
+        fewer samples, which is faster when a rank holds only a few."""
         try:
             import torch.distributed as dist
             self._dist = dist if dist.is_available() and dist.is_initialized() else None
@@ -111,20 +113,30 @@ class SampleEnsemble:
         if world is None:
             world = self._dist.get_world_size() if self._dist else 1
         self.Mbar, self.rank, self.world = int(Mbar), int(rank), int(world)
-        if partition not in ("block", "cyclic"):
-            raise ValueError("partition must be 'block' or 'cyclic'")
+        if partition not in ("block", "cyclic", "balanced"):
+            raise ValueError("partition must be 'block', 'cyclic' or 'balanced'")
         self.partition = partition
         self.offsets = block_partition(self.Mbar, self.world)
+        self.groups = None
+        if partition == "balanced":
+            if terms is None or len(terms) != self.Mbar:
+                raise ValueError("partition='balanced' needs terms (one series length per sample, cheby_exp.series_terms)")
+            self.groups = balanced_partition(terms, self.world)
         self._lib_comm = None
 
     @property
     def local_slice(self):
+        """Index of this rank's samples: a slice ("block", "cyclic") or an index array ("balanced")."""
+        if self.partition == "balanced":
+            return self.groups[self.rank]
         if self.partition == "cyclic":
             return slice(self.rank, self.Mbar, self.world)
         return slice(int(self.offsets[self.rank]), int(self.offsets[self.rank + 1]))
 
     @property
     def n_local(self):
+        if self.partition == "balanced":
+            return int(len(self.groups[self.rank]))
         return len(range(*self.local_slice.indices(self.Mbar)))
 
     def local_times_weights(self, dt, rho):

@@ -53,3 +53,43 @@ def test_sharded_average_world2():
     assert sorted(o[0] for o in out) == [0, 1]
     assert all(o[1] < 1e-14 for o in out)
     assert sum(o[2] for o in out) == Mbar
+
+
+def _worker_balanced(rank, world, port, Mbar, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import krylov_exp_b200 as kx
+    t, w = kx.sample_times_weights(Mbar, 900.0, 1.0)
+    terms = 8 + np.round(17 * np.abs(t) / np.abs(t).max()).astype(int)      # series length grows with |t_k|
+    ens = kx.SampleEnsemble(Mbar, partition="balanced", terms=terms)
+    n = 23
+    rng = np.random.default_rng(5)
+    DU = rng.standard_normal((Mbar, n))
+    tl, wl = ens.local_times_weights(900.0, 1.0)
+    assert np.array_equal(tl, t[ens.local_slice]) and len(tl) == ens.n_local
+    v = wl @ DU[ens.local_slice]
+    ens.allreduce(v)
+    q.put((rank, float(np.abs(v - w @ DU).max()), ens.n_local, int(terms[ens.local_slice].max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_balanced_shares_world2():
+    """Unequal cost-balanced shares (SampleEnsemble(partition="balanced")): the all-reduced weighted sum is the single-process
+    one, every sample is held by exactly one rank, and the rank with the longest series does not hold more samples."""
+    world, Mbar = 2, 24
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_balanced, args=(r, world, port, Mbar, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(o[1] < 1e-14 for o in out)
+    assert sum(o[2] for o in out) == Mbar
+    long_rank = max(out, key=lambda o: o[3])
+    assert long_rank[2] <= min(o[2] for o in out)
