@@ -127,6 +127,16 @@ __device__ long long g_ntim_dummy;
 #define NTIM_T0
 #define NTIM_ADD(i)
 #endif
+// release side of the grid barrier: the CTA's writes (ordered before by bar.sync) must be visible before the arrive.  An
+// acquire-release fence is enough; __threadfence() is the sequentially consistent one (MEMBAR.SC.GPU).
+#ifndef KEXP_NARROW_FENCE_SC
+#define KEXP_NARROW_FENCE_SC 0
+#endif
+#if KEXP_NARROW_FENCE_SC
+#define KEXP_NARROW_FENCE() __threadfence()
+#else
+#define KEXP_NARROW_FENCE() asm volatile("fence.acq_rel.gpu;" ::: "memory")
+#endif
 __device__ __forceinline__ void narrow_barrier(cg::grid_group& grid, unsigned* counter, unsigned& target, long long* tim = nullptr) {
 #if KEXP_NARROW_SYNC
 #if KEXP_NARROW_TIMING
@@ -135,7 +145,7 @@ __device__ __forceinline__ void narrow_barrier(cg::grid_group& grid, unsigned* c
     if (threadIdx.x == 0) {
         long long c1 = clock64();
         target += gridDim.x;
-        __threadfence();
+        KEXP_NARROW_FENCE();
         long long c2 = clock64();
         atomicAdd(counter, 1u);
         while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
@@ -148,7 +158,7 @@ __device__ __forceinline__ void narrow_barrier(cg::grid_group& grid, unsigned* c
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
+        KEXP_NARROW_FENCE();
         atomicAdd(counter, 1u);
         while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
     }
@@ -892,6 +902,10 @@ cheb_apply_narrow_kernel(const int slot) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {           // (CTA 0 wrote them itself: program order)
         for (int k = 0; k < 4; ++k) a.pairs[k] = s_pairs[k];
     }
+#if KEXP_NARROW_TIMING == 2
+    if (threadIdx.x == 0) printf("NTIMA cta %3d A %lld barA %lld rows %d\n", (int)blockIdx.x, s_tim[4], s_tim[5],
+                                 (int)(a.kt2_cta_ptr[blockIdx.x + 1] - a.kt2_cta_ptr[blockIdx.x]));
+#endif
 #if KEXP_NARROW_TIMING
     if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
         printf("NTIM cta %3d W %d iters %lld | rows(own) %lld rows(halo) %lld | A %lld barA %lld start %lld | recv %lld iter %lld | red %lld barK %lld chk %lld C %lld barC %lld | n_own %d n_h1 %d\n",
